@@ -1,0 +1,88 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference, CPU)
+on the deterministic inputs of tests/kat.py.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, these vectors can.  What each file pins:
+  net_<case>.npz ....... DetectionModel forward (nn/tasks.py:138-165, nn/modules/*.py, head.py:64-131) on the seeded
+                         synthetic checkpoint of bs_yolo_b200.arch: decoded y and the three raw head maps
+  nms.npz .............. utils/ops.py:167-316 non_max_suppression (+ torchvision.ops.nms) on every tests/kat.py NMS case
+  letterbox.npz ........ data/augment.py:1535-1601 LetterBox (cv2.resize / copyMakeBorder)
+  predict_<case>.npz ... YOLO(ckpt).predict(list of ndarrays, device="cpu") end to end: Results.boxes.data per image
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import kat  # noqa: E402
+from bs_yolo_b200 import arch  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref_import.import_reference()
+    from ultralytics import YOLO
+    from ultralytics.data.augment import LetterBox
+    from ultralytics.utils import ops
+
+    torch.manual_seed(0)
+    # ---- network forward
+    for case, (model, *_rest) in kat.NET_CASES.items():
+        spec = arch.build_spec(model)
+        sd = arch.synth_state_dict(spec, 0)
+        m = ref_import.reference_model(model, sd)
+        x = torch.from_numpy(kat.net_input(case))
+        with torch.no_grad():
+            y, raws = m(x)
+        np.savez_compressed(os.path.join(OUT, f"net_{case}.npz"), y=y.numpy(), raw0=raws[0].numpy(), raw1=raws[1].numpy(),
+                            raw2=raws[2].numpy(), sd_checksum=np.float64(kat.state_dict_checksum(sd)))
+        print("net", case, tuple(y.shape))
+
+    # ---- NMS
+    nms = {}
+    for case in kat.NMS_CASES:
+        p, kw = kat.nms_case(case)
+        out = ops.non_max_suppression(torch.from_numpy(p.copy()), **kw)
+        nms[f"{case}__n"] = np.array([o.shape[0] for o in out], np.int64)
+        nms[f"{case}__rows"] = np.concatenate([o.numpy().reshape(-1, 6) for o in out], 0).astype(np.float32)
+        nms[f"{case}__insum"] = np.float64(p.astype(np.float64).sum())
+        print("nms", case, nms[f"{case}__n"].tolist())
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), **nms)
+
+    # ---- letterbox
+    lb = {}
+    for case, (h, w, imgsz, _seed) in kat.LETTERBOX_CASES.items():
+        img = kat.letterbox_input(case)
+        for auto in (False, True):
+            out = LetterBox((imgsz, imgsz), auto=auto, stride=32)(image=img)
+            lb[f"{case}__auto{int(auto)}"] = out
+        print("letterbox", case, out.shape)
+    np.savez_compressed(os.path.join(OUT, "letterbox.npz"), **lb)
+
+    # ---- end-to-end predict through the reference's public API and its own checkpoint loader
+    for case, (model, n, h, w, imgsz, seed) in kat.PREDICT_CASES.items():
+        spec = arch.build_spec(model)
+        sd = arch.synth_state_dict(spec, 0)
+        m = ref_import.reference_model(model, sd)
+        m.names = {k: f"class{k}" for k in range(spec["nc"])}
+        m.args = {"task": "detect", "imgsz": imgsz}
+        path = f"/tmp/b2y_golden_{case}.pt"
+        torch.save({"model": m, "ema": None, "train_args": {"task": "detect", "imgsz": imgsz}}, path)
+        yolo = YOLO(path)
+        res = yolo.predict(kat.predict_input(case), device="cpu", imgsz=imgsz, conf=0.25, iou=0.7, max_det=300, verbose=False)
+        d = {f"boxes{i}": r.boxes.data.numpy().astype(np.float32) for i, r in enumerate(res)}
+        d["n"] = np.array([r.boxes.data.shape[0] for r in res], np.int64)
+        np.savez_compressed(os.path.join(OUT, f"predict_{case}.npz"), **d)
+        print("predict", case, d["n"].tolist())
+
+
+if __name__ == "__main__":
+    main()

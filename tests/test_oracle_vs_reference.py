@@ -1,0 +1,49 @@
+"""In-process check of spec/IR/oracle against the live reference (build container only; skipped on the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from bs_yolo_b200 import arch, ir
+from oracle import oracle_net, oracle_post, ref_import
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present")
+
+
+@pytest.mark.parametrize("model", ["yolo11n", "bsyolo_n"])
+def test_spec_and_forward_match_live_reference(model):
+    spec = arch.build_spec(model)
+    sd = arch.synth_state_dict(spec, 3)
+    m = ref_import.reference_model(model, sd)  # strict load: parameter names/shapes identical to the reference's
+    assert ir.strip_tensors(ir.spec_from_model(m)) == ir.strip_tensors(spec)
+    g = ir.ir_from_model(m)
+    x = torch.rand(1, 3, 96, 64)
+    with torch.no_grad():
+        yr, rr = m(x)
+    y, raws = oracle_net.forward(g, x)
+    for a, b in zip(raws, rr):
+        assert float((a - b).norm() / b.norm()) < 1e-5
+    assert float((y - yr).abs().max()) < 2e-3
+
+
+def test_fused_reference_model_is_handled():
+    """model.fuse() removes .bn from the modules it recognises (tasks.py:200-228); the IR must be unchanged."""
+    spec = arch.build_spec("yolo11n")
+    m = ref_import.reference_model("yolo11n", arch.synth_state_dict(spec, 4))
+    g0 = ir.ir_from_model(m)
+    m.fuse(verbose=False)
+    g1 = ir.ir_from_model(m)
+    x = torch.rand(1, 3, 64, 64)
+    y0, _ = oracle_net.forward(g0, x)
+    y1, _ = oracle_net.forward(g1, x)
+    assert float((y0 - y1).abs().max()) < 1e-3
+
+
+def test_scale_boxes_matches_reference():
+    ref_import.import_reference()
+    from ultralytics.utils import ops
+
+    rng = np.random.default_rng(0)
+    b = (rng.random((50, 6)) * 700 - 30).astype(np.float32)
+    for s1, s0 in [((640, 640), (640, 640)), ((384, 640), (1080, 1920)), ((160, 128), (481, 321))]:
+        ref = ops.scale_boxes(s1, torch.from_numpy(b.copy()), s0).numpy()
+        assert np.array_equal(oracle_post.scale_boxes(s1, b, s0), ref)
