@@ -1,0 +1,118 @@
+// Internal helpers shared by the libb2y kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b2y.h"
+
+typedef __nv_bfloat16 bf16;
+
+void b2y_set_error(const char *fmt, ...);
+
+#define B2Y_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      b2y_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return B2Y_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define B2Y_LAUNCH_CHECK()                                                                          \
+  do {                                                                                              \
+    cudaError_t _e = cudaPeekAtLastError();                                                         \
+    if (_e != cudaSuccess) {                                                                        \
+      b2y_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return B2Y_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+#define B2Y_REQUIRE(cond, code, ...) \
+  do {                               \
+    if (!(cond)) {                   \
+      b2y_set_error(__VA_ARGS__);    \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// A strided NHWC view: element (b,h,w,c) lives at base[((b*H + h)*W + w)*cs + c].
+struct View {
+  void *base;   // already offset to the view's first channel
+  int cs;       // channels of the underlying buffer (pixel stride, elements)
+  int c;        // channels of the view
+  int dtype;    // b2y_dtype
+};
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void unpack8(const uint4 &v, float *f) {
+  const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float *f) {
+  uint4 v;
+  __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ void unpack4(const uint2 &v, float *f) {
+  const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+  float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float *f) {
+  uint2 v;
+  __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+  p[0] = __floats2bfloat162_rn(f[0], f[1]);
+  p[1] = __floats2bfloat162_rn(f[2], f[3]);
+  return v;
+}
+
+// ---- parameters of the convolution family (dense / depthwise / stem) -------------------------------------------
+struct ConvParams {
+  const bf16 *in; int in_cs;
+  void *out; int out_cs; int out_f32;
+  const bf16 *res; int res_cs; int res_mode;
+  const void *w;        // dense: bf16 [cout_pad][kh*kw*cin]; depthwise: fp32 [kh*kw][c]; stem: fp32 [cout][27]
+  const float *bias;    // fp32 [cout_pad]
+  int B, H, W, Ho, Wo, cin, cout, cout_pad;
+  int kh, kw, sh, sw, ph, pw, act;
+};
+
+// launchers (one per translation unit); all enqueue on `st` and return a b2y error code
+int launch_conv_simt(const ConvParams &p, cudaStream_t st);
+int launch_stem(const ConvParams &p, cudaStream_t st);
+int launch_dwconv(const ConvParams &p, cudaStream_t st);
+
+struct ConvTcPlan;  // opaque: tensor maps + geometry for one tcgen05 conv
+bool conv_tc_supported(const ConvParams &p, char *why, int why_len);
+int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out);
+void conv_tc_plan_destroy(ConvTcPlan *p);
+int launch_conv_tc(const ConvTcPlan *p, cudaStream_t st);
+
+int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, cudaStream_t st);
+int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, int scale,
+                    cudaStream_t st);
+int launch_attention(const bf16 *qkv, int qkv_cs, bf16 *out, int out_cs, int B, int N, int nh, int kd, int hd,
+                     cudaStream_t st);
+int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, float *rowm, float *colm, cudaStream_t st);
+int launch_ela_gate(const float *rowm, const float *colm, const float *params, int c, int B, int H, int W, int ks,
+                    int groups, float eps, float *hgate, float *wgate, float *chgate, cudaStream_t st);
+int launch_ela_apply(const bf16 *x, int cs, bf16 *out, int out_cs, int c, int B, int H, int W, const float *hgate,
+                     const float *wgate, const float *chgate, float ch_c, float sp_c, float res_c, cudaStream_t st);
+int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, float *gap, cudaStream_t st);
+int launch_msca_gate(const float *gap, const float *se_w, const float *se_b, int c, int B, float *gate,
+                     cudaStream_t st);
+int launch_wsum4(const bf16 *const *br, const int *br_cs, const float *gate, bf16 *out, int out_cs, int c, int B,
+                 int HW, cudaStream_t st);

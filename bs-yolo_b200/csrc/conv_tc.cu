@@ -1,0 +1,452 @@
+// Dense convolution as an implicit GEMM on the 5th-generation tensor cores (sm_100a):
+//   D[pixels, cout] = sum over taps (r,s) and channel chunks of  A_tap[pixels, BK] * W[cout, tap*cin + chunk]^T
+//
+//   * A operand: NHWC bf16 activations fetched by TMA straight out of the (possibly channel-sliced) activation
+//     buffer.  One box {BK channels, TW, TH, 1 image} per filter tap, shifted by the tap offset; out-of-bounds
+//     coordinates are zero-filled by the TMA unit, which *is* the "same" padding (conv.py:29-35 autopad).  No im2col
+//     buffer exists anywhere.  Stride-2 3x3 convs view the input as {2*Cs, W/2, 2, H/2, B} so that every tap is
+//     again a dense box (row/column parity selects the sub-lattice) -- no element strides, no gather.
+//   * B operand: BN-folded weights packed [cout_pad][kh*kw*cin] bf16 (K-major), one box {BK, BN} per k-step.
+//   * Both land in shared memory in the canonical K-major swizzled layout (128B/64B/32B swizzle chosen by BK) that
+//     tcgen05.mma consumes through shared-memory descriptors; accumulators (128 lanes x BN fp32 columns, double
+//     buffered) live in TMEM.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2..5 =
+//     epilogue (tcgen05.ld -> +bias -> SiLU -> residual add|mul -> bf16|fp32 -> global channel slice).  Three
+//     mbarrier pipelines: smem full/empty, TMEM full/empty.  Persistent CTAs walk the tile list.
+// Reference semantics: ultralytics/nn/modules/conv.py:145-151 (act(bn(conv(x))), BN folded per
+// utils/torch_utils.py:242-269), residuals of Bottleneck (block.py:3416-3419), PSABlock (:4379-4383), MSCA (:88).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kNumThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
+
+struct TcGeom {
+  int B, Ho, Wo, cin, cout, cout_pad;
+  int taps_w, taps;            // kw, kh*kw
+  int ph, pw;                  // padding (stride 1) ; for stride 2 fixed 3x3 p1
+  int stride2;                 // 0: 4-D map, 1: 5-D parity map
+  int in_cs;                   // needed for the parity offset in the merged (wp, c) dimension
+  int BK, nkc, kiters;         // channel chunk, chunks per tap, taps*nkc
+  int TH, TW, tiles_h, tiles_w, tiles_per_img;
+  int BN, n_ntiles;
+  long long ntiles;
+  int stages, a_bytes, b_bytes, tx_bytes;
+  int tmem_cols;
+  unsigned long long desc_hi;  // descriptor bits [32,64): SBO, version, layout type
+  unsigned idesc;
+  // epilogue
+  void *out; int out_cs, out_f32;
+  const bf16 *res; int res_cs, res_mode;
+  const float *bias;
+  int act, vec_ok;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const unsigned long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > kWaitTimeoutCycles) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_smem;
+
+  // dynamic smem base rounded up to 1024 B (swizzle atoms need it)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * kMaxStages]), tempty0 = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull0 + 8 * s, 1);
+      mbar_init(tempty0 + 8 * s, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const uint32_t stage_bytes = (uint32_t)(g.a_bytes + g.b_bytes);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        const int nt = (int)(tile % g.n_ntiles);
+        long long sp = tile / g.n_ntiles;
+        const int tw_i = (int)(sp % g.tiles_w);
+        sp /= g.tiles_w;
+        const int th_i = (int)(sp % g.tiles_h);
+        const int b = (int)(sp / g.tiles_h);
+        const int h0 = th_i * g.TH, w0 = tw_i * g.TW, n0 = nt * g.BN;
+        for (int kit = 0; kit < g.kiters; ++kit) {
+          const int tap = kit / g.nkc, c0 = (kit - tap * g.nkc) * g.BK;
+          const int r = tap / g.taps_w, s = tap - r * g.taps_w;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * stage_bytes, b_dst = a_dst + g.a_bytes;
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)g.tx_bytes);
+          if (!g.stride2) {
+            tma_load_4d(a_dst, &tmA, full0 + 8 * stage, c0, w0 + s - g.pw, h0 + r - g.ph, b);
+          } else {
+            const int wpar = (s == 1) ? 0 : 1, hpar = (r == 1) ? 0 : 1;
+            tma_load_5d(a_dst, &tmA, full0 + 8 * stage, wpar * g.in_cs + c0, w0 + (s == 0 ? -1 : 0), hpar,
+                        h0 + (r == 0 ? -1 : 0), b);
+          }
+          tma_load_2d(b_dst, &tmB, full0 + 8 * stage, kit * g.BK, n0);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * g.BN);
+      for (int kit = 0; kit < g.kiters; ++kit) {
+        mbar_wait(full0 + 8 * stage, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_base + stage * stage_bytes, b_addr = a_addr + g.a_bytes;
+          const uint64_t da = ((uint64_t)g.desc_hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+          const uint64_t db = ((uint64_t)g.desc_hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+          for (int k = 0; k < g.BK / 16; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), g.idesc, (kit | k) != 0);
+          umma_commit(empty0 + 8 * stage);                       // frees the smem slot when the MMAs retire
+          if (kit == g.kiters - 1) umma_commit(tfull0 + 8 * as);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quadrant warp % 4)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;  // accumulator row == pixel within the tile
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+      const int nt = (int)(tile % g.n_ntiles);
+      long long sp = tile / g.n_ntiles;
+      const int tw_i = (int)(sp % g.tiles_w);
+      sp /= g.tiles_w;
+      const int th_i = (int)(sp % g.tiles_h);
+      const int b = (int)(sp / g.tiles_h);
+      const int ho = th_i * g.TH + m / g.TW, wo = tw_i * g.TW + m % g.TW, n0 = nt * g.BN;
+      const bool valid = (m < g.TH * g.TW) && ho < g.Ho && wo < g.Wo;
+      const size_t pix = ((size_t)b * g.Ho + ho) * g.Wo + wo;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * g.BN);
+      for (int col = 0; col < g.BN; col += 16) {
+        float v[16];
+        tmem_ld16(taddr + col, v);  // warp-collective: executed by every lane, valid or not
+        const int n = n0 + col;
+        if (!valid || n >= g.cout) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = v[j] + __ldg(g.bias + min(n + j, g.cout_pad - 1));
+          v[j] = g.act ? silu_f(x) : x;
+        }
+        if (g.vec_ok && n + 16 <= g.cout) {
+          if (g.res_mode) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(g.res + pix * g.res_cs + n);
+            float r[16];
+            unpack8(rp[0], r);
+            unpack8(rp[1], r + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (g.res_mode == B2Y_RES_ADD) ? v[j] + r[j] : v[j] * r[j];
+          }
+          if (g.out_f32) {
+            float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.out) + pix * g.out_cs + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(g.out) + pix * g.out_cs + n);
+            op[0] = pack8(v);
+            op[1] = pack8(v + 8);
+          }
+        } else {
+          for (int j = 0; j < 16 && n + j < g.cout; ++j) {
+            float x = v[j];
+            if (g.res_mode) {
+              const float r = __bfloat162float(g.res[pix * g.res_cs + n + j]);
+              x = (g.res_mode == B2Y_RES_ADD) ? x + r : x * r;
+            }
+            if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + j] = x;
+            else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + j] = __float2bfloat16_rn(x);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tempty0 + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+struct ConvTcPlan {
+  CUtensorMap tmA, tmB;
+  TcGeom g;
+  int grid;
+  size_t smem;
+};
+
+bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
+  auto no = [&](const char *m) {
+    if (why) snprintf(why, why_len, "%s", m);
+    return false;
+  };
+  if (p.kh != p.kw) return no("non-square kernel");
+  const bool k1 = p.kh == 1 && p.sh == 1 && p.sw == 1 && p.ph == 0 && p.pw == 0;
+  const bool k3s1 = p.kh == 3 && p.sh == 1 && p.sw == 1 && p.ph == 1 && p.pw == 1;
+  const bool k3s2 = p.kh == 3 && p.sh == 2 && p.sw == 2 && p.ph == 1 && p.pw == 1 && p.H % 2 == 0 && p.W % 2 == 0;
+  if (!(k1 || k3s1 || k3s2)) return no("kernel/stride/padding combination");
+  if (p.cin % 16) return no("cin not a multiple of 16");
+  if (p.cout_pad % 16) return no("cout_pad not a multiple of 16");
+  if (p.in_cs % 8 || (reinterpret_cast<uintptr_t>(p.in) & 15)) return no("input view not 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(p.w) & 15) return no("weights not 16-byte aligned");
+  if (p.Wo > 65535 || p.Ho > 65535) return no("map too large");
+  return true;
+}
+
+int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
+  char why[128];
+  B2Y_REQUIRE(conv_tc_supported(p, why, sizeof(why)), B2Y_ERR_UNSUPPORTED, "tcgen05 conv: %s", why);
+  EncodeTiledFn encode = get_encode_fn();
+  B2Y_REQUIRE(encode != nullptr, B2Y_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  ConvTcPlan *pl = new ConvTcPlan();
+  TcGeom &g = pl->g;
+  g.B = p.B; g.Ho = p.Ho; g.Wo = p.Wo; g.cin = p.cin; g.cout = p.cout; g.cout_pad = p.cout_pad;
+  g.taps_w = p.kw; g.taps = p.kh * p.kw; g.ph = p.ph; g.pw = p.pw; g.stride2 = (p.sh == 2); g.in_cs = p.in_cs;
+  g.BK = (p.cin % 64 == 0) ? 64 : (p.cin % 32 == 0) ? 32 : 16;
+  g.nkc = p.cin / g.BK;
+  g.kiters = g.taps * g.nkc;
+  // spatial tile: TH x TW <= 128 output pixels, maximising useful rows per 128-row MMA
+  {
+    double best = -1.0;
+    int bth = 1, btw = 1;
+    for (int tw = 1; tw <= (p.Wo < 128 ? p.Wo : 128); ++tw) {
+      int th = 128 / tw;
+      if (th > p.Ho) th = p.Ho;
+      if (th < 1) continue;
+      const double eff = (double)p.Ho * p.Wo / ((double)ceil_div(p.Ho, th) * ceil_div(p.Wo, tw) * 128.0);
+      const double score = eff - 1e-4 * (tw > th ? tw - th : th - tw) / 128.0 + ((tw % 8 == 0) ? 1e-5 : 0.0);
+      if (score > best) { best = score; bth = th; btw = tw; }
+    }
+    g.TH = bth; g.TW = btw;
+  }
+  g.tiles_h = ceil_div(p.Ho, g.TH); g.tiles_w = ceil_div(p.Wo, g.TW);
+  g.tiles_per_img = g.tiles_h * g.tiles_w;
+  g.n_ntiles = ceil_div(p.cout_pad, 256);
+  g.BN = ceil_div(ceil_div(p.cout_pad, g.n_ntiles), 16) * 16;
+  g.ntiles = (long long)p.B * g.tiles_per_img * g.n_ntiles;
+  g.a_bytes = 128 * g.BK * 2;
+  g.b_bytes = ((g.BN * g.BK * 2) + 1023) / 1024 * 1024;
+  g.tx_bytes = g.TH * g.TW * g.BK * 2 + g.BN * g.BK * 2;
+  const int stage_bytes = g.a_bytes + g.b_bytes;
+  int stages = (176 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  g.stages = stages;
+  int cols = 32;
+  while (cols < 2 * g.BN) cols <<= 1;
+  g.tmem_cols = cols;
+  const int row_bytes = g.BK * 2;
+  const unsigned layout = (row_bytes == 128) ? 2u : (row_bytes == 64) ? 4u : 6u;  // UMMA LayoutType SW128/SW64/SW32
+  const unsigned sbo = (unsigned)(8 * row_bytes) >> 4;
+  g.desc_hi = (unsigned long long)sbo | (1ull << 14) | ((unsigned long long)layout << 29);  // bits [32,46) [46,48) [61,64)
+  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(g.BN >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  g.out = p.out; g.out_cs = p.out_cs; g.out_f32 = p.out_f32;
+  g.res = p.res; g.res_cs = p.res_cs; g.res_mode = p.res_mode;
+  g.bias = p.bias; g.act = p.act;
+  {
+    const uintptr_t o = reinterpret_cast<uintptr_t>(p.out);
+    bool ok = (o & 15) == 0 && (p.out_f32 ? (p.out_cs % 4 == 0) : (p.out_cs % 8 == 0));
+    if (p.res_mode) ok = ok && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (p.res_cs % 8 == 0);
+    g.vec_ok = ok ? 1 : 0;
+  }
+
+  const CUtensorMapSwizzle sw = (row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_32B;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r;
+  if (!g.stride2) {
+    const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.in_cs * 2, (cuuint64_t)p.W * p.in_cs * 2,
+                                   (cuuint64_t)p.H * p.W * p.in_cs * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)g.BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    r = encode(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16 *>(p.in), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[5] = {(cuuint64_t)p.in_cs + p.cin, (cuuint64_t)p.W / 2, 2, (cuuint64_t)p.H / 2,
+                                (cuuint64_t)p.B};
+    const cuuint64_t strides[4] = {(cuuint64_t)2 * p.in_cs * 2, (cuuint64_t)p.W * p.in_cs * 2,
+                                   (cuuint64_t)2 * p.W * p.in_cs * 2, (cuuint64_t)p.H * p.W * p.in_cs * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)g.BK, (cuuint32_t)g.TW, 1, (cuuint32_t)g.TH, 1};
+    r = encode(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16 *>(p.in), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    delete pl;
+    b2y_set_error("cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
+    return B2Y_ERR_CUDA;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)g.taps * p.cin, (cuuint64_t)p.cout_pad};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.taps * p.cin * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)g.BK, (cuuint32_t)g.BN};
+    r = encode(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(p.w), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    delete pl;
+    b2y_set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+    return B2Y_ERR_CUDA;
+  }
+  pl->smem = (size_t)stages * stage_bytes + 1024;
+  cudaDeviceProp prop;
+  B2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  const long long max_ctas = prop.multiProcessorCount;
+  pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  *out = pl;
+  return B2Y_OK;
+}
+
+void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
+
+int launch_conv_tc(const ConvTcPlan *pl, cudaStream_t st) {
+  conv_tc_kernel<<<pl->grid, kNumThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->g);
+  B2Y_LAUNCH_CHECK();
+  return B2Y_OK;
+}

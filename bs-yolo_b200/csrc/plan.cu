@@ -1,0 +1,318 @@
+// Plan object + C ABI glue: resolves the planner's op list (include/b2y.h) against caller-owned device memory,
+// builds TMA descriptors for the tcgen05 convolutions once, and replays the whole network either eagerly or as a
+// CUDA graph.  Replaces the reference's Python layer interpreter (ultralytics/nn/tasks.py:138-165).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void b2y_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *b2y_last_error(void) { return g_err; }
+extern "C" int b2y_abi_version(void) { return B2Y_ABI_VERSION; }
+
+int decode_launch(const void *const *raw, const int32_t *hs, const int32_t *ws, const float *strides, int32_t n_levels,
+                  int32_t B, int32_t nc, void *y, cudaStream_t st);
+
+struct ResolvedOp {
+  b2y_op op;
+  ConvParams cp;
+  ConvTcPlan *tc = nullptr;
+  int impl = 0;
+};
+
+struct b2y_plan {
+  std::vector<ResolvedOp> ops;
+  std::vector<b2y_buf> bufs;
+  char *ws = nullptr;
+  size_t ws_bytes = 0;
+  const char *wts = nullptr;
+  size_t wts_bytes = 0;
+  int B = 0, device = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+};
+
+namespace {
+inline size_t elem_size(int dtype) { return dtype == B2Y_F32 ? 4 : 2; }
+
+struct Resolver {
+  b2y_plan *pl;
+  bool ok = true;
+  const b2y_buf *buf(int i) {
+    if (i < 0 || i >= (int)pl->bufs.size()) {
+      b2y_set_error("op references buffer %d of %d", i, (int)pl->bufs.size());
+      ok = false;
+      return nullptr;
+    }
+    return &pl->bufs[i];
+  }
+  void *ptr(int i, int coff) {
+    const b2y_buf *b = buf(i);
+    if (!b) return nullptr;
+    return pl->ws + b->offset + (size_t)coff * elem_size(b->dtype);
+  }
+  const void *wptr(int64_t off) { return off < 0 ? nullptr : pl->wts + off; }
+};
+
+int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
+  Resolver R{pl};
+  const b2y_op &o = r.op;
+  const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+  if (!R.ok) return B2Y_ERR_INVALID;
+  ConvParams &c = r.cp;
+  c.in = reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0]));
+  c.in_cs = bi->C;
+  c.out = R.ptr(o.out, o.out_coff);
+  c.out_cs = bo->C;
+  c.out_f32 = (bo->dtype == B2Y_F32);
+  c.res = nullptr; c.res_cs = 0; c.res_mode = o.res_mode;
+  if (o.res_mode) {
+    const b2y_buf *br = R.buf(o.res);
+    if (!R.ok) return B2Y_ERR_INVALID;
+    B2Y_REQUIRE(br->dtype == B2Y_BF16 && br->H == bo->H && br->W == bo->W && o.res_coff + o.cout <= br->C,
+                B2Y_ERR_INVALID, "op %d: residual view does not match the output", idx);
+    c.res = reinterpret_cast<const bf16 *>(R.ptr(o.res, o.res_coff));
+    c.res_cs = br->C;
+  }
+  c.w = R.wptr(o.w_off);
+  c.bias = reinterpret_cast<const float *>(R.wptr(o.b_off));
+  c.B = pl->B; c.H = bi->H; c.W = bi->W; c.Ho = bo->H; c.Wo = bo->W;
+  c.cin = o.cin; c.cout = o.cout; c.cout_pad = o.cout_pad;
+  c.kh = o.kh; c.kw = o.kw; c.sh = o.sh; c.sw = o.sw; c.ph = o.ph; c.pw = o.pw; c.act = o.act;
+  B2Y_REQUIRE(bi->dtype == B2Y_BF16, B2Y_ERR_INVALID, "op %d: conv input must be bf16", idx);
+  B2Y_REQUIRE(c.w && c.bias, B2Y_ERR_INVALID, "op %d: conv needs weights and bias", idx);
+  B2Y_REQUIRE(o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C, B2Y_ERR_INVALID,
+              "op %d: channel view out of range", idx);
+  B2Y_REQUIRE(o.sh > 0 && o.sw > 0 && c.Ho == (c.H + 2 * c.ph - c.kh) / c.sh + 1 &&
+                  c.Wo == (c.W + 2 * c.pw - c.kw) / c.sw + 1,
+              B2Y_ERR_INVALID, "op %d: output map %dx%d inconsistent with input %dx%d k%dx%d s%d p%d", idx, c.Ho, c.Wo,
+              c.H, c.W, c.kh, c.kw, c.sh, c.ph);
+  return B2Y_OK;
+}
+
+int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
+  Resolver R{pl};
+  const b2y_op &o = r.op;
+  switch (o.kind) {
+    case B2Y_OP_CONV:
+      return r.impl == B2Y_IMPL_TCGEN05 ? launch_conv_tc(r.tc, st) : launch_conv_simt(r.cp, st);
+    case B2Y_OP_DWCONV:
+      return launch_dwconv(r.cp, st);
+    case B2Y_OP_STEM:
+      return launch_stem(r.cp, st);
+    case B2Y_OP_SPPF_POOL: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      return launch_sppf_pool(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C,
+                              reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)), bo->C, o.cin, pl->B, bi->H, bi->W, st);
+    }
+    case B2Y_OP_RESAMPLE: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      B2Y_REQUIRE(bo->H == bi->H * o.ip[0] && bo->W == bi->W * o.ip[0], B2Y_ERR_INVALID, "op %d: resample dims", idx);
+      return launch_resample(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C,
+                             reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)), bo->C, o.cin, pl->B, bo->H, bo->W,
+                             o.ip[0], st);
+    }
+    case B2Y_OP_ATTN: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      return launch_attention(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C,
+                              reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)), bo->C, pl->B, bi->H * bi->W, o.ip[0],
+                              o.ip[1], o.ip[2], st);
+    }
+    case B2Y_OP_ROWCOL_MEAN: {
+      const b2y_buf *bi = R.buf(o.in[0]);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      return launch_rowcol_mean(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C, o.cin, pl->B,
+                                bi->H, bi->W, reinterpret_cast<float *>(R.ptr(o.out, 0)),
+                                reinterpret_cast<float *>(R.ptr(o.in[1], 0)), st);
+    }
+    case B2Y_OP_ELA_GATE:
+      return launch_ela_gate(reinterpret_cast<const float *>(R.ptr(o.in[0], 0)),
+                             reinterpret_cast<const float *>(R.ptr(o.in[1], 0)),
+                             reinterpret_cast<const float *>(R.wptr(o.p_off[0])), o.cin, pl->B, o.ip[2], o.ip[3],
+                             o.ip[0], o.ip[1], o.fp[0], reinterpret_cast<float *>(R.ptr(o.out, 0)),
+                             reinterpret_cast<float *>(R.ptr(o.in[2], 0)), reinterpret_cast<float *>(R.ptr(o.in[3], 0)),
+                             st);
+    case B2Y_OP_ELA_APPLY: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      return launch_ela_apply(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C,
+                              reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)), bo->C, o.cin, pl->B, bi->H, bi->W,
+                              reinterpret_cast<const float *>(R.ptr(o.in[1], 0)),
+                              reinterpret_cast<const float *>(R.ptr(o.in[2], 0)),
+                              reinterpret_cast<const float *>(R.ptr(o.in[3], 0)), o.fp[0], o.fp[1], o.fp[2], st);
+    }
+    case B2Y_OP_GAP4:
+    case B2Y_OP_WSUM4: {
+      const bf16 *br[4];
+      int cs[4];
+      int HW = 0;
+      for (int j = 0; j < 4; ++j) {
+        const b2y_buf *b = R.buf(o.in[j]);
+        if (!R.ok) return B2Y_ERR_INVALID;
+        br[j] = reinterpret_cast<const bf16 *>(R.ptr(o.in[j], o.in_coff[j]));
+        cs[j] = b->C;
+        HW = b->H * b->W;
+      }
+      if (o.kind == B2Y_OP_GAP4)
+        return launch_gap4(br, cs, o.cin, pl->B, HW, reinterpret_cast<float *>(R.ptr(o.out, 0)), st);
+      const b2y_buf *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      return launch_wsum4(br, cs, reinterpret_cast<const float *>(R.ptr(o.res, 0)),
+                          reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)), bo->C, o.cin, pl->B, HW, st);
+    }
+    case B2Y_OP_MSCA_GATE:
+      return launch_msca_gate(reinterpret_cast<const float *>(R.ptr(o.in[0], 0)),
+                              reinterpret_cast<const float *>(R.wptr(o.p_off[0])),
+                              reinterpret_cast<const float *>(R.wptr(o.p_off[1])), o.cin, pl->B,
+                              reinterpret_cast<float *>(R.ptr(o.out, 0)), st);
+    case B2Y_OP_DECODE: {
+      const void *raw[4];
+      int32_t hs[4], wsz[4];
+      float strides[4];
+      const int nl = o.ip[1];
+      B2Y_REQUIRE(nl >= 1 && nl <= 4, B2Y_ERR_INVALID, "op %d: decode levels", idx);
+      for (int l = 0; l < nl; ++l) {
+        const b2y_buf *b = R.buf(o.in[l]);
+        if (!R.ok) return B2Y_ERR_INVALID;
+        B2Y_REQUIRE(b->dtype == B2Y_F32 && b->C == 64 + o.ip[0], B2Y_ERR_INVALID, "op %d: head map %d layout", idx, l);
+        raw[l] = R.ptr(o.in[l], 0);
+        hs[l] = b->H;
+        wsz[l] = b->W;
+        strides[l] = o.fp[l];
+      }
+      return decode_launch(raw, hs, wsz, strides, nl, pl->B, o.ip[0], R.ptr(o.out, 0), st);
+    }
+    default:
+      b2y_set_error("op %d: unknown kind %d", idx, o.kind);
+      return B2Y_ERR_UNSUPPORTED;
+  }
+}
+}  // namespace
+
+extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *bufs, int32_t n_bufs, void *workspace,
+                               size_t workspace_bytes, const void *weights, size_t weights_bytes, int32_t batch,
+                               int32_t device, b2y_plan **out) {
+  B2Y_REQUIRE(ops && bufs && workspace && out && n_ops > 0 && n_bufs > 0 && batch > 0, B2Y_ERR_INVALID,
+              "plan_create: bad arguments");
+  B2Y_CUDA_CHECK(cudaSetDevice(device));
+  b2y_plan *pl = new b2y_plan();
+  pl->ws = reinterpret_cast<char *>(workspace);
+  pl->ws_bytes = workspace_bytes;
+  pl->wts = reinterpret_cast<const char *>(weights);
+  pl->wts_bytes = weights_bytes;
+  pl->B = batch;
+  pl->device = device;
+  pl->bufs.assign(bufs, bufs + n_bufs);
+  for (int i = 0; i < n_bufs; ++i) {
+    const b2y_buf &b = bufs[i];
+    const size_t bytes = (size_t)batch * b.H * b.W * b.C * elem_size(b.dtype);
+    if (b.offset < 0 || (b.offset & 255) || (size_t)b.offset + bytes > workspace_bytes) {
+      b2y_set_error("buffer %d (offset %lld, %zu bytes) does not fit the %zu-byte workspace", i, (long long)b.offset,
+                    bytes, workspace_bytes);
+      delete pl;
+      return B2Y_ERR_NOMEM;
+    }
+  }
+  const char *force = getenv("B2Y_FORCE_SIMT");
+  const bool force_simt = force && force[0] == '1';
+  pl->ops.resize(n_ops);
+  int rc = B2Y_OK;
+  for (int i = 0; i < n_ops && rc == B2Y_OK; ++i) {
+    ResolvedOp &r = pl->ops[i];
+    r.op = ops[i];
+    const int k = r.op.kind;
+    if (k == B2Y_OP_CONV || k == B2Y_OP_DWCONV || k == B2Y_OP_STEM) {
+      rc = resolve_conv(pl, r, i);
+      if (rc != B2Y_OK) break;
+      if (k == B2Y_OP_CONV) {
+        char why[128] = "";
+        const bool can_tc = conv_tc_supported(r.cp, why, sizeof(why));
+        int impl = r.op.impl;
+        if (impl == B2Y_IMPL_AUTO) impl = (can_tc && !force_simt) ? B2Y_IMPL_TCGEN05 : B2Y_IMPL_SIMT;
+        if (impl == B2Y_IMPL_TCGEN05) {
+          if (!can_tc) {
+            b2y_set_error("op %d: tcgen05 conv requested but unsupported: %s", i, why);
+            rc = B2Y_ERR_UNSUPPORTED;
+            break;
+          }
+          rc = conv_tc_plan_create(r.cp, device, &r.tc);
+        }
+        r.impl = impl;
+      }
+    }
+  }
+  if (rc != B2Y_OK) {
+    b2y_plan_destroy(pl);
+    return rc;
+  }
+  *out = pl;
+  return B2Y_OK;
+}
+
+extern "C" int b2y_plan_destroy(b2y_plan *pl) {
+  if (!pl) return B2Y_OK;
+  for (auto &r : pl->ops)
+    if (r.tc) conv_tc_plan_destroy(r.tc);
+  if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
+  if (pl->graph) cudaGraphDestroy(pl->graph);
+  delete pl;
+  return B2Y_OK;
+}
+
+extern "C" int b2y_plan_run(b2y_plan *pl, int32_t first, int32_t last, void *stream) {
+  B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "plan_run: null plan");
+  const int n = (int)pl->ops.size();
+  if (last < 0 || last > n) last = n;
+  B2Y_REQUIRE(first >= 0 && first <= last, B2Y_ERR_INVALID, "plan_run: bad op range [%d,%d)", first, last);
+  for (int i = first; i < last; ++i) {
+    const int rc = run_op(pl, pl->ops[i], i, (cudaStream_t)stream);
+    if (rc != B2Y_OK) return rc;
+  }
+  return B2Y_OK;
+}
+
+extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
+  B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "graph_build: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
+  if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
+  B2Y_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = b2y_plan_run(pl, 0, -1, stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  if (rc != B2Y_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  B2Y_CUDA_CHECK(e);
+  pl->graph = g;
+  B2Y_CUDA_CHECK(cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
+  return B2Y_OK;
+}
+
+extern "C" int b2y_plan_graph_launch(b2y_plan *pl, void *stream) {
+  B2Y_REQUIRE(pl && pl->graph_exec, B2Y_ERR_INVALID, "graph_launch: graph not built");
+  B2Y_CUDA_CHECK(cudaGraphLaunch(pl->graph_exec, (cudaStream_t)stream));
+  return B2Y_OK;
+}
+
+extern "C" int b2y_plan_num_launches(const b2y_plan *pl) { return pl ? (int)pl->ops.size() : 0; }
+
+extern "C" int b2y_plan_op_impl(const b2y_plan *pl, int32_t i) {
+  if (!pl || i < 0 || i >= (int)pl->ops.size()) return -1;
+  return pl->ops[i].impl;
+}

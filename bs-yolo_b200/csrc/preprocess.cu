@@ -1,0 +1,87 @@
+// Fused letterbox + BGR->RGB + HWC->(NHWC|NCHW) + /255 preprocess.
+// Reference: LetterBox.__call__ (ultralytics/data/augment.py:1535-1601: resize INTER_LINEAR :1586, border 114 :1589-1591)
+// and BasePredictor.preprocess (ultralytics/engine/predictor.py:116-134: [..., ::-1], transpose, /255).
+// The resize reproduces OpenCV's uint8 INTER_LINEAR bit-for-bit for down-scaling (11-bit fixed-point coefficients,
+// integer two-pass blend; SURVEY §8 "a1 fine print"); identity when the source already has the unpadded size.
+#include "common.cuh"
+
+namespace {
+struct PreParams {
+  const uint8_t *src;
+  void *dst;
+  int B, h, w, H, W, top, left, uh, uw, fmt, resize;
+  double scale_x, scale_y;
+};
+
+__device__ __forceinline__ void axis_coeff(int d, double scale, int src, int &s, int &a0, int &a1) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) { s = 0; f = 0.f; }
+  if (s >= src - 1) { s = src - 1; f = 0.f; }
+  a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  a0 = 2048 - a1;
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
+  const long long total = (long long)p.B * p.H * p.W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % p.W);
+  const int y = (int)((idx / p.W) % p.H);
+  const int b = (int)(idx / ((long long)p.W * p.H));
+  int bgr[3] = {114, 114, 114};
+  const int ux = x - p.left, uy = y - p.top;
+  if (ux >= 0 && ux < p.uw && uy >= 0 && uy < p.uh) {
+    const uint8_t *img = p.src + (size_t)b * p.h * p.w * 3;
+    if (!p.resize) {
+      const uint8_t *s = img + ((size_t)uy * p.w + ux) * 3;
+      bgr[0] = s[0]; bgr[1] = s[1]; bgr[2] = s[2];
+    } else {
+      int sx, xa0, xa1, sy, ya0, ya1;
+      axis_coeff(ux, p.scale_x, p.w, sx, xa0, xa1);
+      axis_coeff(uy, p.scale_y, p.h, sy, ya0, ya1);
+      const int sx1 = min(sx + 1, p.w - 1), sy1 = min(sy + 1, p.h - 1);
+      const uint8_t *r0 = img + (size_t)sy * p.w * 3, *r1 = img + (size_t)sy1 * p.w * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[sx * 3 + c] * xa0 + r0[sx1 * 3 + c] * xa1;
+        const int h1 = r1[sx * 3 + c] * xa0 + r1[sx1 * 3 + c] * xa1;
+        bgr[c] = (((ya0 * (h0 >> 4)) >> 16) + ((ya1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      }
+    }
+  }
+  if (p.fmt == 0) {
+    float f[4] = {__fdiv_rn((float)bgr[2], 255.f), __fdiv_rn((float)bgr[1], 255.f), __fdiv_rn((float)bgr[0], 255.f), 0.f};
+    reinterpret_cast<uint2 *>(p.dst)[idx] = pack4(f);
+  } else if (p.fmt == 1) {
+    float *o = reinterpret_cast<float *>(p.dst) + (size_t)b * 3 * p.H * p.W + (size_t)y * p.W + x;
+    const size_t plane = (size_t)p.H * p.W;
+    o[0] = __fdiv_rn((float)bgr[2], 255.f);
+    o[plane] = __fdiv_rn((float)bgr[1], 255.f);
+    o[2 * plane] = __fdiv_rn((float)bgr[0], 255.f);
+  } else {
+    uint8_t *o = reinterpret_cast<uint8_t *>(p.dst) + (size_t)idx * 3;
+    o[0] = (uint8_t)bgr[0]; o[1] = (uint8_t)bgr[1]; o[2] = (uint8_t)bgr[2];
+  }
+}
+}  // namespace
+
+extern "C" int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, void *dst, int32_t H, int32_t W,
+                              int32_t top, int32_t left, int32_t uh, int32_t uw, int32_t dst_format, void *stream) {
+  B2Y_REQUIRE(src && dst && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, B2Y_ERR_INVALID, "preprocess: bad arguments");
+  B2Y_REQUIRE(top >= 0 && left >= 0 && top + uh <= H && left + uw <= W && uh > 0 && uw > 0, B2Y_ERR_INVALID,
+              "preprocess: letterbox geometry (%d,%d,%dx%d) does not fit %dx%d", top, left, uh, uw, H, W);
+  B2Y_REQUIRE(dst_format >= 0 && dst_format <= 2, B2Y_ERR_INVALID, "preprocess: unknown dst_format %d", dst_format);
+  PreParams p;
+  p.src = reinterpret_cast<const uint8_t *>(src);
+  p.dst = dst;
+  p.B = B; p.h = h; p.w = w; p.H = H; p.W = W; p.top = top; p.left = left; p.uh = uh; p.uw = uw; p.fmt = dst_format;
+  p.resize = !(uh == h && uw == w);
+  p.scale_x = 1.0 / ((double)uw / (double)w);
+  p.scale_y = 1.0 / ((double)uh / (double)h);
+  const long long total = (long long)B * H * W;
+  preprocess_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  B2Y_LAUNCH_CHECK();
+  return B2Y_OK;
+}

@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference's tensor utilities for the detect path, backed by the CUDA kernels.
+
+Same names, argument meaning and error behaviour as ultralytics/utils/ops.py so parity tests read like the
+reference's own (`test_utils_ops`, tests/test_python.py:412-438):
+  non_max_suppression  <- ultralytics/utils/ops.py:167-316   (one C-ABI call: b2y_nms)
+  scale_boxes          <- ultralytics/utils/ops.py:92-127
+  letterbox/preprocess <- ultralytics/data/augment.py:1535-1601, engine/predictor.py:116-134 (b2y_preprocess)
+There is no CPU fallback: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi as A
+from .engine import letterbox_geometry
+
+_ws_cache: dict = {}
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _workspace(dev, nbytes: int) -> torch.Tensor:
+    key = (dev.index,)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = t
+    return t
+
+
+def nms_raw(pred: torch.Tensor, conf=0.25, iou=0.7, max_det=300, classes=None, agnostic=False, multi_label=False,
+            max_nms=30000, max_wh=7680.0, return_anchors=False):
+    """pred (B, 4+nc, A) fp32 CUDA -> dets (B, max_det, 6) fp32, counts (B,) int32 [, kept anchor index (B, max_det)]."""
+    if not pred.is_cuda:
+        raise A.B2YError("non_max_suppression: CUDA tensor required (no CPU fallback on the B200 path)")
+    if pred.dtype != torch.float32:
+        raise TypeError("non_max_suppression: prediction must be float32")
+    pred = pred.contiguous()
+    B, ch, An = pred.shape
+    nc = ch - 4
+    L = A.lib()
+    nbytes = L.b2y_nms_workspace_bytes(B, nc, An, int(bool(multi_label)), max_nms)
+    ws = _workspace(pred.device, nbytes)
+    dets = torch.zeros(B, max_det, 6, dtype=torch.float32, device=pred.device)
+    counts = torch.zeros(B, dtype=torch.int32, device=pred.device)
+    anchors = torch.zeros(B, max_det, dtype=torch.int32, device=pred.device) if return_anchors else None
+    if classes is not None:
+        cl = (C.c_int32 * len(classes))(*[int(c) for c in classes])
+        ncl = len(classes)
+    else:
+        cl, ncl = None, 0
+    A.check(L.b2y_nms(pred.data_ptr(), B, nc, An, float(conf), float(iou), int(max_det), int(max_nms), float(max_wh),
+                      int(bool(agnostic)), int(bool(multi_label)), cl, ncl, ws.data_ptr(), ws.numel(), dets.data_ptr(),
+                      counts.data_ptr(), anchors.data_ptr() if anchors is not None else None, _stream(pred.device)))
+    return (dets, counts, anchors) if return_anchors else (dets, counts)
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                        labels=(), max_det=300, nc=0, max_time_img=0.05, max_nms=30000, max_wh=7680, in_place=True,
+                        rotated=False):
+    """Drop-in for ultralytics.utils.ops.non_max_suppression (ops.py:167-316) on CUDA tensors; returns a list of
+    (n_i, 6) tensors [x1, y1, x2, y2, conf, cls], bit-identical rows in the same order.
+
+    Documented deviations: the input is never modified (the reference mutates it when in_place, ops.py:244) and there
+    is no wall-clock abort (ops.py:312-314, `max_time_img` is ignored)."""
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    if isinstance(prediction, (list, tuple)):
+        prediction = prediction[0]
+    if rotated or (labels is not None and len(labels)):
+        raise NotImplementedError("rotated boxes / apriori labels are not on the B200 detect path")
+    if prediction.shape[-1] == 6:
+        raise NotImplementedError("end-to-end (B,N,6) predictions are not on the B200 detect path")
+    nc = nc or (prediction.shape[1] - 4)
+    if prediction.shape[1] - nc - 4 != 0:
+        raise NotImplementedError("mask coefficients (segment models) are not on the B200 detect path")
+    dets, counts = nms_raw(prediction, conf_thres, iou_thres, max_det, classes, agnostic, multi_label, max_nms,
+                           float(max_wh))
+    n = counts.tolist()  # the one device->host sync of the post-process
+    return [dets[i, : n[i]] for i in range(len(n))]
+
+
+def _as_device_batch(images, device) -> torch.Tensor:
+    if isinstance(images, torch.Tensor):
+        t = images
+    else:
+        if len({im.shape for im in images}) != 1:
+            raise ValueError("all images of a batch must share one shape on the B200 path (shard ragged batches by shape)")
+        t = torch.from_numpy(np.ascontiguousarray(np.stack(images)))
+    if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+        raise TypeError("expected uint8 images of shape (B, h, w, 3) in BGR order")
+    return t.to(device, non_blocking=True).contiguous()
+
+
+def _letterbox_call(images, imgsz, auto, stride, device, fmt):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise A.B2YError("preprocess: CUDA device required (no CPU fallback on the B200 path)")
+    src = _as_device_batch(images, device)
+    B, h, w = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+    imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+    H, W, top, left, uh, uw = letterbox_geometry((h, w), imgsz, auto, stride)
+    if fmt == 1:
+        dst = torch.empty(B, 3, H, W, dtype=torch.float32, device=device)
+    elif fmt == 2:
+        dst = torch.empty(B, H, W, 3, dtype=torch.uint8, device=device)
+    else:
+        dst = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=device)
+    A.check(A.lib().b2y_preprocess(src.data_ptr(), B, h, w, dst.data_ptr(), H, W, top, left, uh, uw, fmt, _stream(device)))
+    return dst
+
+
+def letterbox(images, imgsz=640, auto=False, stride=32, device="cuda"):
+    """LetterBox(imgsz, auto, stride)(image=...) for a same-shape batch: uint8 (B,h,w,3) -> uint8 (B,H',W',3)."""
+    return _letterbox_call(images, imgsz, auto, stride, device, 2)
+
+
+def preprocess(images, imgsz=640, auto=True, stride=32, device="cuda"):
+    """BasePredictor.preprocess for a same-shape batch of uint8 BGR images: -> (B,3,H',W') fp32 RGB in [0,1]."""
+    return _letterbox_call(images, imgsz, auto, stride, device, 1)
+
+
+def scale_boxes_batched(dets: torch.Tensor, counts: torch.Tensor, img1_shape, img0_shapes):
+    """scale_boxes + clip_boxes (ops.py:92-127, 319-338) in place on padded dets (B, max_det, 6)."""
+    B, max_det, _ = dets.shape
+    geom = []
+    for (h0, w0) in img0_shapes:
+        gain = min(img1_shape[0] / h0, img1_shape[1] / w0)
+        padx = round((img1_shape[1] - w0 * gain) / 2 - 0.1)
+        pady = round((img1_shape[0] - h0 * gain) / 2 - 0.1)
+        geom.append([gain, padx, pady, w0, h0])
+    g = torch.tensor(geom, dtype=torch.float32).to(dets.device, non_blocking=True)
+    A.check(A.lib().b2y_scale_boxes(dets.data_ptr(), counts.data_ptr(), g.data_ptr(), B, max_det, _stream(dets.device)))
+    return dets

@@ -1,0 +1,493 @@
+"""Planner: lowers the graph IR (ir.build_ir) to the flat op list of include/b2y.h.
+
+Design (B200-first, not a layer-by-layer translation of the reference's Python interpreter,
+ultralytics/nn/tasks.py:138-165):
+  * activations are NHWC bf16; every tensor operand is a *channel-slice view* of a buffer, so all the
+    reference's torch.cat / chunk / split calls (C2f block.py:3308-3310, C3 :3334, SPPF :3149, C2PSA :4466-4468,
+    Concat conv.py:455, Detect head.py:70) cost nothing: producers write straight into their slice of the concat
+    buffer and consumers read slices through strided TMA descriptors;
+  * BatchNorm is already folded (ir.py); bias + SiLU + residual add/mul happen in the conv epilogue;
+  * the Detect output convs emit fp32 so DFL / dist2bbox / sigmoid run in fp32 (decode.cu);
+  * hidden channel counts that are not a multiple of 16 (the 8-channel Bottleneck of yolo11n layer 2) are
+    zero-padded to 16 so the tensor-core path takes them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _cabi as A
+
+Node = dict[str, Any]
+
+
+@dataclass(frozen=True)
+class View:
+    buf: int
+    coff: int
+    c: int      # channels physically covered by the view (incl. zero padding)
+    H: int
+    W: int
+    creal: int = -1  # logical channels (<= c); -1: == c
+
+    @property
+    def real(self) -> int:
+        return self.c if self.creal < 0 else self.creal
+
+
+@dataclass
+class BufSpec:
+    C: int
+    H: int
+    W: int
+    dtype: int = A.BF16
+    name: str = ""
+    offset: int = 0  # bytes per batch element are H*W*C*elem; absolute offsets assigned by Plan.layout(B)
+
+    def elems(self) -> int:
+        return self.C * self.H * self.W
+
+
+@dataclass
+class OpSpec:
+    kind: int
+    name: str = ""
+    ins: list = field(default_factory=list)   # list[View|int buffer id]
+    out: Any = None
+    res: Any = None
+    res_mode: int = A.RES_NONE
+    cin: int = 0
+    cout: int = 0
+    cout_pad: int = 0
+    k: tuple = (1, 1)
+    s: tuple = (1, 1)
+    p: tuple = (0, 0)
+    act: int = 0
+    impl: int = A.IMPL_AUTO
+    w_off: int = -1
+    b_off: int = -1
+    p_off: tuple = (-1, -1, -1, -1)
+    ip: tuple = ()
+    fp: tuple = ()
+    flops: int = 0        # 2*MAC, per image
+    bytes_alg: int = 0    # algorithmic bytes (in + out + weights), per image (weights counted once)
+    w_fp32: Any = None    # tests only (Plan(keep_fp32=True))
+
+
+def _r(v, m):
+    return (v + m - 1) // m * m
+
+
+class WeightBlob:
+    def __init__(self):
+        self.parts: list[tuple[int, np.ndarray]] = []
+        self.size = 0
+
+    def add(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr)
+        off = _r(self.size, 256)
+        self.parts.append((off, arr))
+        self.size = off + arr.nbytes
+        return off
+
+    def tobytes(self) -> bytes:
+        out = bytearray(_r(self.size, 256))
+        for off, arr in self.parts:
+            out[off:off + arr.nbytes] = arr.tobytes()
+        return bytes(out)
+
+
+def _bf16_bits(t: torch.Tensor) -> np.ndarray:
+    return t.to(torch.bfloat16).contiguous().view(torch.int16).numpy()
+
+
+class Plan:
+    """Flat op list + buffers + packed weights for one (H, W) input size (batch is bound later)."""
+
+    def __init__(self, ir: Node, H: int, W: int, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False):
+        if H % 32 or W % 32:
+            raise ValueError(f"input {H}x{W} must be a multiple of the max stride 32 (utils/checks.py:120-171)")
+        self.ir, self.H, self.W = ir, H, W
+        self.conv_impl = conv_impl
+        self.keep_fp32 = keep_fp32  # tests only: keep unrounded packed conv weights next to the bf16 blob
+        self.bufs: list[BufSpec] = []
+        self.ops: list[OpSpec] = []
+        self.blob = WeightBlob()
+        self.nc = ir["nc"]
+        self.layer_out: dict[int, View] = {}
+        self.layer_op_range: dict[int, tuple[int, int]] = {}
+        self.input_buf = self.new_buf(4, H, W, name="input_rgb0")
+        self.head_bufs: list[int] = []
+        self.y_buf = -1
+        self.A = 0
+        self._lower()
+
+    # ------------------------------------------------------------------ buffers / views
+    def new_buf(self, C, H, W, dtype=A.BF16, name="") -> int:
+        self.bufs.append(BufSpec(_r(C, 8) if dtype == A.BF16 else C, H, W, dtype, name))
+        return len(self.bufs) - 1
+
+    def full(self, buf: int, c: int | None = None) -> View:
+        b = self.bufs[buf]
+        return View(buf, 0, b.C if c is None else c, b.H, b.W)
+
+    @staticmethod
+    def sub(v: View, coff: int, c: int) -> View:
+        assert coff + c <= v.c
+        return View(v.buf, v.coff + coff, c, v.H, v.W)
+
+    # ------------------------------------------------------------------ conv family
+    def conv(self, n: Node, x: View, dest: View | None = None, res: View | None = None, res_mode=A.RES_NONE,
+             out_dtype=A.BF16, pad16=False, wb=None) -> View:
+        """Conv / DWConv node -> one op. ``wb``: optional (weight, bias) override (used for folded variants)."""
+        w, b = wb if wb is not None else (n["weight"], n["bias"])
+        c1, c2, (kh, kw), (sh, sw), (ph, pw), g = n["c1"], n["c2"], n["k"], n["s"], n["p"], n["g"]
+        assert x.real == c1, (n["name"], x, c1)
+        Ho, Wo = (x.H + 2 * ph - kh) // sh + 1, (x.W + 2 * pw - kw) // sw + 1
+        act = 1 if n["act"] == "silu" else 0
+        if g == 1:
+            cpad = _r(c2, 16)
+            cstore = cpad if (pad16 and dest is None) else c2
+            if dest is None:
+                dest = self.full(self.new_buf(cstore, Ho, Wo, out_dtype, n["name"]), cstore)
+                if cstore != c2:
+                    dest = View(dest.buf, 0, cstore, Ho, Wo, creal=c2)
+            assert dest.c == cstore and (dest.H, dest.W) == (Ho, Wo), (n["name"], dest, cstore, Ho, Wo)
+            wp = torch.zeros(cpad, kh * kw, x.c)
+            wp[:c2, :, :c1] = w.permute(0, 2, 3, 1).reshape(c2, kh * kw, c1)
+            bp = torch.zeros(cpad)
+            bp[:c2] = b
+            op = OpSpec(A.OP_CONV, n["name"], [x], dest, res, res_mode, x.c, cstore, cpad, (kh, kw), (sh, sw), (ph, pw),
+                        act, self.conv_impl, self.blob.add(_bf16_bits(wp.reshape(cpad, -1))),
+                        self.blob.add(bp.numpy().astype(np.float32)))
+            if self.keep_fp32:
+                op.w_fp32 = wp.reshape(cpad, -1).clone()
+            op.flops = 2 * c2 * c1 * kh * kw * Ho * Wo
+            esz = 4 if out_dtype == A.F32 else 2
+            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * esz + c2 * c1 * kh * kw * 2
+        else:
+            assert g == c1 == c2, f"{n['name']}: only depthwise grouped convs are on the hot path"
+            if dest is None:
+                dest = self.full(self.new_buf(c2, Ho, Wo, name=n["name"]), c2)
+            assert dest.c == c2 and (dest.H, dest.W) == (Ho, Wo)
+            wp = w.reshape(c2, kh * kw).t().contiguous()  # [kh*kw][C]
+            op = OpSpec(A.OP_DWCONV, n["name"], [x], dest, res, res_mode, c1, c2, c2, (kh, kw), (sh, sw), (ph, pw), act,
+                        A.IMPL_SIMT, self.blob.add(wp.numpy().astype(np.float32)),
+                        self.blob.add(b.numpy().astype(np.float32)))
+            op.flops = 2 * c2 * kh * kw * Ho * Wo
+            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + c2 * kh * kw * 2
+        self.ops.append(op)
+        return dest
+
+    def stem(self, n: Node, dest: View | None) -> View:
+        c2 = n["c2"]
+        assert n["c1"] == 3 and n["k"] == (3, 3) and n["s"] == (2, 2) and n["g"] == 1
+        Ho, Wo = self.H // 2, self.W // 2
+        if dest is None:
+            dest = self.full(self.new_buf(c2, Ho, Wo, name=n["name"]), c2)
+        wp = n["weight"].permute(0, 2, 3, 1).reshape(c2, 27)  # [(r*3+s)*3 + rgb]
+        op = OpSpec(A.OP_STEM, n["name"], [View(self.input_buf, 0, 3, self.H, self.W)], dest, None, A.RES_NONE, 3, c2, c2,
+                    (3, 3), (2, 2), (1, 1), 1 if n["act"] == "silu" else 0, A.IMPL_SIMT,
+                    self.blob.add(wp.numpy().astype(np.float32)), self.blob.add(n["bias"].numpy().astype(np.float32)))
+        op.flops = 2 * c2 * 27 * Ho * Wo
+        op.bytes_alg = 3 * self.H * self.W * 2 + c2 * Ho * Wo * 2
+        self.ops.append(op)
+        return dest
+
+    def copy(self, src: View, dest: View, scale=1, name="copy"):
+        assert src.c == dest.c and dest.H == src.H * scale and dest.W == src.W * scale
+        op = OpSpec(A.OP_RESAMPLE, name, [src], dest, cin=src.c, cout=src.c, ip=(scale,))
+        op.bytes_alg = src.c * src.H * src.W * 2 + dest.c * dest.H * dest.W * 2
+        self.ops.append(op)
+        return dest
+
+    # ------------------------------------------------------------------ blocks
+    def bottleneck(self, n, x, dest):
+        t = self.conv(n["cv1"], x, pad16=True)
+        return self.conv(n["cv2"], t, dest, res=x if n["add"] else None, res_mode=A.RES_ADD if n["add"] else A.RES_NONE)
+
+    def pmsfa(self, n, x, dest):
+        c = n["c"]
+        cat = self.full(self.new_buf(c, x.H, x.W, name=n["name"] + ".cat"), c)
+        self.conv(n["conv1"], x, cat)
+        t2 = self.conv(n["conv2"], self.sub(cat, 0, c // 2))
+        self.conv(n["conv3"], self.sub(t2, 0, c // 4), self.sub(cat, 0, c // 4))
+        self.copy(self.sub(t2, c // 4, c // 4), self.sub(cat, c // 4, c // 4), name=n["name"] + ".cat2")
+        return self.conv(n["conv4"], cat, dest, res=x, res_mode=A.RES_ADD)
+
+    def inner(self, n, x, dest):
+        return {"Bottleneck": self.bottleneck, "PMSFA": self.pmsfa, "C3k": self.c3k}[n["type"]](n, x, dest)
+
+    def c3k(self, n, x, dest):
+        c_ = n["cv1"]["c2"]
+        z = self.full(self.new_buf(2 * c_, x.H, x.W, name=n["name"] + ".cat"), 2 * c_)
+        t = self.conv(n["cv1"], x)
+        for i, m in enumerate(n["m"]):
+            t = self.inner(m, t, self.sub(z, 0, c_) if i == len(n["m"]) - 1 else None)
+        if not n["m"]:
+            self.copy(t, self.sub(z, 0, c_))
+        self.conv(n["cv2"], x, self.sub(z, c_, c_))
+        return self.conv(n["cv3"], z, dest)
+
+    def c3k2(self, n, x, dest):
+        c, nm = n["c"], len(n["m"])
+        y = self.full(self.new_buf((2 + nm) * c, x.H, x.W, name=n["name"] + ".cat"), (2 + nm) * c)
+        self.conv(n["cv1"], x, self.sub(y, 0, 2 * c))
+        for i, m in enumerate(n["m"]):
+            self.inner(m, self.sub(y, (1 + i) * c, c), self.sub(y, (2 + i) * c, c))
+        return self.conv(n["cv2"], y, dest)
+
+    def sppf(self, n, x, dest):
+        c_ = n["cv1"]["c2"]
+        if n["k"] != 5:
+            raise NotImplementedError("SPPF kernel size other than 5 is not on the B200 path")
+        s = self.full(self.new_buf(4 * c_, x.H, x.W, name=n["name"] + ".cat"), 4 * c_)
+        self.conv(n["cv1"], x, self.sub(s, 0, c_))
+        op = OpSpec(A.OP_SPPF_POOL, n["name"] + ".pool", [self.sub(s, 0, c_)], self.sub(s, c_, 3 * c_), cin=c_, cout=3 * c_)
+        op.bytes_alg = 4 * c_ * x.H * x.W * 2
+        self.ops.append(op)
+        return self.conv(n["cv2"], s, dest)
+
+    def psablock(self, n, x, dest):
+        a = n["attn"]
+        nh, kd, hd = a["nh"], a["kd"], a["hd"]
+        c = nh * hd
+        N = x.H * x.W
+        qkv = self.conv(a["qkv"], x)
+        ao = self.full(self.new_buf(c, x.H, x.W, name=a["name"] + ".av"), c)
+        op = OpSpec(A.OP_ATTN, a["name"], [qkv], ao, cin=qkv.c, cout=c, ip=(nh, kd, hd))
+        op.flops = 2 * nh * N * N * (kd + hd) + 5 * nh * N * N
+        op.bytes_alg = (qkv.c + c) * N * 2
+        self.ops.append(op)
+        ao2 = self.full(self.new_buf(c, x.H, x.W, name=a["name"] + ".av_pe"), c)
+        pe = a["pe"]
+        for h in range(nh):  # pe(v): depthwise 3x3 over the v channels of head h, + attention output (block.py:4286)
+            sl = slice(h * hd, (h + 1) * hd)
+            sub_node = dict(pe, c1=hd, c2=hd, g=hd, name=f"{pe['name']}[h{h}]")
+            self.conv(sub_node, self.sub(qkv, h * (2 * kd + hd) + 2 * kd, hd), self.sub(ao2, h * hd, hd),
+                      res=self.sub(ao, h * hd, hd), res_mode=A.RES_ADD, wb=(pe["weight"][sl], pe["bias"][sl]))
+        add = A.RES_ADD if n["add"] else A.RES_NONE
+        b1 = self.conv(a["proj"], ao2, res=x if n["add"] else None, res_mode=add)
+        f = self.conv(n["ffn"][0], b1)
+        return self.conv(n["ffn"][1], f, dest, res=b1 if n["add"] else None, res_mode=add)
+
+    def c2psa(self, n, x, dest):
+        c = n["c"]
+        p = self.full(self.new_buf(2 * c, x.H, x.W, name=n["name"] + ".cat"), 2 * c)
+        self.conv(n["cv1"], x, p)
+        b = self.sub(p, c, c)
+        for i, m in enumerate(n["m"]):
+            b = self.psablock(m, b, self.sub(p, c, c) if i == len(n["m"]) - 1 else None)
+        return self.conv(n["cv2"], p, dest)
+
+    def scdown(self, n, x, dest):
+        return self.conv(n["cv2"], self.conv(n["cv1"], x), dest)
+
+    def msca(self, n, x, dest):
+        c = n["c"]
+        attn = self.conv(n["conv0"], x)
+        s, t = n["dilconv"]["weight"].reshape(c), n["dilconv"]["bias"]
+        br = []
+        for b in range(4):
+            u = self.conv(n[f"conv{b}_1"], attn)
+            n2 = n[f"conv{b}_2"]
+            wb = None
+            if b < 3:  # fold the shared per-channel 1x1 "dilconv" (MSCA.py:28-29,57,61,65) into the strip conv
+                wb = (n2["weight"] * s.view(c, 1, 1, 1), n2["bias"] * s + t)
+            br.append(self.conv(n2, u, wb=wb))
+        gap = self.new_buf(4 * c, 1, 1, A.F32, n["name"] + ".gap")
+        self.ops.append(OpSpec(A.OP_GAP4, n["name"] + ".gap", list(br), gap, cin=c, cout=c,
+                               bytes_alg=4 * c * x.H * x.W * 2))
+        gate = self.new_buf(4 * c, 1, 1, A.F32, n["name"] + ".gate")
+        se_w = torch.stack([n[f"SE{j}"]["weight"].reshape(c, c) for j in range(1, 5)])
+        se_b = torch.stack([n[f"SE{j}"]["bias"] for j in range(1, 5)])
+        self.ops.append(OpSpec(A.OP_MSCA_GATE, n["name"] + ".se", [gap], gate, cin=c, cout=c,
+                               p_off=(self.blob.add(se_w.numpy().astype(np.float32)),
+                                      self.blob.add(se_b.numpy().astype(np.float32)), -1, -1),
+                               flops=2 * 4 * c * c, bytes_alg=4 * c * c * 4))
+        xa = self.full(self.new_buf(c, x.H, x.W, name=n["name"] + ".xatt"), c)
+        self.ops.append(OpSpec(A.OP_WSUM4, n["name"] + ".wsum", list(br), xa, res=gate, cin=c, cout=c,
+                               bytes_alg=5 * c * x.H * x.W * 2))
+        return self.conv(n["conv4"], xa, dest, res=x, res_mode=A.RES_MUL)
+
+    def ela(self, n, x, dest):
+        c, ks = n["c"], n["ks"]
+        if dest is None:
+            dest = self.full(self.new_buf(c, x.H, x.W, name=n["name"]), c)
+        rowm = self.new_buf(c, x.H, 1, A.F32, n["name"] + ".rowm")
+        colm = self.new_buf(c, x.W, 1, A.F32, n["name"] + ".colm")
+        self.ops.append(OpSpec(A.OP_ROWCOL_MEAN, n["name"] + ".means", [x, colm], rowm, cin=c, cout=c,
+                               bytes_alg=2 * c * x.H * x.W * 2))
+        hg = self.new_buf(c, x.H, 1, A.F32, n["name"] + ".hgate")
+        wg = self.new_buf(c, x.W, 1, A.F32, n["name"] + ".wgate")
+        cg = self.new_buf(c, 1, 1, A.F32, n["name"] + ".chgate")
+        params = torch.cat([n["sp_w"].reshape(-1), n["gn_w"], n["gn_b"], n["ch_w"].reshape(-1)])
+        self.ops.append(OpSpec(A.OP_ELA_GATE, n["name"] + ".gate", [rowm, colm, wg, cg], hg, cin=c, cout=c,
+                               p_off=(self.blob.add(params.numpy().astype(np.float32)), -1, -1, -1),
+                               ip=(ks, n["groups"], x.H, x.W), fp=(n["gn_eps"],)))
+        co = [float(v) for v in n["coef"]]
+        self.ops.append(OpSpec(A.OP_ELA_APPLY, n["name"] + ".apply", [x, hg, wg, cg], dest, cin=c, cout=c, fp=tuple(co),
+                               bytes_alg=2 * c * x.H * x.W * 2))
+        return dest
+
+    def detect(self, n, xs):
+        nc = n["nc"]
+        no = 64 + nc
+        for i, x in enumerate(xs):
+            hb = self.new_buf(no, x.H, x.W, A.F32, f"{n['name']}.raw{i}")
+            self.head_bufs.append(hb)
+            head = View(hb, 0, no, x.H, x.W)
+            t = self.conv(n["cv2"][i][1], self.conv(n["cv2"][i][0], x))
+            self.conv(n["cv2"][i][2], t, self.sub(head, 0, 64), out_dtype=A.F32)
+            c3 = n["cv3"][i]
+            s = self.conv(c3[0][1], self.conv(c3[0][0], x))
+            s = self.conv(c3[1][1], self.conv(c3[1][0], s))
+            self.conv(c3[2], s, self.sub(head, 64, nc), out_dtype=A.F32)
+        self.A = sum(x.H * x.W for x in xs)
+        self.y_buf = self.new_buf(self.A, 4 + nc, 1, A.F32, n["name"] + ".y")
+        op = OpSpec(A.OP_DECODE, n["name"] + ".decode", list(self.head_bufs), self.y_buf, cin=no, cout=4 + nc,
+                    ip=(nc, len(xs)), fp=tuple(float(s) for s in n["stride"]))
+        op.bytes_alg = self.A * (no * 4 + (4 + nc) * 4)
+        self.ops.append(op)
+
+    # ------------------------------------------------------------------ whole graph
+    def _lower(self):
+        layers = self.ir["layers"]
+        # shapes
+        shape: dict[int, tuple[int, int, int]] = {}
+        prev = (3, self.H, self.W)
+
+        def src_of(i, f):
+            return i - 1 if f == -1 else f
+
+        for L in layers:
+            i, f, m = L["i"], L["f"], L["module"]
+            ty = m["type"]
+            ins = [prev if (i == 0 and ff == -1) else shape[src_of(i, ff)] for ff in ([f] if isinstance(f, int) else f)]
+            c, h, w = ins[0]
+            if ty == "Conv":
+                (kh, kw), (sh, sw), (ph, pw) = m["k"], m["s"], m["p"]
+                o = (m["c2"], (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1)
+            elif ty in ("C3k2", "SPPF", "C2PSA"):
+                o = (m["cv2"]["c2"], h, w)
+            elif ty == "SCDown":
+                o = (m["cv2"]["c2"], h // 2, w // 2)
+            elif ty in ("MSCA", "ELA"):
+                o = (c, h, w)
+            elif ty == "Upsample":
+                o = (c, 2 * h, 2 * w)
+            elif ty == "Concat":
+                o = (sum(s[0] for s in ins), h, w)
+            elif ty == "Detect":
+                o = None
+            else:
+                raise NotImplementedError(ty)
+            shape[i] = o
+        # concat destinations: the first Concat consumer of a layer gets a direct write
+        dest: dict[int, View] = {}
+        cat_view: dict[int, View] = {}
+        for L in layers:
+            if L["module"]["type"] != "Concat":
+                continue
+            i = L["i"]
+            C, Hc, Wc = shape[i]
+            cv = self.full(self.new_buf(C, Hc, Wc, name=f"model.{i}.cat"), C)
+            cat_view[i] = cv
+            off = 0
+            for ff in L["f"]:
+                j = src_of(i, ff)
+                cj = shape[j][0]
+                if j not in dest and layers[j]["module"]["type"] != "Concat" and cj % 8 == 0 and off % 8 == 0:
+                    dest[j] = self.sub(cv, off, cj)
+                off += cj
+        # emit
+        fn = {"C3k2": self.c3k2, "SPPF": self.sppf, "C2PSA": self.c2psa, "SCDown": self.scdown, "MSCA": self.msca,
+              "ELA": self.ela}
+        for L in layers:
+            i, f, m = L["i"], L["f"], L["module"]
+            ty = m["type"]
+            first = len(self.ops)
+            d = dest.get(i)
+            if ty == "Detect":
+                self.detect(m, [self.layer_out[src_of(i, ff)] for ff in f])
+            elif ty == "Concat":
+                cv, off = cat_view[i], 0
+                for ff in f:
+                    j = src_of(i, ff)
+                    v = self.layer_out[j]
+                    tgt = self.sub(cv, off, v.c)
+                    if (v.buf, v.coff) != (tgt.buf, tgt.coff):
+                        self.copy(v, tgt, name=f"model.{i}.copy{j}")
+                    off += v.c
+                self.layer_out[i] = cv
+            else:
+                if i == 0:
+                    if ty != "Conv" or m["c1"] != 3:
+                        raise NotImplementedError("first layer must be the 3-channel stem Conv")
+                    out = self.stem(m, d)
+                else:
+                    x = self.layer_out[src_of(i, f)]
+                    if ty == "Conv":
+                        out = self.conv(m, x, d)
+                    elif ty == "Upsample":
+                        if d is None:
+                            d = self.full(self.new_buf(x.c, 2 * x.H, 2 * x.W, name=m["name"]), x.c)
+                        out = self.copy(x, d, scale=2, name=m["name"])
+                    else:
+                        out = fn[ty](m, x, d)
+                self.layer_out[i] = out
+            self.layer_op_range[i] = (first, len(self.ops))
+
+    # ------------------------------------------------------------------ binding to a batch size
+    def layout(self, B: int) -> tuple[list[int], int]:
+        """Byte offsets of every buffer for batch B (256-B aligned, no aliasing) and the workspace size."""
+        offs, cur = [], 0
+        for b in self.bufs:
+            offs.append(cur)
+            cur = _r(cur + B * b.elems() * (4 if b.dtype == A.F32 else 2), 256)
+        return offs, cur
+
+    def c_arrays(self, B: int):
+        offs, total = self.layout(B)
+        bufs = (A.Buf * len(self.bufs))()
+        for i, b in enumerate(self.bufs):
+            bufs[i] = A.Buf(offs[i], b.C, b.H, b.W, b.dtype)
+        ops = (A.Op * len(self.ops))()
+        for i, o in enumerate(self.ops):
+            c = A.Op()
+            c.kind = o.kind
+            for j in range(4):
+                c.in_[j], c.in_coff[j] = -1, 0
+            for j, v in enumerate(o.ins):
+                if isinstance(v, View):
+                    c.in_[j], c.in_coff[j] = v.buf, v.coff
+                else:
+                    c.in_[j] = int(v)
+            if isinstance(o.out, View):
+                c.out, c.out_coff = o.out.buf, o.out.coff
+            else:
+                c.out, c.out_coff = int(o.out), 0
+            if isinstance(o.res, View):
+                c.res, c.res_coff = o.res.buf, o.res.coff
+            elif o.res is not None:
+                c.res, c.res_coff = int(o.res), 0
+            else:
+                c.res, c.res_coff = -1, 0
+            c.res_mode, c.cin, c.cout, c.cout_pad = o.res_mode, o.cin, o.cout, o.cout_pad
+            (c.kh, c.kw), (c.sh, c.sw), (c.ph, c.pw) = o.k, o.s, o.p
+            c.act, c.impl, c.w_off, c.b_off = o.act, o.impl, o.w_off, o.b_off
+            for j in range(4):
+                c.p_off[j] = o.p_off[j] if j < len(o.p_off) else -1
+            for j, v in enumerate(o.ip):
+                c.ip[j] = int(v)
+            for j, v in enumerate(o.fp):
+                c.fp[j] = float(v)
+            ops[i] = c
+        return ops, bufs, total
+
+    # ------------------------------------------------------------------ roofline accounting
+    def work_per_image(self) -> tuple[int, int]:
+        return sum(o.flops for o in self.ops), sum(o.bytes_alg for o in self.ops)

@@ -1,0 +1,137 @@
+/* b2y.h -- C ABI of libb2y.so: the B200 (sm_100a) detection inference path that drops in behind the
+ * BS-YOLO / Ultralytics fork's predict() hot path.
+ *
+ * The reference has no native interface on this path (it is torch eager + torchvision + OpenCV);
+ * each entry point therefore cites the reference *Python* interface it replaces.  Plain pointers and sizes
+ * only; device pointers are raw `void*` (e.g. torch `tensor.data_ptr()`), streams are `cudaStream_t` passed as
+ * `void*`.  Every function returns B2Y_OK (0) or a negative error code, never throws, never synchronises the
+ * device unless stated, and keeps no global state besides the last-error string (thread local).
+ */
+#ifndef B2Y_H_
+#define B2Y_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2Y_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B2Y_API __attribute__((visibility("default")))
+#else
+#define B2Y_API
+#endif
+
+enum {
+  B2Y_OK = 0,
+  B2Y_ERR_INVALID = -1,     /* bad argument / unsupported shape   -> ValueError in the Python shim        */
+  B2Y_ERR_UNSUPPORTED = -2, /* op not on the B200 path            -> NotImplementedError (no CPU fallback) */
+  B2Y_ERR_CUDA = -3,        /* CUDA runtime / driver error        -> RuntimeError                          */
+  B2Y_ERR_NOMEM = -4        /* workspace too small                -> MemoryError                           */
+};
+
+/* ---- plan: the lowered network (replaces BaseModel._predict_once, ultralytics/nn/tasks.py:138-165, and the
+ *      module forwards in nn/modules/{conv,block,head}.py + nn/Addmodules/{MSCA,ELA}.py) ------------------- */
+
+enum b2y_dtype { B2Y_BF16 = 0, B2Y_F32 = 1 };
+
+enum b2y_op_kind {
+  B2Y_OP_CONV = 1,      /* dense conv k{1,3} s{1,2} + bias (+SiLU) (+residual add|mul); conv.py:145-151         */
+  B2Y_OP_DWCONV = 2,    /* depthwise kh x kw conv + bias (+SiLU) (+residual add); conv.py:224-229, MSCA.py:24-39  */
+  B2Y_OP_STEM = 3,      /* Cin=3 3x3 s2 first conv on the 4-channel-padded preprocess output                     */
+  B2Y_OP_SPPF_POOL = 4, /* three chained MaxPool2d(5,1,2) written to three channel slices; block.py:3145-3149   */
+  B2Y_OP_RESAMPLE = 5,  /* channel-slice copy, optionally nearest 2x upsample (nn.Upsample, Concat conv.py:455)  */
+  B2Y_OP_ATTN = 6,      /* softmax(q^T k * kd^-0.5) v per head; block.py:4280-4286                               */
+  B2Y_OP_ROWCOL_MEAN = 7, /* ELA: row / column / global means; ELA.py:74-84                                      */
+  B2Y_OP_ELA_GATE = 8,  /* ELA: dilated conv1d + GroupNorm + sigmoid gates; ELA.py:77-86                         */
+  B2Y_OP_ELA_APPLY = 9, /* ELA: x * (a*ch + b*h*w) + c*x; ELA.py:94-100                                          */
+  B2Y_OP_GAP4 = 10,     /* MSCA: global average pool of the four branches; MSCA.py:71-74                         */
+  B2Y_OP_MSCA_GATE = 11,/* MSCA: SE 1x1 convs + softmax(sigmoid()) over branches; MSCA.py:71-77                  */
+  B2Y_OP_WSUM4 = 12,    /* MSCA: gate-weighted sum of the four branches; MSCA.py:84                              */
+  B2Y_OP_DECODE = 13    /* Detect._inference: DFL + dist2bbox + stride + sigmoid; head.py:100-131                */
+};
+
+enum b2y_conv_impl { B2Y_IMPL_AUTO = 0, B2Y_IMPL_SIMT = 1, B2Y_IMPL_TCGEN05 = 2 };
+enum b2y_res_mode { B2Y_RES_NONE = 0, B2Y_RES_ADD = 1, B2Y_RES_MUL = 2 };
+
+/* A buffer is one NHWC activation tensor (batch B is a plan property): B x H x W x C elements. */
+typedef struct {
+  int64_t offset; /* byte offset into the workspace (256-B aligned) */
+  int32_t C, H, W;
+  int32_t dtype;  /* b2y_dtype */
+} b2y_buf;
+
+/* One fused op.  Tensor operands are *views*: (buffer index, first channel); the view's channel count is
+ * cin / cout.  Unused operands are -1.  Weights live in one device blob, addressed by byte offsets. */
+typedef struct {
+  int32_t kind;
+  int32_t in[4], in_coff[4];
+  int32_t out, out_coff;
+  int32_t res, res_coff, res_mode;
+  int32_t cin, cout;       /* logical channels read / written per pixel                                   */
+  int32_t cout_pad;        /* rows in the packed weight matrix (>= cout, multiple of 16 for the tcgen05 path) */
+  int32_t kh, kw, sh, sw, ph, pw;
+  int32_t act;             /* 0 none, 1 SiLU */
+  int32_t impl;            /* b2y_conv_impl */
+  int64_t w_off, b_off;    /* weights / bias byte offsets (-1: none); extra parameter blocks follow in p_off */
+  int64_t p_off[4];
+  int32_t ip[8];           /* op-specific integers (nh, kd, hd | groups, ks | nc, level sizes ...)          */
+  float fp[4];             /* op-specific floats                                                            */
+} b2y_op;
+
+typedef struct b2y_plan b2y_plan;
+
+B2Y_API int b2y_abi_version(void);
+B2Y_API const char *b2y_last_error(void);
+
+/* Build a plan over caller-owned device memory (workspace: activations, weights: packed parameter blob).
+ * Creates TMA descriptors and per-op launch geometry; does not launch anything. */
+B2Y_API int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *bufs, int32_t n_bufs, void *workspace,
+                    size_t workspace_bytes, const void *weights, size_t weights_bytes, int32_t batch, int32_t device,
+                    b2y_plan **out);
+B2Y_API int b2y_plan_destroy(b2y_plan *plan);
+/* Enqueue ops [first, last) on `stream` (last = -1: to the end).  Replaces AutoBackend.forward -> self.model(im)
+ * (ultralytics/nn/autobackend.py:523-524). */
+B2Y_API int b2y_plan_run(b2y_plan *plan, int32_t first, int32_t last, void *stream);
+/* Capture the whole plan into a CUDA graph (stream must not be capturing) / replay it. */
+B2Y_API int b2y_plan_graph_build(b2y_plan *plan, void *stream);
+B2Y_API int b2y_plan_graph_launch(b2y_plan *plan, void *stream);
+/* Number of kernels one full run launches; which conv implementation op `i` resolved to (b2y_conv_impl). */
+B2Y_API int b2y_plan_num_launches(const b2y_plan *plan);
+B2Y_API int b2y_plan_op_impl(const b2y_plan *plan, int32_t i);
+
+/* ---- preprocess: LetterBox + BGR->RGB + /255 (ultralytics/data/augment.py:1535-1601,
+ *      engine/predictor.py:116-134).  src: B x h x w x 3 uint8 (device).  The resized image (uw x uh, OpenCV
+ *      INTER_LINEAR fixed-point semantics; identity when uw==w && uh==h) is placed at (top,left) of an H x W canvas
+ *      padded with 114.  dst_format 0: NHWC bf16 with 4 channels (R,G,B,0) feeding the stem; 1: NCHW fp32 (the
+ *      reference's tensor); 2: HWC uint8 letterboxed BGR (LetterBox output, for bit-exact tests). */
+B2Y_API int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, void *dst, int32_t H, int32_t W, int32_t top,
+                   int32_t left, int32_t uh, int32_t uw, int32_t dst_format, void *stream);
+
+/* ---- decode: Detect._inference (ultralytics/nn/modules/head.py:100-131; DFL block.py:73-76; make_anchors /
+ *      dist2bbox utils/tal.py:371-395).  raw[l]: B x H_l x W_l x (64+nc) fp32 NHWC head maps.
+ *      y: B x (4+nc) x A fp32, rows cx,cy,w,h,p0.. (the reference's layout). */
+B2Y_API int b2y_decode(const void *const *raw, const int32_t *hs, const int32_t *ws, const float *strides, int32_t n_levels,
+               int32_t B, int32_t nc, void *y, void *stream);
+
+/* ---- NMS: ops.non_max_suppression (ultralytics/utils/ops.py:167-316) + torchvision.ops.nms, bit-exact.
+ *      pred: B x (4+nc) x A fp32 (not modified).  dets: B x max_det x 6 fp32 rows [x1,y1,x2,y2,conf,cls] in
+ *      descending-score order, counts: B int32.  kept_anchor (optional, may be NULL): B x max_det int32 anchor index
+ *      of every kept row.  classes: optional device-side filter list (host pointer, copied at call time).
+ *      Documented deviations: no wall-clock abort (ops.py:312-314), input not mutated (ops.py:244). */
+B2Y_API size_t b2y_nms_workspace_bytes(int32_t B, int32_t nc, int32_t A, int32_t multi_label, int32_t max_nms);
+B2Y_API int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float conf_thres, double iou_thres, int32_t max_det,
+            int32_t max_nms, float max_wh, int32_t agnostic, int32_t multi_label, const int32_t *classes,
+            int32_t n_classes, void *workspace, size_t workspace_bytes, void *dets, void *counts, void *kept_anchor,
+            void *stream);
+
+/* ---- scale_boxes + clip_boxes (ultralytics/utils/ops.py:92-127, 319-338) applied in place to dets
+ *      (B x max_det x 6); one (gain, padx, pady, w0, h0) record of 5 floats per image (device pointer). */
+B2Y_API int b2y_scale_boxes(void *dets, const void *counts, const void *geom, int32_t B, int32_t max_det, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2Y_H_ */

@@ -1,0 +1,165 @@
+"""Test infrastructure: executes a bs_yolo_b200.plan.Plan op list with plain PyTorch (fp32, CPU), following the op
+semantics documented in include/b2y.h.  It lets the CPU suite check the planner's lowering (channel-slice concat
+fusion, residual placement, BN/dilconv folds, ELA/MSCA decomposition, per-head pe convs, weight packing) against the
+oracle without a GPU; the GPU suite then only has to establish kernel == op semantics."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from bs_yolo_b200 import _cabi as A
+from bs_yolo_b200.plan import Plan, View
+
+
+class PlanEmulator:
+    def __init__(self, plan: Plan, B: int, round_bf16: bool = False):
+        self.plan, self.B, self.round = plan, B, round_bf16
+        self.blob = plan.blob.tobytes()
+        self.bufs = [torch.zeros(B, b.H, b.W, b.C) for b in plan.bufs]
+
+    # -- helpers
+    def f32(self, off, n):
+        return torch.from_numpy(np.frombuffer(self.blob, np.float32, n, off).copy())
+
+    def bf16(self, off, n):
+        bits = np.frombuffer(self.blob, np.int16, n, off).astype(np.int32) << 16
+        return torch.from_numpy(bits.view(np.float32).copy())
+
+    def get(self, v):
+        if isinstance(v, View):
+            return self.bufs[v.buf][..., v.coff:v.coff + v.c]
+        return self.bufs[v]
+
+    def put(self, v: View, val, c=None):
+        c = v.c if c is None else c
+        if self.round and self.plan.bufs[v.buf].dtype == A.BF16:
+            val = val.to(torch.bfloat16).float()
+        self.bufs[v.buf][..., v.coff:v.coff + c] = val[..., :c]
+
+    def set_input(self, x):  # (B,3,H,W) float
+        self.bufs[self.plan.input_buf][..., :3] = x.permute(0, 2, 3, 1)
+        if self.round:
+            self.bufs[self.plan.input_buf] = self.bufs[self.plan.input_buf].to(torch.bfloat16).float()
+
+    # -- ops
+    def run(self, first=0, last=None):
+        for op in self.plan.ops[first:last]:
+            getattr(self, "op_" + A.OP_NAMES[op.kind])(op)
+
+    def _epilogue(self, op, y):
+        if op.act:
+            y = F.silu(y)
+        if op.res_mode:
+            r = self.get(op.res)
+            y = y[..., :op.cout] + r if op.res_mode == A.RES_ADD else y[..., :op.cout] * r
+        self.put(op.out, y, op.cout)
+
+    def op_conv(self, op):
+        kh, kw = op.k
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        wflat = op.w_fp32 if (op.w_fp32 is not None and not self.round) else self.bf16(op.w_off, op.cout_pad * kh * kw * op.cin)
+        w = wflat.reshape(op.cout_pad, kh, kw, op.cin).permute(0, 3, 1, 2)
+        b = self.f32(op.b_off, op.cout_pad)
+        y = F.conv2d(x, w, b, stride=op.s, padding=op.p).permute(0, 2, 3, 1)
+        self._epilogue(op, y)
+
+    def op_dwconv(self, op):
+        kh, kw = op.k
+        c = op.cout
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        w = self.f32(op.w_off, kh * kw * c).view(kh, kw, c).permute(2, 0, 1).unsqueeze(1)
+        y = F.conv2d(x, w, self.f32(op.b_off, c), stride=op.s, padding=op.p, groups=c).permute(0, 2, 3, 1)
+        self._epilogue(op, y)
+
+    def op_stem(self, op):
+        c = op.cout
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        w = self.f32(op.w_off, c * 27).view(c, 3, 3, 3).permute(0, 3, 1, 2)
+        y = F.conv2d(x, w, self.f32(op.b_off, c), stride=2, padding=1).permute(0, 2, 3, 1)
+        self._epilogue(op, y)
+
+    def op_sppf_pool(self, op):
+        c = op.cin
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        outs = []
+        for _ in range(3):
+            x = F.max_pool2d(x, 5, 1, 2)
+            outs.append(x)
+        self.put(op.out, torch.cat(outs, 1).permute(0, 2, 3, 1), 3 * c)
+
+    def op_resample(self, op):
+        x = self.get(op.ins[0])
+        s = op.ip[0]
+        if s != 1:
+            x = x.repeat_interleave(s, 1).repeat_interleave(s, 2)
+        self.put(op.out, x)
+
+    def op_attn(self, op):
+        nh, kd, hd = op.ip
+        qkv = self.get(op.ins[0])
+        B, H, W, _ = qkv.shape
+        q, k, v = qkv.reshape(B, H * W, nh, 2 * kd + hd).permute(0, 2, 1, 3).split([kd, kd, hd], -1)  # (B,nh,N,d)
+        p = torch.softmax(q @ k.transpose(-1, -2) * kd ** -0.5, -1)
+        o = (p @ v).permute(0, 2, 1, 3).reshape(B, H, W, nh * hd)
+        self.put(op.out, o)
+
+    def op_rowcol_mean(self, op):
+        x = self.get(op.ins[0])
+        self.bufs[op.out][:, :, 0, :] = x.mean(2)
+        self.bufs[op.ins[1]][:, :, 0, :] = x.mean(1)
+
+    def op_ela_gate(self, op):
+        ks, groups, H, W = op.ip
+        c = op.cin
+        p = self.f32(op.p_off[0], 2 * c * ks + 2 * c)
+        sp_w, gn_w, gn_b, ch_w = p[:c * ks].view(c, ks), p[c * ks:c * ks + c], p[c * ks + c:c * ks + 2 * c], p[c * ks + 2 * c:].view(c, ks)
+        rowm, colm = self.bufs[op.ins[0]][:, :, 0, :], self.bufs[op.ins[1]][:, :, 0, :]
+
+        def gate(m):  # (B,L,c)
+            v = F.conv1d(m.transpose(1, 2), sp_w.unsqueeze(1), padding=ks - 1, dilation=2, groups=c)
+            return torch.sigmoid(F.group_norm(v, groups, gn_w, gn_b, op.fp[0])).transpose(1, 2)
+
+        self.bufs[op.out][:, :, 0, :] = gate(rowm)
+        self.bufs[op.ins[2]][:, :, 0, :] = gate(colm)
+        self.bufs[op.ins[3]][:, 0, 0, :] = torch.sigmoid(ch_w[:, (ks - 1) // 2] * rowm.mean(1))
+
+    def op_ela_apply(self, op):
+        x = self.get(op.ins[0])
+        hg = self.bufs[op.ins[1]][:, :, 0, :].unsqueeze(2)
+        wg = self.bufs[op.ins[2]][:, :, 0, :].unsqueeze(1)
+        cg = self.bufs[op.ins[3]][:, 0, 0, :].view(self.B, 1, 1, -1)
+        a, b, r = op.fp
+        self.put(op.out, x * (a * cg + b * (hg * wg)) + r * x)
+
+    def op_gap4(self, op):
+        c = op.cin
+        for j in range(4):
+            self.bufs[op.out][:, 0, 0, j * c:(j + 1) * c] = self.get(op.ins[j]).mean((1, 2))
+
+    def op_msca_gate(self, op):
+        c = op.cin
+        w = self.f32(op.p_off[0], 4 * c * c).view(4, c, c)
+        b = self.f32(op.p_off[1], 4 * c).view(4, c)
+        gap = self.bufs[op.ins[0]][:, 0, 0, :].view(self.B, 4, c)
+        z = torch.sigmoid(torch.einsum("jok,bjk->bjo", w, gap) + b)
+        self.bufs[op.out][:, 0, 0, :] = torch.softmax(z, 1).reshape(self.B, 4 * c)
+
+    def op_wsum4(self, op):
+        c = op.cin
+        g = self.bufs[op.res][:, 0, 0, :].view(self.B, 4, 1, 1, c)
+        self.put(op.out, sum(g[:, j] * self.get(op.ins[j]) for j in range(4)))
+
+    def op_decode(self, op):
+        from oracle import oracle_net
+        nc, nl = op.ip
+        raws = [self.bufs[i].permute(0, 3, 1, 2) for i in op.ins[:nl]]
+        y = oracle_net.decode(raws, list(op.fp[:nl]), nc)  # (B, 4+nc, A)
+        self.bufs[op.out][:, :, 0, :] = y
+
+    # -- results
+    def y(self):
+        return self.bufs[self.plan.y_buf][:, :, 0, :]
+
+    def raws(self):
+        return [self.bufs[i].permute(0, 3, 1, 2) for i in self.plan.head_bufs]
