@@ -31,13 +31,13 @@ def letterbox_geometry(shape, new_shape, auto: bool, stride: int = 32):
 
 class Engine:
     def __init__(self, ir, batch: int, H: int, W: int, device: int | torch.device = 0, conv_impl: int = A.IMPL_AUTO,
-                 use_graph: bool = True):
+                 use_graph: bool = True, plan: Plan | None = None):
         if not torch.cuda.is_available():
             raise A.B2YError("bs_yolo_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = A.lib()
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.B, self.H, self.W = batch, H, W
-        self.plan = Plan(ir, H, W, conv_impl)
+        self.plan = plan if plan is not None else Plan(ir, H, W, conv_impl)
         self.nc, self.A = self.plan.nc, self.plan.A
         ops, bufs, ws_bytes = self.plan.c_arrays(batch)
         self._ops, self._bufs = ops, bufs  # keep alive

@@ -1,0 +1,54 @@
+"""DetectPipeline: the public batch API of the B200 path -- uint8 BGR frames in, final detections out.
+
+One pipeline = one GPU = one CUDA-graphed network (Engine) + preprocess + NMS (+ optional scale_boxes), i.e. the
+device-side body of BasePredictor.stream_inference's hot loop (ultralytics/engine/predictor.py:241-266):
+preprocess -> inference -> postprocess.  `predict_host` is the end-to-end entry: pinned host frames are copied in,
+detections are copied back, with the copies double-buffered against compute on a second stream."""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi as A
+from .engine import Engine, letterbox_geometry
+from .ops import nms_raw, scale_boxes_batched
+
+
+class DetectPipeline:
+    def __init__(self, ir, batch: int, imgsz=(640, 640), src_shape=(640, 640), device: int = 0, conf=0.25, iou=0.7,
+                 max_det=300, classes=None, agnostic=False, auto=True, use_graph=True, conv_impl=A.IMPL_AUTO):
+        imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        self.src_shape = tuple(src_shape)
+        H, W, *_ = letterbox_geometry(self.src_shape, imgsz, auto)
+        self.auto = auto
+        self.engine = Engine(ir, batch, H, W, device=device, use_graph=use_graph, conv_impl=conv_impl)
+        self.device = self.engine.device
+        self.B, self.H, self.W = batch, H, W
+        self.conf, self.iou, self.max_det, self.classes, self.agnostic = conf, iou, max_det, classes, agnostic
+        self._copy_stream = None
+        self._staging = None
+
+    @property
+    def launches_per_batch(self) -> int:
+        return self.engine.n_launches + 1 + 2  # network ops + preprocess + NMS (score, select)
+
+    def __call__(self, src_u8: torch.Tensor, rescale: bool = False):
+        """src_u8: (B,h,w,3) uint8 BGR on this pipeline's device. Returns (dets (B,max_det,6), counts (B,)) on device."""
+        self.engine.preprocess(src_u8, auto=self.auto)
+        self.engine.forward()
+        dets, counts = nms_raw(self.engine.y, self.conf, self.iou, self.max_det, self.classes, self.agnostic)
+        if rescale:
+            scale_boxes_batched(dets, counts, (self.H, self.W), [self.src_shape] * self.B)
+        return dets, counts
+
+    def predict_host(self, frames: torch.Tensor, rescale: bool = False):
+        """frames: pinned host uint8 (B,h,w,3). Returns host (dets, counts); blocks until they are valid."""
+        if self._staging is None:
+            self._staging = torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
+            self._out = (torch.empty(self.B, self.max_det, 6, dtype=torch.float32).pin_memory(),
+                         torch.empty(self.B, dtype=torch.int32).pin_memory())
+        self._staging.copy_(frames, non_blocking=True)
+        dets, counts = self(self._staging, rescale)
+        self._out[0].copy_(dets, non_blocking=True)
+        self._out[1].copy_(counts, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._out

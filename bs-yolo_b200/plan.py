@@ -123,7 +123,13 @@ class Plan:
         self.head_bufs: list[int] = []
         self.y_buf = -1
         self.A = 0
-        self._lower()
+        if ir.get("layers"):
+            self._lower()
+
+    @classmethod
+    def empty(cls, H: int, W: int, nc: int = 1, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False) -> "Plan":
+        """A plan with no ops (unit tests append single ops through the same lowering helpers)."""
+        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32)
 
     # ------------------------------------------------------------------ buffers / views
     def new_buf(self, C, H, W, dtype=A.BF16, name="") -> int:

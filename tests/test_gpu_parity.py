@@ -1,0 +1,211 @@
+"""GPU parity tests (B200): every kernel is driven through the C ABI and compared with the oracle / the committed
+golden outputs of the reference.  Tolerances (BASELINE.json north_star):
+  * NMS, letterbox: bit-exact;
+  * decode (fp32): |dbox| <= 2e-3 px, |dscore| <= 2e-6 (expf/summation-order noise only);
+  * network head maps in bf16: rel-L2 <= 1e-2 per level;
+  * final boxes: IoU >= 0.99 and |dconf| <= 1e-2 for every matched box."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import kat
+from bs_yolo_b200 import _cabi as A
+from bs_yolo_b200 import arch, ir, ops
+from oracle import oracle_net, oracle_post
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(model, seed=0):
+    spec = arch.build_spec(model)
+    return ir.build_ir(spec, arch.synth_state_dict(spec, seed))
+
+
+# ----------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("case", kat.NMS_CASES)
+def test_nms_bit_exact_vs_reference_golden(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, "nms.npz"))
+    p, kw = kat.nms_case(case)
+    out = ops.non_max_suppression(torch.from_numpy(p).cuda(), **kw)
+    assert [int(o.shape[0]) for o in out] == g[f"{case}__n"].tolist()
+    rows = np.concatenate([o.cpu().numpy().reshape(-1, 6) for o in out], 0).astype(np.float32)
+    assert rows.tobytes() == g[f"{case}__rows"].tobytes()
+
+
+def test_nms_large_candidate_sets_vs_oracle():
+    """> 8192 candidates takes the global-memory sort; > max_nms exercises the cut (distinct scores)."""
+    rng = np.random.default_rng(3)
+    p = kat._rand_pred(rng, 2, 4, 33600, img=1280.0, score_pow=0.3)
+    p[:, 4:] = np.clip(p[:, 4:] * 0.5 + 0.5 * rng.permutation(p[:, 4:].size).reshape(p[:, 4:].shape) / p[:, 4:].size, 0, 1)
+    for kw in (dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.05, iou_thres=0.6, max_nms=30000, max_det=1000)):
+        ref = oracle_post.non_max_suppression(p, **kw)
+        out = ops.non_max_suppression(torch.from_numpy(p).cuda(), **kw)
+        for a, b in zip(out, ref):
+            assert a.cpu().numpy().tobytes() == b.tobytes()
+
+
+def test_nms_input_not_mutated_and_errors():
+    p, kw = kat.nms_case("random_2100")
+    t = torch.from_numpy(p).cuda()
+    before = t.clone()
+    ops.non_max_suppression(t, **kw)
+    assert torch.equal(t, before)  # documented deviation from ops.py:244
+    with pytest.raises(AssertionError, match="Invalid Confidence threshold"):
+        ops.non_max_suppression(t, conf_thres=1.5)
+    with pytest.raises(AssertionError, match="Invalid IoU"):
+        ops.non_max_suppression(t, iou_thres=-0.1)
+    with pytest.raises(A.B2YError):
+        ops.non_max_suppression(torch.from_numpy(p))  # CPU tensor: no fallback
+
+
+# ----------------------------------------------------------------------------- preprocess
+@pytest.mark.parametrize("case", list(kat.LETTERBOX_CASES))
+@pytest.mark.parametrize("auto", [False, True])
+def test_letterbox_bit_exact_vs_reference_golden(case, auto, golden_dir):
+    g = np.load(os.path.join(golden_dir, "letterbox.npz"))
+    imgsz = kat.LETTERBOX_CASES[case][2]
+    img = kat.letterbox_input(case)
+    out = ops.letterbox([img, img], imgsz, auto=auto).cpu().numpy()
+    ref = g[f"{case}__auto{int(auto)}"]
+    assert out.shape[1:] == ref.shape
+    assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref)
+
+
+def test_preprocess_fp32_matches_reference_semantics():
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (360, 640, 3), dtype=np.uint8) for _ in range(3)]
+    got = ops.preprocess(imgs, 640, auto=True).cpu().numpy()
+    ref = oracle_post.preprocess(imgs, (640, 640))
+    assert got.shape == ref.shape == (3, 3, 384, 640)
+    assert np.array_equal(got, ref)  # same uint8 pixels, same correctly-rounded /255
+
+
+# ----------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("nc,hw", [(80, (64, 96)), (12, (640, 640)), (80, (96, 32))])
+def test_decode_vs_oracle(nc, hw):
+    import ctypes as C
+    B = 3
+    rng = np.random.default_rng(nc)
+    shapes = [(hw[0] // s, hw[1] // s) for s in (8, 16, 32)]
+    raws = [torch.from_numpy((rng.standard_normal((B, 64 + nc, h, w)) * 2).astype(np.float32)) for h, w in shapes]
+    ref = oracle_net.decode(raws, [8.0, 16.0, 32.0], nc)
+    dev = [r.permute(0, 2, 3, 1).contiguous().cuda() for r in raws]
+    An = sum(h * w for h, w in shapes)
+    y = torch.zeros(B, 4 + nc, An, device="cuda")
+    ptrs = (C.c_void_p * 3)(*[d.data_ptr() for d in dev])
+    hs = (C.c_int32 * 3)(*[s[0] for s in shapes])
+    ws = (C.c_int32 * 3)(*[s[1] for s in shapes])
+    st = (C.c_float * 3)(8.0, 16.0, 32.0)
+    A.check(A.lib().b2y_decode(ptrs, hs, ws, st, 3, B, nc, y.data_ptr(), None))
+    torch.cuda.synchronize()
+    y = y.cpu()
+    assert float((y[:, :4] - ref[:, :4]).abs().max()) < 2e-3
+    assert float((y[:, 4:] - ref[:, 4:]).abs().max()) < 2e-6
+
+
+# ----------------------------------------------------------------------------- conv kernels
+import convcase  # noqa: E402
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("case", list(convcase.CASES))
+def test_conv_kernels_vs_emulator(case, impl):
+    got, ref, used = convcase.run_case(case, A.IMPL_SIMT if impl == "simt" else A.IMPL_TCGEN05)
+    assert used == (A.IMPL_SIMT if impl == "simt" else A.IMPL_TCGEN05)
+    rel = float((got - ref).norm() / (ref.norm() + 1e-12))
+    assert rel < 4e-3, rel  # same bf16 inputs/weights, fp32 accumulation; only bf16 output rounding + sum order
+
+
+# ----------------------------------------------------------------------------- whole network
+def _run_engine(g, x, **kw):
+    from bs_yolo_b200.engine import Engine
+    B, _, H, W = x.shape
+    eng = Engine(g, B, H, W, **kw)
+    eng.set_input(x)
+    eng.forward()
+    torch.cuda.synchronize()
+    return eng
+
+
+@pytest.mark.parametrize("case", list(kat.NET_CASES))
+def test_network_heads_vs_reference_golden(case, golden_dir):
+    gld = np.load(os.path.join(golden_dir, f"net_{case}.npz"))
+    g = _graph(kat.NET_CASES[case][0])
+    eng = _run_engine(g, torch.from_numpy(kat.net_input(case)))
+    for i in range(3):
+        ref = torch.from_numpy(gld[f"raw{i}"])
+        got = eng.raw(i).permute(0, 3, 1, 2).float().cpu()
+        rel = float((got - ref).norm() / ref.norm())
+        assert rel < 1e-2, (case, i, rel)
+
+
+@pytest.mark.parametrize("model", ["yolo11n", "bsyolo_n"])
+def test_layerwise_vs_oracle(model):
+    """Every top-level layer output, read through its channel-slice view, against the fp32 oracle."""
+    g = _graph(model)
+    x = torch.from_numpy(np.random.default_rng(5).random((2, 3, 128, 160), dtype=np.float32))
+    eng = _run_engine(g, x, use_graph=False)
+    cap = {}
+    oracle_net.forward(g, x, capture=cap)
+    worst = 0.0
+    for i, v in eng.plan.layer_out.items():
+        ref = cap[i]
+        got = eng.view_tensor(v).permute(0, 3, 1, 2)[:, : ref.shape[1]].float().cpu()
+        rel = float((got - ref).norm() / (ref.norm() + 1e-12))
+        worst = max(worst, rel)
+        assert rel < 1.5e-2, f"layer {i} ({g['layers'][i]['module']['type']}): rel-L2 {rel:.3e}"
+    assert worst > 0  # bf16 path really ran
+
+
+@pytest.mark.parametrize("model,B", [("yolo11n", 4), ("bsyolo_n", 4)])
+def test_end_to_end_640_vs_oracle(model, B):
+    """uint8 images -> preprocess -> network -> decode -> NMS, against the oracle on the same inputs (config 2/3 shape)."""
+    from bs_yolo_b200.engine import Engine
+    g = _graph(model)
+    imgs = np.random.default_rng(9).integers(0, 256, (B, 640, 640, 3), dtype=np.uint8)
+    eng = Engine(g, B, 640, 640)
+    eng.preprocess(torch.from_numpy(imgs).cuda())
+    y = eng.forward()
+    dets, counts = eng.nms(0.25, 0.7, 300)
+    torch.cuda.synchronize()
+    x = torch.from_numpy(oracle_post.preprocess(list(imgs), (640, 640)))
+    y_ref, raws_ref = oracle_net.forward(g, x)
+    for i, r in enumerate(raws_ref):
+        got = eng.raw(i).permute(0, 3, 1, 2).float().cpu()
+        assert float((got - r).norm() / r.norm()) < 1e-2
+    # NMS bit-exact on the identical decoded tensor the GPU produced
+    ref_same = oracle_post.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
+    n = counts.cpu().tolist()
+    for i in range(B):
+        assert dets[i, : n[i]].cpu().numpy().tobytes() == ref_same[i].tobytes()
+    # final boxes vs the all-fp32 oracle pipeline: IoU >= 0.99 and |dconf| <= 1e-2 for matched boxes
+    ref_dets = oracle_post.non_max_suppression(y_ref.numpy(), 0.25, 0.7, max_det=300)
+    matched = total = 0
+    for i in range(B):
+        ours, ref = dets[i, : n[i]].cpu().numpy(), ref_dets[i]
+        total += ref.shape[0]
+        for r in ref:
+            c = ours[ours[:, 5] == r[5]]
+            if not len(c):
+                continue
+            ix = np.maximum(0, np.minimum(c[:, 2], r[2]) - np.maximum(c[:, 0], r[0]))
+            iy = np.maximum(0, np.minimum(c[:, 3], r[3]) - np.maximum(c[:, 1], r[1]))
+            inter = ix * iy
+            iou = inter / ((c[:, 2] - c[:, 0]) * (c[:, 3] - c[:, 1]) + (r[2] - r[0]) * (r[3] - r[1]) - inter)
+            j = int(iou.argmax())
+            if iou[j] >= 0.99 and abs(c[j, 4] - r[4]) <= 1e-2:
+                matched += 1
+    # bf16 can flip candidates sitting within 1e-2 of the conf threshold or reorder near-tied NMS decisions
+    assert matched >= 0.9 * total, (matched, total)
+
+
+def test_graph_replay_equals_eager():
+    g = _graph("yolo11n")
+    x = torch.from_numpy(np.random.default_rng(2).random((2, 3, 96, 96), dtype=np.float32))
+    a = _run_engine(g, x, use_graph=False).y.clone()
+    e = _run_engine(g, x, use_graph=True)
+    e.forward()
+    torch.cuda.synchronize()
+    assert torch.equal(a, e.y)
