@@ -121,7 +121,7 @@ class Engine:
             A.check(self.lib.b2y_plan_graph_launch(self.handle, st))
         else:
             A.check(self.lib.b2y_plan_run(self.handle, 0, -1, st))
-        return self.y
+        return self.y if self.plan.y_buf >= 0 else None
 
     def run_ops(self, first: int, last: int):
         A.check(self.lib.b2y_plan_run(self.handle, first, last, self._stream()))

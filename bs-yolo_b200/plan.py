@@ -119,7 +119,7 @@ class Plan:
         self.nc = ir["nc"]
         self.layer_out: dict[int, View] = {}
         self.layer_op_range: dict[int, tuple[int, int]] = {}
-        self.input_buf = self.new_buf(4, H, W, name="input_rgb0")
+        self.input_buf = self.new_buf(4, H, W, name="input_rgb0", exact=True)  # 8-byte pixels (R,G,B,0)
         self.head_bufs: list[int] = []
         self.y_buf = -1
         self.A = 0
@@ -132,8 +132,8 @@ class Plan:
         return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32)
 
     # ------------------------------------------------------------------ buffers / views
-    def new_buf(self, C, H, W, dtype=A.BF16, name="") -> int:
-        self.bufs.append(BufSpec(_r(C, 8) if dtype == A.BF16 else C, H, W, dtype, name))
+    def new_buf(self, C, H, W, dtype=A.BF16, name="", exact=False) -> int:
+        self.bufs.append(BufSpec(_r(C, 8) if (dtype == A.BF16 and not exact) else C, H, W, dtype, name))
         return len(self.bufs) - 1
 
     def full(self, buf: int, c: int | None = None) -> View:
