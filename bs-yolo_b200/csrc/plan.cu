@@ -287,18 +287,29 @@ extern "C" int b2y_plan_run(b2y_plan *pl, int32_t first, int32_t last, void *str
 
 extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "graph_build: null plan");
-  cudaStream_t st = (cudaStream_t)stream;
+  (void)stream;  // capture happens on a private stream: the caller's may be the legacy default stream, which cannot capture
   if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
   if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
-  B2Y_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  const int rc = b2y_plan_run(pl, 0, -1, stream);
+  cudaStream_t st = nullptr;
+  B2Y_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(st);
+    b2y_set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+    return B2Y_ERR_CUDA;
+  }
+  const int rc = b2y_plan_run(pl, 0, -1, st);
   cudaGraph_t g = nullptr;
-  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  e = cudaStreamEndCapture(st, &g);
+  cudaStreamDestroy(st);
   if (rc != B2Y_OK) {
     if (g) cudaGraphDestroy(g);
     return rc;
   }
-  B2Y_CUDA_CHECK(e);
+  if (e != cudaSuccess) {
+    b2y_set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    return B2Y_ERR_CUDA;
+  }
   pl->graph = g;
   B2Y_CUDA_CHECK(cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
   return B2Y_OK;
