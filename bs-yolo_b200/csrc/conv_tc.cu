@@ -2,43 +2,51 @@
 //   D[pixels, cout] = sum over taps (r,s) and channel chunks of  A_tap[pixels, BK] * W[cout, tap*cin + chunk]^T
 //
 //   * A operand: NHWC bf16 activations fetched by TMA straight out of the (possibly channel-sliced) activation
-//     buffer.  One box {BK channels, TW, TH, 1 image} per filter tap, shifted by the tap offset; out-of-bounds
-//     coordinates are zero-filled by the TMA unit, which *is* the "same" padding (conv.py:29-35 autopad).  No im2col
-//     buffer exists anywhere.  Stride-2 3x3 convs view the input as {2*Cs, W/2, 2, H/2, B} so that every tap is
-//     again a dense box (row/column parity selects the sub-lattice) -- no element strides, no gather.
-//   * B operand: BN-folded weights packed [cout_pad][kh*kw*cin] bf16 (K-major), one box {BK, BN} per k-step.
-//   * Both land in shared memory in the canonical K-major swizzled layout (128B/64B/32B swizzle chosen by BK) that
-//     tcgen05.mma consumes through shared-memory descriptors; accumulators (128 lanes x BN fp32 columns, double
-//     buffered) live in TMEM.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator, warps 2..5 =
-//     epilogue (tcgen05.ld -> +bias -> SiLU -> residual add|mul -> bf16|fp32 -> global channel slice).  Three
-//     mbarrier pipelines: smem full/empty, TMEM full/empty.  Persistent CTAs walk the tile list.
+//     buffer, ONE halo box per (tile, channel chunk): {BK channels, TW+2, TH+2} for 3x3 s1, {BK, TW, TH} for 1x1.
+//     Out-of-bounds coordinates are zero-filled by the TMA unit, which *is* the "same" padding (conv.py:29-35).
+//     The nine taps are not nine loads: they are nine *shifted shared-memory descriptors* over the same halo tile.
+//     Accumulator row m corresponds to halo pixel (m / P, m % P) with pitch P = TW+2, so tap (r,s) is the operand
+//     starting r*P+s rows further down; the P-TW garbage columns per row are simply not stored.  Stride-2 3x3 convs
+//     view the input as {2*Cs, W/2, 2, H/2, B}: four parity planes, each a dense halo box, each tap = (plane, shift).
+//     No im2col buffer, no gather, L2->SM traffic ~1.4x the input instead of 9x.
+//   * B operand: BN-folded weights packed [cout_pad][kh*kw*cin] bf16 (K-major).  When the whole matrix fits it is
+//     loaded ONCE per persistent CTA and stays resident in shared memory; otherwise it is streamed per (chunk, tap).
+//   * Both operands sit in shared memory in the canonical K-major swizzled layout (128B/64B/32B swizzle by BK) that
+//     tcgen05.mma consumes through shared-memory descriptors (row-shifted views are plain start-address offsets);
+//     accumulators (128 lanes x BN fp32 columns, double buffered) live in TMEM.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM allocator, warps 2..9 = epilogue
+//     (tcgen05.ld -> +bias -> SiLU -> residual add|mul -> bf16|fp32 -> global channel slice; two warps per TMEM
+//     lane quadrant split the columns).  mbarrier pipelines: A full/empty, B full/empty (or one "weights resident"
+//     barrier), TMEM full/empty.  Persistent CTAs walk the tile list.
 // Reference semantics: ultralytics/nn/modules/conv.py:145-151 (act(bn(conv(x))), BN folded per
 // utils/torch_utils.py:242-269), residuals of Bottleneck (block.py:3416-3419), PSABlock (:4379-4383), MSCA (:88).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kNumThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
 
 struct TcGeom {
   int B, Ho, Wo, cin, cout, cout_pad;
-  int taps_w, taps;            // kw, kh*kw
-  int ph, pw;                  // padding (stride 1) ; for stride 2 fixed 3x3 p1
-  int stride2;                 // 0: 4-D map, 1: 5-D parity map
-  int in_cs;                   // needed for the parity offset in the merged (wp, c) dimension
-  int BK, nkc, kiters;         // channel chunk, chunks per tap, taps*nkc
-  int TH, TW, tiles_h, tiles_w, tiles_per_img;
+  int taps, nplanes, stride2, in_cs;
+  int BK, nkc;
+  int TH, TW, P, tiles_h, tiles_w;
   int BN, n_ntiles;
   long long ntiles;
-  int stages, a_bytes, b_bytes, tx_bytes;
+  int sa, sb, resident;                 // A stages, B stages (streamed), weights resident flag
+  int plane_bytes, a_stage_bytes, a_tx_bytes, b_tile_bytes, b_tx_bytes, w_bytes_tx;
+  int row_bytes;
+  int tap_plane[9], tap_shift[9];       // tap -> (parity plane, row shift inside the halo tile)
   int tmem_cols;
-  unsigned long long desc_hi;  // descriptor bits [32,64): SBO, version, layout type
+  unsigned desc_hi;                     // descriptor bits [32,64): SBO, version, layout type (base_offset added per use)
   unsigned idesc;
+  int ox, oy;                           // halo origin offsets: TMA coordinate = tile origin - (ox, oy)
   // epilogue
   void *out; int out_cs, out_f32;
   const bf16 *res; int res_cs, res_mode;
@@ -120,27 +128,51 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// SiLU with one MUFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2  (tanh.approx rel. error ~2^-11 << bf16 epsilon)
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// K-major swizzled smem descriptor for an operand starting at byte address `addr`: any 16-byte-aligned row of a tile
+// whose base is aligned to the swizzle repeat.  Measured on B200: the swizzle XOR is applied to the absolute shared
+// memory address bits (exactly like the TMA write side), so row-shifted views need NO base_offset (bits [49,52) = 0);
+// setting base_offset = (addr >> 7) & 7 for shifted starts produces garbage (profiles/r01_notes.md).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t desc_hi) {
+  const uint32_t hi = desc_hi;
+  return ((uint64_t)hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((addr & 0x3FFFFu) >> 4);
+}
+
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 5];
   __shared__ uint32_t tmem_base_smem;
 
-  // dynamic smem base rounded up to 1024 B (swizzle atoms need it)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * kMaxStages]), tempty0 = smem_u32(&bars[2 * kMaxStages + 2]);
+  const uint32_t fullA = smem_u32(&bars[0]), emptyA = smem_u32(&bars[kMaxStages]);
+  const uint32_t fullB = smem_u32(&bars[2 * kMaxStages]), emptyB = smem_u32(&bars[3 * kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[4 * kMaxStages]), tempty0 = smem_u32(&bars[4 * kMaxStages + 2]);
+  const uint32_t wfull = smem_u32(&bars[4 * kMaxStages + 4]);
+  // smem carve-up: [A ring: sa stages][B: resident weights (taps*nkc tiles) | ring of sb tiles]
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)(g.sa * g.a_stage_bytes);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(fullA + 8 * s, 1);
+      mbar_init(emptyA + 8 * s, 1);
+      mbar_init(fullB + 8 * s, 1);
+      mbar_init(emptyB + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, 128);
+      mbar_init(tempty0 + 8 * s, 32 * kEpiWarps);
     }
+    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -154,15 +186,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
-  const uint32_t stage_bytes = (uint32_t)(g.a_bytes + g.b_bytes);
-
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
+      if (g.resident) {
+        mbar_expect_tx(wfull, (uint32_t)g.w_bytes_tx);
+        for (int t = 0; t < g.taps * g.nkc; ++t) tma_load_2d(b_base + t * g.b_tile_bytes, &tmB, wfull, t * g.BK, 0);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
         const int nt = (int)(tile % g.n_ntiles);
         long long sp = tile / g.n_ntiles;
@@ -170,56 +204,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sp /= g.tiles_w;
         const int th_i = (int)(sp % g.tiles_h);
         const int b = (int)(sp / g.tiles_h);
-        const int h0 = th_i * g.TH, w0 = tw_i * g.TW, n0 = nt * g.BN;
-        for (int kit = 0; kit < g.kiters; ++kit) {
-          const int tap = kit / g.nkc, c0 = (kit - tap * g.nkc) * g.BK;
-          const int r = tap / g.taps_w, s = tap - r * g.taps_w;
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * stage_bytes, b_dst = a_dst + g.a_bytes;
-          mbar_expect_tx(full0 + 8 * stage, (uint32_t)g.tx_bytes);
+        const int h0 = th_i * g.TH - g.oy, w0 = tw_i * g.TW - g.ox, n0 = nt * g.BN;
+        for (int kc = 0; kc < g.nkc; ++kc) {
+          const int c0 = kc * g.BK;
+          mbar_wait(emptyA + 8 * sa, pha ^ 1);
+          const uint32_t dst = a_base + sa * g.a_stage_bytes;
+          mbar_expect_tx(fullA + 8 * sa, (uint32_t)g.a_tx_bytes);
           if (!g.stride2) {
-            tma_load_4d(a_dst, &tmA, full0 + 8 * stage, c0, w0 + s - g.pw, h0 + r - g.ph, b);
+            tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, b);
           } else {
-            const int wpar = (s == 1) ? 0 : 1, hpar = (r == 1) ? 0 : 1;
-            tma_load_5d(a_dst, &tmA, full0 + 8 * stage, wpar * g.in_cs + c0, w0 + (s == 0 ? -1 : 0), hpar,
-                        h0 + (r == 0 ? -1 : 0), b);
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl)
+              tma_load_5d(dst + pl * g.plane_bytes, &tmA, fullA + 8 * sa, (pl & 1) * g.in_cs + c0, w0, pl >> 1, h0, b);
           }
-          tma_load_2d(b_dst, &tmB, full0 + 8 * stage, kit * g.BK, n0);
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          if (++sa == g.sa) { sa = 0; pha ^= 1; }
+          if (!g.resident) {
+            for (int tap = 0; tap < g.taps; ++tap) {
+              mbar_wait(emptyB + 8 * sb, phb ^ 1);
+              mbar_expect_tx(fullB + 8 * sb, (uint32_t)g.b_tx_bytes);
+              tma_load_2d(b_base + sb * g.b_tile_bytes, &tmB, fullB + 8 * sb, tap * g.cin + c0, n0);
+              if (++sb == g.sb) { sb = 0; phb ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t aphase = 0;
+    int sa = 0, sb = 0, as = 0;
+    uint32_t pha = 0, phb = 0, aphase = 0;
+    if (g.resident) {
+      mbar_wait(wfull, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * g.BN);
-      for (int kit = 0; kit < g.kiters; ++kit) {
-        mbar_wait(full0 + 8 * stage, phase);
+      for (int kc = 0; kc < g.nkc; ++kc) {
+        mbar_wait(fullA + 8 * sa, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_stage = a_base + sa * g.a_stage_bytes;
+        for (int tap = 0; tap < g.taps; ++tap) {
+          uint32_t b_addr;
+          if (g.resident) {
+            b_addr = b_base + (tap * g.nkc + kc) * g.b_tile_bytes;
+          } else {
+            mbar_wait(fullB + 8 * sb, phb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            b_addr = b_base + sb * g.b_tile_bytes;
+          }
+          if (lane == 0) {
+            const uint32_t a_addr = a_stage + g.tap_plane[tap] * g.plane_bytes + g.tap_shift[tap] * g.row_bytes;
+            for (int k = 0; k < g.BK / 16; ++k)
+              umma_bf16(tmem_d, make_desc(a_addr + 32 * k, g.desc_hi), make_desc(b_addr + 32 * k, g.desc_hi), g.idesc,
+                        (kc | tap | k) != 0);
+            if (!g.resident) umma_commit(emptyB + 8 * sb);
+          }
+          __syncwarp();
+          if (!g.resident) {
+            if (++sb == g.sb) { sb = 0; phb ^= 1; }
+          }
+        }
         if (lane == 0) {
-          const uint32_t a_addr = smem_base + stage * stage_bytes, b_addr = a_addr + g.a_bytes;
-          const uint64_t da = ((uint64_t)g.desc_hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-          const uint64_t db = ((uint64_t)g.desc_hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
-          for (int k = 0; k < g.BK / 16; ++k)
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), g.idesc, (kit | k) != 0);
-          umma_commit(empty0 + 8 * stage);                       // frees the smem slot when the MMAs retire
-          if (kit == g.kiters - 1) umma_commit(tfull0 + 8 * as);  // accumulator complete
+          umma_commit(emptyA + 8 * sa);                        // frees the halo tile when the MMAs retire
+          if (kc == g.nkc - 1) umma_commit(tfull0 + 8 * as);   // accumulator complete
         }
         __syncwarp();
-        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        if (++sa == g.sa) { sa = 0; pha ^= 1; }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quadrant warp % 4)
-    const int quad = warp & 3;
-    const int m = quad * 32 + lane;  // accumulator row == pixel within the tile
+    // ===================================================== epilogue: 8 warps, two per TMEM lane quadrant (warp % 4)
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;  // accumulator row == halo pixel index within the tile
+    const int th = m / g.P, tw = m - th * g.P;
     int as = 0;
     uint32_t aphase = 0;
     for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
@@ -229,21 +289,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sp /= g.tiles_w;
       const int th_i = (int)(sp % g.tiles_h);
       const int b = (int)(sp / g.tiles_h);
-      const int ho = th_i * g.TH + m / g.TW, wo = tw_i * g.TW + m % g.TW, n0 = nt * g.BN;
-      const bool valid = (m < g.TH * g.TW) && ho < g.Ho && wo < g.Wo;
+      const int ho = th_i * g.TH + th, wo = tw_i * g.TW + tw, n0 = nt * g.BN;
+      const bool valid = (th < g.TH) && (tw < g.TW) && ho < g.Ho && wo < g.Wo;
       const size_t pix = ((size_t)b * g.Ho + ho) * g.Wo + wo;
       mbar_wait(tfull0 + 8 * as, aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * g.BN);
-      for (int col = 0; col < g.BN; col += 16) {
+      for (int col = half * 16; col < g.BN; col += 32) {
         float v[16];
         tmem_ld16(taddr + col, v);  // warp-collective: executed by every lane, valid or not
         const int n = n0 + col;
         if (!valid || n >= g.cout) continue;
+        if (n + 16 <= g.cout_pad) {
+          const float4 *bp = reinterpret_cast<const float4 *>(g.bias + n);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = v[j] + __ldg(g.bias + min(n + j, g.cout_pad - 1));
-          v[j] = g.act ? silu_f(x) : x;
+          for (int j = 0; j < 4; ++j) {
+            const float4 bb = __ldg(bp + j);
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+        }
+        if (g.act) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
         }
         if (g.vec_ok && n + 16 <= g.cout) {
           if (g.res_mode) {
@@ -307,6 +374,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
 }  // namespace
 
 struct ConvTcPlan {
@@ -341,45 +410,84 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   B2Y_REQUIRE(encode != nullptr, B2Y_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   ConvTcPlan *pl = new ConvTcPlan();
   TcGeom &g = pl->g;
+  memset(&g, 0, sizeof(g));
   g.B = p.B; g.Ho = p.Ho; g.Wo = p.Wo; g.cin = p.cin; g.cout = p.cout; g.cout_pad = p.cout_pad;
-  g.taps_w = p.kw; g.taps = p.kh * p.kw; g.ph = p.ph; g.pw = p.pw; g.stride2 = (p.sh == 2); g.in_cs = p.in_cs;
+  g.taps = p.kh * p.kw; g.stride2 = (p.sh == 2); g.in_cs = p.in_cs;
+  g.nplanes = g.stride2 ? 4 : 1;
   g.BK = (p.cin % 64 == 0) ? 64 : (p.cin % 32 == 0) ? 32 : 16;
   g.nkc = p.cin / g.BK;
-  g.kiters = g.taps * g.nkc;
-  // spatial tile: TH x TW <= 128 output pixels, maximising useful rows per 128-row MMA
+  g.row_bytes = g.BK * 2;
+  const int halo = (p.kh == 3) ? (g.stride2 ? 1 : 2) : 0;  // extra halo columns/rows per tile
+  g.ox = g.oy = (p.kh == 3) ? 1 : 0;
+  // spatial tile: accumulator rows m = th*P + tw, P = TW + halo; maximise useful rows per 128-row MMA
   {
     double best = -1.0;
     int bth = 1, btw = 1;
-    for (int tw = 1; tw <= (p.Wo < 128 ? p.Wo : 128); ++tw) {
-      int th = 128 / tw;
+    for (int tw = 1; tw <= (p.Wo < 128 - halo ? p.Wo : 128 - halo); ++tw) {
+      const int P = tw + halo;
+      int th = (128 - tw) / P + 1;  // (th-1)*P + tw <= 128
       if (th > p.Ho) th = p.Ho;
-      if (th < 1) continue;
+      if (th < 1 || th + halo > 256 || P > 256) continue;
       const double eff = (double)p.Ho * p.Wo / ((double)ceil_div(p.Ho, th) * ceil_div(p.Wo, tw) * 128.0);
-      const double score = eff - 1e-4 * (tw > th ? tw - th : th - tw) / 128.0 + ((tw % 8 == 0) ? 1e-5 : 0.0);
+      const double amp = (double)(th + halo) * P / ((double)th * tw);  // halo read amplification
+      const double score = eff - 0.02 * amp;
       if (score > best) { best = score; bth = th; btw = tw; }
     }
-    g.TH = bth; g.TW = btw;
+    g.TH = bth; g.TW = btw; g.P = btw + halo;
   }
   g.tiles_h = ceil_div(p.Ho, g.TH); g.tiles_w = ceil_div(p.Wo, g.TW);
-  g.tiles_per_img = g.tiles_h * g.tiles_w;
   g.n_ntiles = ceil_div(p.cout_pad, 256);
   g.BN = ceil_div(ceil_div(p.cout_pad, g.n_ntiles), 16) * 16;
-  g.ntiles = (long long)p.B * g.tiles_per_img * g.n_ntiles;
-  g.a_bytes = 128 * g.BK * 2;
-  g.b_bytes = ((g.BN * g.BK * 2) + 1023) / 1024 * 1024;
-  g.tx_bytes = g.TH * g.TW * g.BK * 2 + g.BN * g.BK * 2;
-  const int stage_bytes = g.a_bytes + g.b_bytes;
-  int stages = (176 * 1024) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) stages = 2;
-  g.stages = stages;
+  g.ntiles = (long long)p.B * g.tiles_h * g.tiles_w * g.n_ntiles;
+  // tap table
+  int max_shift = 0;
+  for (int r = 0; r < p.kh; ++r)
+    for (int s = 0; s < p.kw; ++s) {
+      const int t = r * p.kw + s;
+      if (p.kh == 1) { g.tap_plane[t] = 0; g.tap_shift[t] = 0; }
+      else if (!g.stride2) { g.tap_plane[t] = 0; g.tap_shift[t] = r * g.P + s; }
+      else {
+        g.tap_plane[t] = ((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1);
+        g.tap_shift[t] = ((r == 0) ? 0 : 1) * g.P + ((s == 0) ? 0 : 1);
+      }
+      if (g.tap_shift[t] > max_shift) max_shift = g.tap_shift[t];
+    }
+  const int box_rows = (g.TH + halo) * g.P;
+  const int rows_alloc = (box_rows > max_shift + 128) ? box_rows : (max_shift + 128);
+  g.plane_bytes = round_up(rows_alloc * g.row_bytes, 1024);
+  g.a_stage_bytes = g.nplanes * g.plane_bytes;
+  g.a_tx_bytes = g.nplanes * box_rows * g.row_bytes;
+  g.b_tile_bytes = round_up(g.BN * g.row_bytes, 1024);
+  g.b_tx_bytes = g.BN * g.row_bytes;
+  const int w_tiles = g.taps * g.nkc;
+  const long long w_res_bytes = (long long)w_tiles * g.b_tile_bytes;
+  const int budget = 200 * 1024;
+  g.resident = (g.n_ntiles == 1 && w_res_bytes + 2 * g.a_stage_bytes <= budget - 8 * 1024) ? 1 : 0;
+  g.w_bytes_tx = w_tiles * g.b_tx_bytes;
+  int b_bytes_total;
+  if (g.resident) {
+    g.sb = 0;
+    b_bytes_total = (int)w_res_bytes;
+  } else {
+    g.sb = 4;
+    b_bytes_total = g.sb * g.b_tile_bytes;
+    while (g.sb > 2 && b_bytes_total + 2 * g.a_stage_bytes > budget) { --g.sb; b_bytes_total = g.sb * g.b_tile_bytes; }
+  }
+  int sa = (budget - b_bytes_total) / g.a_stage_bytes;
+  if (sa > 4) sa = 4;
+  if (sa > kMaxStages) sa = kMaxStages;
+  if (sa < 1) {
+    delete pl;
+    b2y_set_error("tcgen05 conv: tile does not fit shared memory (A stage %d B, B %d B)", g.a_stage_bytes, b_bytes_total);
+    return B2Y_ERR_UNSUPPORTED;
+  }
+  g.sa = sa;
   int cols = 32;
   while (cols < 2 * g.BN) cols <<= 1;
   g.tmem_cols = cols;
-  const int row_bytes = g.BK * 2;
-  const unsigned layout = (row_bytes == 128) ? 2u : (row_bytes == 64) ? 4u : 6u;  // UMMA LayoutType SW128/SW64/SW32
-  const unsigned sbo = (unsigned)(8 * row_bytes) >> 4;
-  g.desc_hi = (unsigned long long)sbo | (1ull << 14) | ((unsigned long long)layout << 29);  // bits [32,46) [46,48) [61,64)
+  const unsigned layout = (g.row_bytes == 128) ? 2u : (g.row_bytes == 64) ? 4u : 6u;  // UMMA LayoutType SW128/SW64/SW32
+  const unsigned sbo = (unsigned)(8 * g.row_bytes) >> 4;
+  g.desc_hi = sbo | (1u << 14) | (layout << 29);  // bits [32,46) SBO, [46,48) version=1, [61,64) layout
   g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(g.BN >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
   g.out = p.out; g.out_cs = p.out_cs; g.out_f32 = p.out_f32;
   g.res = p.res; g.res_cs = p.res_cs; g.res_mode = p.res_mode;
@@ -391,16 +499,16 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
     g.vec_ok = ok ? 1 : 0;
   }
 
-  const CUtensorMapSwizzle sw = (row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : (row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                    : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUtensorMapSwizzle sw = (g.row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (g.row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r;
   if (!g.stride2) {
     const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.in_cs * 2, (cuuint64_t)p.W * p.in_cs * 2,
                                    (cuuint64_t)p.H * p.W * p.in_cs * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)g.BK, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)g.BK, (cuuint32_t)g.P, (cuuint32_t)(g.TH + halo), 1};
     r = encode(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16 *>(p.in), dims, strides, box, ones,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
@@ -408,7 +516,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
                                 (cuuint64_t)p.B};
     const cuuint64_t strides[4] = {(cuuint64_t)2 * p.in_cs * 2, (cuuint64_t)p.W * p.in_cs * 2,
                                    (cuuint64_t)2 * p.W * p.in_cs * 2, (cuuint64_t)p.H * p.W * p.in_cs * 2};
-    const cuuint32_t box[5] = {(cuuint32_t)g.BK, (cuuint32_t)g.TW, 1, (cuuint32_t)g.TH, 1};
+    const cuuint32_t box[5] = {(cuuint32_t)g.BK, (cuuint32_t)g.P, 1, (cuuint32_t)(g.TH + halo), 1};
     r = encode(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16 *>(p.in), dims, strides, box, ones,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -429,14 +537,15 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
     b2y_set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
     return B2Y_ERR_CUDA;
   }
-  pl->smem = (size_t)stages * stage_bytes + 1024;
+  pl->smem = (size_t)g.sa * g.a_stage_bytes + b_bytes_total + 1024;
   cudaDeviceProp prop;
   B2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-  const long long max_ctas = prop.multiProcessorCount;
+  const int per_sm = (pl->smem <= 100 * 1024 && g.tmem_cols <= 256) ? 2 : 1;
+  const long long max_ctas = (long long)prop.multiProcessorCount * per_sm;
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
   static bool attr_done = false;
   if (!attr_done) {
-    B2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_done = true;
   }
   *out = pl;
