@@ -30,7 +30,7 @@ namespace {
 constexpr int kEpiWarps = 8;
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
-constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;  // ~2 s: trap instead of hanging the GPU
+constexpr unsigned kWaitSpinLimit = 1u << 26;  // failed try_wait polls before trapping (seconds), never reached when healthy
 
 struct TcGeom {
   int B, Ho, Wo, cin, cout, cout_pad;
@@ -52,6 +52,11 @@ struct TcGeom {
   const bf16 *res; int res_cs, res_mode;
   const float *bias;
   int act, vec_ok;
+  // tile decode by multiply-shift (tile ids < 2^31)
+  unsigned dv_nt_mul, dv_nt_shr, dv_tw_mul, dv_tw_shr, dv_th_mul, dv_th_shr;
+  // bf16 outputs leave through shared memory + TMA store
+  int tma_out, oc, n_oboxes, obox_bytes, o_row_bytes, o_sw_mask, o_stages, o_stage_bytes;
+  int o_off, bias_off;                  // byte offsets of the output staging area / bias table in dynamic smem
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,8 +71,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const unsigned long long t0 = clock64();
+  uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -77,8 +81,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > kWaitTimeoutCycles) __trap();
+    if (++spins > kWaitSpinLimit) __trap();  // a broken pipeline must fault, not hang the GPU
   }
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
+  return mul ? (__umulhi(n, mul) >> shr) : n;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
@@ -135,6 +151,12 @@ __device__ __forceinline__ float silu_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// same, for a pre-halved argument h = (x + bias) / 2
+__device__ __forceinline__ float silu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // K-major swizzled smem descriptor for an operand starting at byte address `addr`: any 16-byte-aligned row of a tile
 // whose base is aligned to the swizzle repeat.  Measured on B200: the swizzle XOR is applied to the absolute shared
@@ -145,21 +167,39 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t desc_hi) {
   return ((uint64_t)hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((addr & 0x3FFFFu) >> 4);
 }
 
+struct TileCoord {
+  int b, th_i, tw_i, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcGeom &g, uint32_t tile) {
+  TileCoord t;
+  uint32_t sp = fast_div(tile, g.dv_nt_mul, g.dv_nt_shr);
+  t.nt = (int)(tile - sp * g.n_ntiles);
+  uint32_t q = fast_div(sp, g.dv_tw_mul, g.dv_tw_shr);
+  t.tw_i = (int)(sp - q * g.tiles_w);
+  const uint32_t q2 = fast_div(q, g.dv_th_mul, g.dv_th_shr);
+  t.th_i = (int)(q - q2 * g.tiles_h);
+  t.b = (int)q2;
+  return t;
+}
+
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGeom g) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 5];
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t fullA = smem_u32(&bars[0]), emptyA = smem_u32(&bars[kMaxStages]);
   const uint32_t fullB = smem_u32(&bars[2 * kMaxStages]), emptyB = smem_u32(&bars[3 * kMaxStages]);
   const uint32_t tfull0 = smem_u32(&bars[4 * kMaxStages]), tempty0 = smem_u32(&bars[4 * kMaxStages + 2]);
   const uint32_t wfull = smem_u32(&bars[4 * kMaxStages + 4]);
-  // smem carve-up: [A ring: sa stages][B: resident weights (taps*nkc tiles) | ring of sb tiles]
+  // smem carve-up: [A ring: sa stages][B: resident weights (taps*nkc tiles) | ring of sb tiles][out staging][bias]
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)(g.sa * g.a_stage_bytes);
+  float *bias_s = reinterpret_cast<float *>(smem_gen + g.bias_off);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
@@ -175,6 +215,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // bias table (pre-halved when the activation is SiLU: silu(x+b) = h + h*tanh(h), h = 0.5x + 0.5b)
+  for (int i = threadIdx.x; i < g.cout_pad; i += kNumThreads) bias_s[i] = g.act ? 0.5f * g.bias[i] : g.bias[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                  "r"((uint32_t)g.tmem_cols)
@@ -185,6 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t ntiles = (uint32_t)g.ntiles;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -197,25 +240,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
-        const int nt = (int)(tile % g.n_ntiles);
-        long long sp = tile / g.n_ntiles;
-        const int tw_i = (int)(sp % g.tiles_w);
-        sp /= g.tiles_w;
-        const int th_i = (int)(sp % g.tiles_h);
-        const int b = (int)(sp / g.tiles_h);
-        const int h0 = th_i * g.TH - g.oy, w0 = tw_i * g.TW - g.ox, n0 = nt * g.BN;
+      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        const int h0 = tc.th_i * g.TH - g.oy, w0 = tc.tw_i * g.TW - g.ox, n0 = tc.nt * g.BN;
         for (int kc = 0; kc < g.nkc; ++kc) {
           const int c0 = kc * g.BK;
           mbar_wait(emptyA + 8 * sa, pha ^ 1);
           const uint32_t dst = a_base + sa * g.a_stage_bytes;
           mbar_expect_tx(fullA + 8 * sa, (uint32_t)g.a_tx_bytes);
           if (!g.stride2) {
-            tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, b);
+            tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, tc.b);
           } else {
 #pragma unroll
             for (int pl = 0; pl < 4; ++pl)
-              tma_load_5d(dst + pl * g.plane_bytes, &tmA, fullA + 8 * sa, (pl & 1) * g.in_cs + c0, w0, pl >> 1, h0, b);
+              tma_load_5d(dst + pl * g.plane_bytes, &tmA, fullA + 8 * sa, (pl & 1) * g.in_cs + c0, w0, pl >> 1, h0, tc.b);
           }
           if (++sa == g.sa) { sa = 0; pha ^= 1; }
           if (!g.resident) {
@@ -237,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(wfull, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * g.BN);
@@ -256,9 +294,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (lane == 0) {
             const uint32_t a_addr = a_stage + g.tap_plane[tap] * g.plane_bytes + g.tap_shift[tap] * g.row_bytes;
+            const uint64_t da = make_desc(a_addr, g.desc_hi), db = make_desc(b_addr, g.desc_hi);
             for (int k = 0; k < g.BK / 16; ++k)
-              umma_bf16(tmem_d, make_desc(a_addr + 32 * k, g.desc_hi), make_desc(b_addr + 32 * k, g.desc_hi), g.idesc,
-                        (kc | tap | k) != 0);
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), g.idesc, (kc | tap | k) != 0);
             if (!g.resident) umma_commit(emptyB + 8 * sb);
           }
           __syncwarp();
@@ -280,72 +318,115 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;  // accumulator row == halo pixel index within the tile
     const int th = m / g.P, tw = m - th * g.P;
-    int as = 0;
+    const bool row_ok = (th < g.TH) && (tw < g.TW);
+    const uint32_t rr = (uint32_t)(th * g.TW + tw);  // row in the compacted output tile (garbage halo columns dropped)
+    const bool elected = (threadIdx.x == 64);
+    const uint32_t o_base = smem_base + (uint32_t)g.o_off;
+    const int nchunks = g.BN >> 4;
+    int as = 0, os = 0;
     uint32_t aphase = 0;
-    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
-      const int nt = (int)(tile % g.n_ntiles);
-      long long sp = tile / g.n_ntiles;
-      const int tw_i = (int)(sp % g.tiles_w);
-      sp /= g.tiles_w;
-      const int th_i = (int)(sp % g.tiles_h);
-      const int b = (int)(sp / g.tiles_h);
-      const int ho = th_i * g.TH + th, wo = tw_i * g.TW + tw, n0 = nt * g.BN;
-      const bool valid = (th < g.TH) && (tw < g.TW) && ho < g.Ho && wo < g.Wo;
-      const size_t pix = ((size_t)b * g.Ho + ho) * g.Wo + wo;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(g, tile);
+      const int ho = tc.th_i * g.TH + th, wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
+      const bool valid = row_ok && ho < g.Ho && wo < g.Wo;
+      const size_t pix = ((size_t)tc.b * g.Ho + ho) * g.Wo + wo;
       mbar_wait(tfull0 + 8 * as, aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (g.tma_out) {
+        // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
+        if (elected) {
+          if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        named_bar_sync(1, 32 * kEpiWarps);
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * g.BN);
-      for (int col = half * 16; col < g.BN; col += 32) {
+      const uint32_t o_stage = o_base + (uint32_t)(os * g.o_stage_bytes);
+      for (int c = half; c < nchunks; c += 2) {
         float v[16];
-        tmem_ld16(taddr + col, v);  // warp-collective: executed by every lane, valid or not
-        const int n = n0 + col;
-        if (!valid || n >= g.cout) continue;
-        if (n + 16 <= g.cout_pad) {
-          const float4 *bp = reinterpret_cast<const float4 *>(g.bias + n);
+        tmem_ld16(taddr + c * 16, v);  // warp-collective: executed by every lane, valid or not
+        const int col = c * 16, n = n0 + col;
+        if (n >= g.cout) continue;  // warp-uniform
+        const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n);
+        if (g.act) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 bb = __ldg(bp + j);
+            const float4 hb = bp[j];
+            v[4 * j] = silu_half(fmaf(v[4 * j], 0.5f, hb.x));
+            v[4 * j + 1] = silu_half(fmaf(v[4 * j + 1], 0.5f, hb.y));
+            v[4 * j + 2] = silu_half(fmaf(v[4 * j + 2], 0.5f, hb.z));
+            v[4 * j + 3] = silu_half(fmaf(v[4 * j + 3], 0.5f, hb.w));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bb = bp[j];
             v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
           }
         }
-        if (g.act) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
-        }
-        if (g.vec_ok && n + 16 <= g.cout) {
-          if (g.res_mode) {
+        const bool full16 = (n + 16 <= g.cout);
+        if (g.res_mode && valid) {
+          if (g.vec_ok && full16) {
             const uint4 *rp = reinterpret_cast<const uint4 *>(g.res + pix * g.res_cs + n);
             float r[16];
-            unpack8(rp[0], r);
-            unpack8(rp[1], r + 8);
+            unpack8(__ldg(rp), r);
+            unpack8(__ldg(rp + 1), r + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (g.res_mode == B2Y_RES_ADD) ? v[j] + r[j] : v[j] * r[j];
-          }
-          if (g.out_f32) {
-            float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.out) + pix * g.out_cs + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(g.out) + pix * g.out_cs + n);
-            op[0] = pack8(v);
-            op[1] = pack8(v + 8);
-          }
-        } else {
-          for (int j = 0; j < 16 && n + j < g.cout; ++j) {
-            float x = v[j];
-            if (g.res_mode) {
+            for (int j = 0; j < 16 && n + j < g.cout; ++j) {
               const float r = __bfloat162float(g.res[pix * g.res_cs + n + j]);
-              x = (g.res_mode == B2Y_RES_ADD) ? x + r : x * r;
+              v[j] = (g.res_mode == B2Y_RES_ADD) ? v[j] + r : v[j] * r;
             }
-            if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + j] = x;
-            else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + j] = __float2bfloat16_rn(x);
+          }
+        }
+        if (g.tma_out) {
+          if (row_ok) {
+            const int bx = col / g.oc, cb = (col - bx * g.oc) * 2;  // box index, byte offset of the chunk in the row
+            uint32_t off = rr * (uint32_t)g.o_row_bytes + (uint32_t)cb;
+            const uint32_t off2 = off + 16;
+            off ^= ((off >> 7) & (uint32_t)g.o_sw_mask) << 4;
+            const uint32_t o2 = off2 ^ (((off2 >> 7) & (uint32_t)g.o_sw_mask) << 4);
+            const uint32_t dst = o_stage + (uint32_t)(bx * g.obox_bytes);
+            const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + off), "r"(p0.x), "r"(p0.y), "r"(p0.z), "r"(p0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o2), "r"(p1.x), "r"(p1.y), "r"(p1.z), "r"(p1.w) : "memory");
+          }
+        } else if (valid) {
+          if (g.vec_ok && full16) {
+            if (g.out_f32) {
+              float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.out) + pix * g.out_cs + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(g.out) + pix * g.out_cs + n);
+              op[0] = pack8(v);
+              op[1] = pack8(v + 8);
+            }
+          } else {
+            for (int j = 0; j < 16 && n + j < g.cout; ++j) {
+              if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + j] = v[j];
+              else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + j] = __float2bfloat16_rn(v[j]);
+            }
           }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(tempty0 + 8 * as);
+      mbar_arrive(tempty0 + 8 * as);  // accumulator stage drained: the MMA warp may overwrite it
       if (++as == 2) { as = 0; aphase ^= 1; }
+      if (g.tma_out) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
+        named_bar_sync(2, 32 * kEpiWarps);
+        if (elected) {
+          for (int bx = 0; bx < g.n_oboxes; ++bx)
+            if (n0 + bx * g.oc < g.cout)
+              tma_store_4d(&tmO, o_stage + (uint32_t)(bx * g.obox_bytes), n0 + bx * g.oc, tc.tw_i * g.TW, tc.th_i * g.TH, tc.b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++os == g.o_stages) os = 0;
+      }
     }
+    if (g.tma_out && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -356,6 +437,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  : "memory");
   }
 }
+
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -376,10 +458,19 @@ EncodeTiledFn get_encode_fn() {
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+void find_div(unsigned d, unsigned &mul, unsigned &shr) {  // n / d == umulhi(n, mul) >> shr for n < 2^31 (mul == 0: d == 1)
+  if (d <= 1) { mul = 0; shr = 0; return; }
+  unsigned lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const unsigned p = 31 + lg;
+  mul = (unsigned)(((1ull << p) + d - 1) / d);
+  shr = p - 32;
+}
+
 }  // namespace
 
 struct ConvTcPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   TcGeom g;
   int grid;
   size_t smem;
@@ -461,8 +552,20 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   g.b_tx_bytes = g.BN * g.row_bytes;
   const int w_tiles = g.taps * g.nkc;
   const long long w_res_bytes = (long long)w_tiles * g.b_tile_bytes;
-  const int budget = 200 * 1024;
-  g.resident = (g.n_ntiles == 1 && w_res_bytes + 2 * g.a_stage_bytes <= budget - 8 * 1024) ? 1 : 0;
+  // bf16 outputs are staged in shared memory and leave through TMA stores (coalesced, clipped, channel-sliced by the
+  // tensor map); fp32 head outputs and unaligned views are stored directly from registers.
+  g.tma_out = (!p.out_f32 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_cs % 8 == 0 && p.cout % 8 == 0) ? 1 : 0;
+  g.oc = g.BN <= 16 ? 16 : (g.BN <= 32 ? 32 : 64);
+  g.n_oboxes = ceil_div(g.BN, g.oc);
+  g.o_row_bytes = g.oc * 2;
+  g.o_sw_mask = g.oc == 64 ? 7 : (g.oc == 32 ? 3 : 1);
+  g.obox_bytes = 128 * g.o_row_bytes;
+  g.o_stages = g.tma_out ? (g.BN <= 128 ? 2 : 1) : 0;
+  g.o_stage_bytes = g.n_oboxes * g.obox_bytes;
+  const int out_bytes = g.o_stages * g.o_stage_bytes;
+  const int bias_bytes = round_up(p.cout_pad * 4, 1024);
+  const int budget = 220 * 1024 - out_bytes - bias_bytes;
+  g.resident = (g.n_ntiles == 1 && w_res_bytes + 2 * g.a_stage_bytes <= budget) ? 1 : 0;
   g.w_bytes_tx = w_tiles * g.b_tx_bytes;
   int b_bytes_total;
   if (g.resident) {
@@ -482,6 +585,16 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
     return B2Y_ERR_UNSUPPORTED;
   }
   g.sa = sa;
+  g.o_off = g.sa * g.a_stage_bytes + b_bytes_total;
+  g.bias_off = g.o_off + out_bytes;
+  find_div((unsigned)g.n_ntiles, g.dv_nt_mul, g.dv_nt_shr);
+  find_div((unsigned)g.tiles_w, g.dv_tw_mul, g.dv_tw_shr);
+  find_div((unsigned)g.tiles_h, g.dv_th_mul, g.dv_th_shr);
+  if (g.ntiles >= (1ll << 31)) {
+    delete pl;
+    b2y_set_error("tcgen05 conv: too many tiles");
+    return B2Y_ERR_UNSUPPORTED;
+  }
   int cols = 32;
   while (cols < 2 * g.BN) cols <<= 1;
   g.tmem_cols = cols;
@@ -537,7 +650,25 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
     b2y_set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
     return B2Y_ERR_CUDA;
   }
-  pl->smem = (size_t)g.sa * g.a_stage_bytes + b_bytes_total + 1024;
+  if (g.tma_out) {
+    const CUtensorMapSwizzle osw = (g.oc == 64) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (g.oc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.out_cs * 2, (cuuint64_t)p.Wo * p.out_cs * 2,
+                                   (cuuint64_t)p.Ho * p.Wo * p.out_cs * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)g.oc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    r = encode(&pl->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.out, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               osw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete pl;
+      b2y_set_error("cuTensorMapEncodeTiled(output) failed with CUresult %d", (int)r);
+      return B2Y_ERR_CUDA;
+    }
+  } else {
+    pl->tmO = pl->tmB;  // unused
+  }
+  pl->smem = (size_t)g.bias_off + bias_bytes + 1024;
   cudaDeviceProp prop;
   B2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   const int per_sm = (pl->smem <= 100 * 1024 && g.tmem_cols <= 256) ? 2 : 1;
@@ -545,7 +676,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
   static bool attr_done = false;
   if (!attr_done) {
-    B2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    B2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_done = true;
   }
   *out = pl;
@@ -555,7 +686,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
 void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
 
 int launch_conv_tc(const ConvTcPlan *pl, cudaStream_t st) {
-  conv_tc_kernel<<<pl->grid, kNumThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->g);
+  conv_tc_kernel<<<pl->grid, kNumThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->tmO, pl->g);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
