@@ -2,49 +2,57 @@
 //   D[pixels, cout] = sum over taps (r,s) and channel chunks of  A_tap[pixels, BK] * W[cout, tap*cin + chunk]^T
 //
 //   * A operand: NHWC bf16 activations fetched by TMA straight out of the (possibly channel-sliced) activation
-//     buffer, ONE halo box per (tile, channel chunk): {BK channels, TW+2, TH+2} for 3x3 s1, {BK, TW, TH} for 1x1.
+//     buffer, ONE halo box per (tile, channel chunk): {BK channels, TW+2, rows+2} for 3x3 s1, {BK, TW, rows} for 1x1.
 //     Out-of-bounds coordinates are zero-filled by the TMA unit, which *is* the "same" padding (conv.py:29-35).
-//     The nine taps are not nine loads: they are nine *shifted shared-memory descriptors* over the same halo tile.
+//     The nine taps are not nine loads: they are nine *row-shifted shared-memory descriptors* over the same halo tile.
 //     Accumulator row m corresponds to halo pixel (m / P, m % P) with pitch P = TW+2, so tap (r,s) is the operand
 //     starting r*P+s rows further down; the P-TW garbage columns per row are simply not stored.  Stride-2 3x3 convs
 //     view the input as {2*Cs, W/2, 2, H/2, B}: four parity planes, each a dense halo box, each tap = (plane, shift).
-//     No im2col buffer, no gather, L2->SM traffic ~1.4x the input instead of 9x.
+//     No im2col buffer, no gather, L2->SM traffic ~1.3x the input instead of 9x.
+//   * A tile is MB stacked 128-row accumulator blocks (MB*TH output rows x TW columns) fed from ONE halo load and
+//     drained by ONE TMA store: the thin, memory-bound layers of yolo11n (16..64 channels on 160x160 / 80x80 maps)
+//     amortise every barrier round trip over MB blocks.
 //   * B operand: BN-folded weights packed [cout_pad][kh*kw*cin] bf16 (K-major).  When the whole matrix fits it is
 //     loaded ONCE per persistent CTA and stays resident in shared memory; otherwise it is streamed per (chunk, tap).
 //   * Both operands sit in shared memory in the canonical K-major swizzled layout (128B/64B/32B swizzle by BK) that
-//     tcgen05.mma consumes through shared-memory descriptors (row-shifted views are plain start-address offsets);
-//     accumulators (128 lanes x BN fp32 columns, double buffered) live in TMEM.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM allocator, warps 2..9 = epilogue
-//     (tcgen05.ld -> +bias -> SiLU -> residual add|mul -> bf16|fp32 -> global channel slice; two warps per TMEM
-//     lane quadrant split the columns).  mbarrier pipelines: A full/empty, B full/empty (or one "weights resident"
-//     barrier), TMEM full/empty.  Persistent CTAs walk the tile list.
+//     tcgen05.mma consumes through shared-memory descriptors (row-shifted views are plain start-address offsets: the
+//     swizzle XOR acts on absolute smem address bits, measured); accumulators (128 lanes x MB*BN fp32 columns, double
+//     buffered) live in TMEM.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane, fully unrolled descriptor arithmetic) + TMEM
+//     allocator, warps 2..9 = epilogue (tcgen05.ld -> +bias -> SiLU -> residual add|mul -> bf16 into a swizzled smem
+//     staging tile -> TMA store into the output channel slice; fp32 head outputs are stored from registers).
+//     mbarrier pipelines: A full/empty, B full/empty (or one "weights resident" barrier), TMEM full/empty.
+//     Persistent CTAs walk the tile list.
 // Reference semantics: ultralytics/nn/modules/conv.py:145-151 (act(bn(conv(x))), BN folded per
 // utils/torch_utils.py:242-269), residuals of Bottleneck (block.py:3416-3419), PSABlock (:4379-4383), MSCA (:88).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int kEpiWarps = 8;
-constexpr int kNumThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kNumThreads = 64 + kEpiThreads;
 constexpr int kMaxStages = 8;
-constexpr unsigned kWaitSpinLimit = 1u << 26;  // failed try_wait polls before trapping (seconds), never reached when healthy
+constexpr int kMaxMB = 4;
+constexpr unsigned kWaitSpinLimit = 1u << 26;  // failed try_wait polls before trapping; never reached when healthy
 
 struct TcGeom {
   int B, Ho, Wo, cin, cout, cout_pad;
   int taps, nplanes, stride2, in_cs;
   int BK, nkc;
-  int TH, TW, P, tiles_h, tiles_w;
+  int TH, TW, P, MB, tiles_h, tiles_w;  // TH: output rows per 128-row block; a tile has MB blocks (MB*TH rows)
   int BN, n_ntiles;
   long long ntiles;
   int sa, sb, resident;                 // A stages, B stages (streamed), weights resident flag
   int plane_bytes, a_stage_bytes, a_tx_bytes, b_tile_bytes, b_tx_bytes, w_bytes_tx;
-  int row_bytes;
-  int tap_plane[9], tap_shift[9];       // tap -> (parity plane, row shift inside the halo tile)
+  int row_bytes, blk_rows_bytes;        // bytes per halo row; byte offset between consecutive blocks' A operands
+  int tap_off16[9];                     // tap -> operand start offset inside the A stage, in 16-byte units
   int tmem_cols;
-  unsigned desc_hi;                     // descriptor bits [32,64): SBO, version, layout type (base_offset added per use)
+  unsigned desc_hi;                     // descriptor bits [32,64): SBO, version, layout type
   unsigned idesc;
   int ox, oy;                           // halo origin offsets: TMA coordinate = tile origin - (ox, oy)
   // epilogue
@@ -52,8 +60,7 @@ struct TcGeom {
   const bf16 *res; int res_cs, res_mode;
   const float *bias;
   int act, vec_ok;
-  // tile decode by multiply-shift (tile ids < 2^31)
-  unsigned dv_nt_mul, dv_nt_shr, dv_tw_mul, dv_tw_shr, dv_th_mul, dv_th_shr;
+  unsigned dv_nt_mul, dv_nt_shr, dv_tw_mul, dv_tw_shr, dv_th_mul, dv_th_shr;  // tile decode by multiply-shift
   // bf16 outputs leave through shared memory + TMA store
   int tma_out, oc, n_oboxes, obox_bytes, o_row_bytes, o_sw_mask, o_stages, o_stage_bytes;
   int o_off, bias_off;                  // byte offsets of the output staging area / bias table in dynamic smem
@@ -90,12 +97,6 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -118,6 +119,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map
       "[%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -144,27 +151,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// SiLU with one MUFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2  (tanh.approx rel. error ~2^-11 << bf16 epsilon)
-__device__ __forceinline__ float silu_fast(float x) {
-  const float h = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-// same, for a pre-halved argument h = (x + bias) / 2
+// SiLU with one MUFU op on a pre-halved argument h = (x + bias)/2:  x*sigmoid(x) = h + h*tanh(h)
+// (tanh.approx rel. error ~2^-11 << bf16 epsilon)
 __device__ __forceinline__ float silu_half(float h) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
-}
-
-// K-major swizzled smem descriptor for an operand starting at byte address `addr`: any 16-byte-aligned row of a tile
-// whose base is aligned to the swizzle repeat.  Measured on B200: the swizzle XOR is applied to the absolute shared
-// memory address bits (exactly like the TMA write side), so row-shifted views need NO base_offset (bits [49,52) = 0);
-// setting base_offset = (addr >> 7) & 7 for shifted starts produces garbage (profiles/r01_notes.md).
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t desc_hi) {
-  const uint32_t hi = desc_hi;
-  return ((uint64_t)hi << 32) | (uint64_t)(1u << 16) | (uint64_t)((addr & 0x3FFFFu) >> 4);
 }
 
 struct TileCoord {
@@ -172,9 +164,9 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const TcGeom &g, uint32_t tile) {
   TileCoord t;
-  uint32_t sp = fast_div(tile, g.dv_nt_mul, g.dv_nt_shr);
+  const uint32_t sp = fast_div(tile, g.dv_nt_mul, g.dv_nt_shr);
   t.nt = (int)(tile - sp * g.n_ntiles);
-  uint32_t q = fast_div(sp, g.dv_tw_mul, g.dv_tw_shr);
+  const uint32_t q = fast_div(sp, g.dv_tw_mul, g.dv_tw_shr);
   t.tw_i = (int)(sp - q * g.tiles_w);
   const uint32_t q2 = fast_div(q, g.dv_th_mul, g.dv_th_shr);
   t.th_i = (int)(q - q2 * g.tiles_h);
@@ -182,6 +174,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TcGeom &g, uint32_t tile)
   return t;
 }
 
+// Shared-memory operand descriptors (K-major, swizzled): bits [0,14) start address >> 4, [16,30) LBO (unused for
+// swizzled K-major, 1), [32,46) SBO >> 4 = 8 rows, [46,48) version 1, [61,64) swizzle mode.  Measured on B200: the
+// swizzle XOR is applied to the absolute shared-memory address bits (exactly like the TMA write side), so a view that
+// starts at any 16-byte-aligned row of a swizzle-aligned tile needs NO base_offset (bits [49,52) stay 0); setting
+// base_offset = (addr >> 7) & 7 for shifted starts produces garbage (profiles/r01_notes.md).
+template <int TAPS, int KSTEPS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGeom g) {
@@ -210,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, 32 * kEpiWarps);
+      mbar_init(tempty0 + 8 * s, kEpiThreads);
     }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,6 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t ntiles = (uint32_t)g.ntiles;
+  const int rows_tile = g.MB * g.TH;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -236,13 +235,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       if (g.resident) {
         mbar_expect_tx(wfull, (uint32_t)g.w_bytes_tx);
-        for (int t = 0; t < g.taps * g.nkc; ++t) tma_load_2d(b_base + t * g.b_tile_bytes, &tmB, wfull, t * g.BK, 0);
+        for (int t = 0; t < TAPS * g.nkc; ++t) tma_load_2d(b_base + t * g.b_tile_bytes, &tmB, wfull, t * g.BK, 0);
       }
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
-        const int h0 = tc.th_i * g.TH - g.oy, w0 = tc.tw_i * g.TW - g.ox, n0 = tc.nt * g.BN;
+        const int h0 = tc.th_i * rows_tile - g.oy, w0 = tc.tw_i * g.TW - g.ox, n0 = tc.nt * g.BN;
         for (int kc = 0; kc < g.nkc; ++kc) {
           const int c0 = kc * g.BK;
           mbar_wait(emptyA + 8 * sa, pha ^ 1);
@@ -257,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++sa == g.sa) { sa = 0; pha ^= 1; }
           if (!g.resident) {
-            for (int tap = 0; tap < g.taps; ++tap) {
+            for (int tap = 0; tap < TAPS; ++tap) {
               mbar_wait(emptyB + 8 * sb, phb ^ 1);
               mbar_expect_tx(fullB + 8 * sb, (uint32_t)g.b_tx_bytes);
               tma_load_2d(b_base + sb * g.b_tile_bytes, &tmB, fullB + 8 * sb, tap * g.cin + c0, n0);
@@ -271,6 +270,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== MMA issuer
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, aphase = 0;
+    uint32_t tap_off[TAPS];  // registers: the tap loop below is fully unrolled
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) tap_off[t] = (uint32_t)g.tap_off16[t];
+    const uint64_t desc0 = ((uint64_t)g.desc_hi << 32) | (uint64_t)(1u << 16);
+    const uint32_t blk16 = (uint32_t)g.blk_rows_bytes >> 4, btile16 = (uint32_t)g.b_tile_bytes >> 4;
+    const uint32_t idesc = g.idesc;
+    const int MB = g.MB, nkc = g.nkc;
     if (g.resident) {
       mbar_wait(wfull, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -278,35 +284,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * g.BN);
-      for (int kc = 0; kc < g.nkc; ++kc) {
+      const uint32_t tmem_d0 = tmem_base + (uint32_t)(as * MB * g.BN);
+      for (int kc = 0; kc < nkc; ++kc) {
         mbar_wait(fullA + 8 * sa, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_stage = a_base + sa * g.a_stage_bytes;
-        for (int tap = 0; tap < g.taps; ++tap) {
-          uint32_t b_addr;
-          if (g.resident) {
-            b_addr = b_base + (tap * g.nkc + kc) * g.b_tile_bytes;
-          } else {
-            mbar_wait(fullB + 8 * sb, phb);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            b_addr = b_base + sb * g.b_tile_bytes;
-          }
+        const uint32_t a16 = ((a_base + sa * g.a_stage_bytes) & 0x3FFFFu) >> 4;
+        if (g.resident) {
           if (lane == 0) {
-            const uint32_t a_addr = a_stage + g.tap_plane[tap] * g.plane_bytes + g.tap_shift[tap] * g.row_bytes;
-            const uint64_t da = make_desc(a_addr, g.desc_hi), db = make_desc(b_addr, g.desc_hi);
-            for (int k = 0; k < g.BK / 16; ++k)
-              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), g.idesc, (kc | tap | k) != 0);
-            if (!g.resident) umma_commit(emptyB + 8 * sb);
+            const uint32_t b16 = ((b_base & 0x3FFFFu) >> 4) + (uint32_t)kc * btile16;
+            for (int j = 0; j < MB; ++j) {
+              const uint32_t tmem_d = tmem_d0 + (uint32_t)(j * g.BN);
+              const uint32_t aj = a16 + (uint32_t)j * blk16;
+#pragma unroll
+              for (int tap = 0; tap < TAPS; ++tap) {
+                const uint64_t da = desc0 | (uint64_t)(aj + tap_off[tap]);
+                const uint64_t db = desc0 | (uint64_t)(b16 + (uint32_t)(tap * nkc) * btile16);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                            (tap | k) ? 1u : (uint32_t)(kc != 0));
+              }
+            }
           }
           __syncwarp();
-          if (!g.resident) {
+        } else {
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(fullB + 8 * sb, phb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+              const uint64_t db = desc0 | (uint64_t)(((b_base + sb * g.b_tile_bytes) & 0x3FFFFu) >> 4);
+              for (int j = 0; j < MB; ++j) {
+                const uint64_t da = desc0 | (uint64_t)(a16 + (uint32_t)j * blk16 + (uint32_t)g.tap_off16[tap]);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(tmem_d0 + (uint32_t)(j * g.BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                            (uint32_t)((kc | tap | k) != 0));
+              }
+              umma_commit(emptyB + 8 * sb);
+            }
+            __syncwarp();
             if (++sb == g.sb) { sb = 0; phb ^= 1; }
           }
         }
         if (lane == 0) {
-          umma_commit(emptyA + 8 * sa);                        // frees the halo tile when the MMAs retire
-          if (kc == g.nkc - 1) umma_commit(tfull0 + 8 * as);   // accumulator complete
+          umma_commit(emptyA + 8 * sa);                      // frees the halo tile when the MMAs retire
+          if (kc == nkc - 1) umma_commit(tfull0 + 8 * as);   // accumulators complete
         }
         __syncwarp();
         if (++sa == g.sa) { sa = 0; pha ^= 1; }
@@ -316,20 +339,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================================================== epilogue: 8 warps, two per TMEM lane quadrant (warp % 4)
     const int quad = warp & 3, half = (warp - 2) >> 2;
-    const int m = quad * 32 + lane;  // accumulator row == halo pixel index within the tile
+    const int m = quad * 32 + lane;  // accumulator row == halo pixel index within the block
     const int th = m / g.P, tw = m - th * g.P;
     const bool row_ok = (th < g.TH) && (tw < g.TW);
-    const uint32_t rr = (uint32_t)(th * g.TW + tw);  // row in the compacted output tile (garbage halo columns dropped)
+    const uint32_t rr0 = (uint32_t)(th * g.TW + tw);  // row in the compacted output block (halo columns dropped)
+    const uint32_t blk_out_rows = (uint32_t)(g.TH * g.TW);
     const bool elected = (threadIdx.x == 64);
     const uint32_t o_base = smem_base + (uint32_t)g.o_off;
-    const int nchunks = g.BN >> 4;
+    const int nch = g.BN >> 4, nflat = g.MB * nch;
     int as = 0, os = 0;
     uint32_t aphase = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(g, tile);
-      const int ho = tc.th_i * g.TH + th, wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
-      const bool valid = row_ok && ho < g.Ho && wo < g.Wo;
-      const size_t pix = ((size_t)tc.b * g.Ho + ho) * g.Wo + wo;
+      const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
+      const int ho0 = tc.th_i * rows_tile + th;
       mbar_wait(tfull0 + 8 * as, aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (g.tma_out) {
@@ -338,30 +361,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        named_bar_sync(1, 32 * kEpiWarps);
+        named_bar_sync(1, kEpiThreads);
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * g.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * g.MB * g.BN);
       const uint32_t o_stage = o_base + (uint32_t)(os * g.o_stage_bytes);
-      for (int c = half; c < nchunks; c += 2) {
+      for (int f = half; f < nflat; f += 2) {  // f = block j * nch + 16-column chunk c
+        const int j = f / nch, c = f - j * nch;
         float v[16];
-        tmem_ld16(taddr + c * 16, v);  // warp-collective: executed by every lane, valid or not
+        tmem_ld16(taddr + (uint32_t)(j * g.BN + c * 16), v);  // warp-collective: every lane, valid or not
         const int col = c * 16, n = n0 + col;
         if (n >= g.cout) continue;  // warp-uniform
+        const int ho = ho0 + j * g.TH;
+        const bool valid = row_ok && ho < g.Ho && wo < g.Wo;
+        const size_t pix = ((size_t)tc.b * g.Ho + ho) * g.Wo + wo;
         const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n);
         if (g.act) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 hb = bp[j];
-            v[4 * j] = silu_half(fmaf(v[4 * j], 0.5f, hb.x));
-            v[4 * j + 1] = silu_half(fmaf(v[4 * j + 1], 0.5f, hb.y));
-            v[4 * j + 2] = silu_half(fmaf(v[4 * j + 2], 0.5f, hb.z));
-            v[4 * j + 3] = silu_half(fmaf(v[4 * j + 3], 0.5f, hb.w));
+          for (int q = 0; q < 4; ++q) {
+            const float4 hb = bp[q];
+            v[4 * q] = silu_half(fmaf(v[4 * q], 0.5f, hb.x));
+            v[4 * q + 1] = silu_half(fmaf(v[4 * q + 1], 0.5f, hb.y));
+            v[4 * q + 2] = silu_half(fmaf(v[4 * q + 2], 0.5f, hb.z));
+            v[4 * q + 3] = silu_half(fmaf(v[4 * q + 3], 0.5f, hb.w));
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bb = bp[j];
-            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = bp[q];
+            v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
           }
         }
         const bool full16 = (n + 16 <= g.cout);
@@ -372,18 +399,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             unpack8(__ldg(rp), r);
             unpack8(__ldg(rp + 1), r + 8);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (g.res_mode == B2Y_RES_ADD) ? v[j] + r[j] : v[j] * r[j];
+            for (int q = 0; q < 16; ++q) v[q] = (g.res_mode == B2Y_RES_ADD) ? v[q] + r[q] : v[q] * r[q];
           } else {
-            for (int j = 0; j < 16 && n + j < g.cout; ++j) {
-              const float r = __bfloat162float(g.res[pix * g.res_cs + n + j]);
-              v[j] = (g.res_mode == B2Y_RES_ADD) ? v[j] + r : v[j] * r;
+            for (int q = 0; q < 16 && n + q < g.cout; ++q) {
+              const float r = __bfloat162float(g.res[pix * g.res_cs + n + q]);
+              v[q] = (g.res_mode == B2Y_RES_ADD) ? v[q] + r : v[q] * r;
             }
           }
         }
         if (g.tma_out) {
           if (row_ok) {
-            const int bx = col / g.oc, cb = (col - bx * g.oc) * 2;  // box index, byte offset of the chunk in the row
-            uint32_t off = rr * (uint32_t)g.o_row_bytes + (uint32_t)cb;
+            const int bx = col / g.oc, cb = (col - bx * g.oc) * 2;  // 64-channel box, byte offset of the chunk in the row
+            uint32_t off = (rr0 + (uint32_t)j * blk_out_rows) * (uint32_t)g.o_row_bytes + (uint32_t)cb;
             const uint32_t off2 = off + 16;
             off ^= ((off >> 7) & (uint32_t)g.o_sw_mask) << 4;
             const uint32_t o2 = off2 ^ (((off2 >> 7) & (uint32_t)g.o_sw_mask) << 4);
@@ -397,16 +424,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (g.out_f32) {
               float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(g.out) + pix * g.out_cs + n);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             } else {
               uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(g.out) + pix * g.out_cs + n);
               op[0] = pack8(v);
               op[1] = pack8(v + 8);
             }
           } else {
-            for (int j = 0; j < 16 && n + j < g.cout; ++j) {
-              if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + j] = v[j];
-              else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + j] = __float2bfloat16_rn(v[j]);
+            for (int q = 0; q < 16 && n + q < g.cout; ++q) {
+              if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + q] = v[q];
+              else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + q] = __float2bfloat16_rn(v[q]);
             }
           }
         }
@@ -416,11 +443,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++as == 2) { as = 0; aphase ^= 1; }
       if (g.tma_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
-        named_bar_sync(2, 32 * kEpiWarps);
+        named_bar_sync(2, kEpiThreads);
         if (elected) {
           for (int bx = 0; bx < g.n_oboxes; ++bx)
             if (n0 + bx * g.oc < g.cout)
-              tma_store_4d(&tmO, o_stage + (uint32_t)(bx * g.obox_bytes), n0 + bx * g.oc, tc.tw_i * g.TW, tc.th_i * g.TH, tc.b);
+              tma_store_4d(&tmO, o_stage + (uint32_t)(bx * g.obox_bytes), n0 + bx * g.oc, tc.tw_i * g.TW,
+                           tc.th_i * rows_tile, tc.b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (++os == g.o_stages) os = 0;
@@ -437,7 +465,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  : "memory");
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -467,6 +494,13 @@ void find_div(unsigned d, unsigned &mul, unsigned &shr) {  // n / d == umulhi(n,
   shr = p - 32;
 }
 
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcGeom);
+
+KernelFn pick_kernel(int taps, int ksteps) {
+  if (taps == 1) return ksteps == 4 ? conv_tc_kernel<1, 4> : ksteps == 2 ? conv_tc_kernel<1, 2> : conv_tc_kernel<1, 1>;
+  return ksteps == 4 ? conv_tc_kernel<9, 4> : ksteps == 2 ? conv_tc_kernel<9, 2> : conv_tc_kernel<9, 1>;
+}
+
 }  // namespace
 
 struct ConvTcPlan {
@@ -474,6 +508,7 @@ struct ConvTcPlan {
   TcGeom g;
   int grid;
   size_t smem;
+  KernelFn fn;
 };
 
 bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
@@ -499,6 +534,9 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   B2Y_REQUIRE(conv_tc_supported(p, why, sizeof(why)), B2Y_ERR_UNSUPPORTED, "tcgen05 conv: %s", why);
   EncodeTiledFn encode = get_encode_fn();
   B2Y_REQUIRE(encode != nullptr, B2Y_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cudaDeviceProp prop;
+  B2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  const int num_sms = prop.multiProcessorCount;
   ConvTcPlan *pl = new ConvTcPlan();
   TcGeom &g = pl->g;
   memset(&g, 0, sizeof(g));
@@ -510,48 +548,8 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   g.row_bytes = g.BK * 2;
   const int halo = (p.kh == 3) ? (g.stride2 ? 1 : 2) : 0;  // extra halo columns/rows per tile
   g.ox = g.oy = (p.kh == 3) ? 1 : 0;
-  // spatial tile: accumulator rows m = th*P + tw, P = TW + halo; maximise useful rows per 128-row MMA
-  {
-    double best = -1.0;
-    int bth = 1, btw = 1;
-    for (int tw = 1; tw <= (p.Wo < 128 - halo ? p.Wo : 128 - halo); ++tw) {
-      const int P = tw + halo;
-      int th = (128 - tw) / P + 1;  // (th-1)*P + tw <= 128
-      if (th > p.Ho) th = p.Ho;
-      if (th < 1 || th + halo > 256 || P > 256) continue;
-      const double eff = (double)p.Ho * p.Wo / ((double)ceil_div(p.Ho, th) * ceil_div(p.Wo, tw) * 128.0);
-      const double amp = (double)(th + halo) * P / ((double)th * tw);  // halo read amplification
-      const double score = eff - 0.02 * amp;
-      if (score > best) { best = score; bth = th; btw = tw; }
-    }
-    g.TH = bth; g.TW = btw; g.P = btw + halo;
-  }
-  g.tiles_h = ceil_div(p.Ho, g.TH); g.tiles_w = ceil_div(p.Wo, g.TW);
   g.n_ntiles = ceil_div(p.cout_pad, 256);
   g.BN = ceil_div(ceil_div(p.cout_pad, g.n_ntiles), 16) * 16;
-  g.ntiles = (long long)p.B * g.tiles_h * g.tiles_w * g.n_ntiles;
-  // tap table
-  int max_shift = 0;
-  for (int r = 0; r < p.kh; ++r)
-    for (int s = 0; s < p.kw; ++s) {
-      const int t = r * p.kw + s;
-      if (p.kh == 1) { g.tap_plane[t] = 0; g.tap_shift[t] = 0; }
-      else if (!g.stride2) { g.tap_plane[t] = 0; g.tap_shift[t] = r * g.P + s; }
-      else {
-        g.tap_plane[t] = ((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1);
-        g.tap_shift[t] = ((r == 0) ? 0 : 1) * g.P + ((s == 0) ? 0 : 1);
-      }
-      if (g.tap_shift[t] > max_shift) max_shift = g.tap_shift[t];
-    }
-  const int box_rows = (g.TH + halo) * g.P;
-  const int rows_alloc = (box_rows > max_shift + 128) ? box_rows : (max_shift + 128);
-  g.plane_bytes = round_up(rows_alloc * g.row_bytes, 1024);
-  g.a_stage_bytes = g.nplanes * g.plane_bytes;
-  g.a_tx_bytes = g.nplanes * box_rows * g.row_bytes;
-  g.b_tile_bytes = round_up(g.BN * g.row_bytes, 1024);
-  g.b_tx_bytes = g.BN * g.row_bytes;
-  const int w_tiles = g.taps * g.nkc;
-  const long long w_res_bytes = (long long)w_tiles * g.b_tile_bytes;
   // bf16 outputs are staged in shared memory and leave through TMA stores (coalesced, clipped, channel-sliced by the
   // tensor map); fp32 head outputs and unaligned views are stored directly from registers.
   g.tma_out = (!p.out_f32 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_cs % 8 == 0 && p.cout % 8 == 0) ? 1 : 0;
@@ -559,44 +557,111 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   g.n_oboxes = ceil_div(g.BN, g.oc);
   g.o_row_bytes = g.oc * 2;
   g.o_sw_mask = g.oc == 64 ? 7 : (g.oc == 32 ? 3 : 1);
-  g.obox_bytes = 128 * g.o_row_bytes;
-  g.o_stages = g.tma_out ? (g.BN <= 128 ? 2 : 1) : 0;
-  g.o_stage_bytes = g.n_oboxes * g.obox_bytes;
-  const int out_bytes = g.o_stages * g.o_stage_bytes;
   const int bias_bytes = round_up(p.cout_pad * 4, 1024);
-  const int budget = 220 * 1024 - out_bytes - bias_bytes;
-  g.resident = (g.n_ntiles == 1 && w_res_bytes + 2 * g.a_stage_bytes <= budget) ? 1 : 0;
+  const int w_tiles = g.taps * g.nkc;
+  g.b_tile_bytes = round_up(g.BN * g.row_bytes, 1024);
+  g.b_tx_bytes = g.BN * g.row_bytes;
+  const long long w_res_bytes = (long long)w_tiles * g.b_tile_bytes;
   g.w_bytes_tx = w_tiles * g.b_tx_bytes;
+
+  // spatial block: accumulator rows m = th*P + tw, P = TW + halo; maximise useful rows per 128-row MMA block
+  {
+    double best = -1.0;
+    int bth = 1, btw = 1;
+    for (int tw = 1; tw <= (p.Wo < 128 - halo ? p.Wo : 128 - halo); ++tw) {
+      const int P = tw + halo;
+      int th = (128 - tw) / P + 1;  // (th-1)*P + tw <= 128
+      if (th > p.Ho) th = p.Ho;
+      if (th < 1 || P > 256) continue;
+      const double eff = (double)p.Ho * p.Wo / ((double)ceil_div(p.Ho, th) * ceil_div(p.Wo, tw) * 128.0);
+      const double amp = (double)(th + halo) * P / ((double)th * tw);  // halo read amplification
+      const double score = eff - 0.02 * amp;
+      if (score > best) { best = score; bth = th; btw = tw; }
+    }
+    g.TH = bth; g.TW = btw; g.P = btw + halo;
+  }
+  g.tiles_w = ceil_div(p.Wo, g.TW);
+
+  // blocks per tile (MB), stages and residency under the shared-memory / TMEM / parallelism budgets
+  const int smem_budget = 220 * 1024;
+  int best_mb = 0;
+  for (int mb = kMaxMB; mb >= 1; --mb) {
+    if (2 * mb * g.BN > 512) continue;                 // TMEM columns (double buffered)
+    if (mb * g.TH + halo > 256) continue;              // TMA box limit
+    if (mb > 1 && (mb - 1) * g.TH >= p.Ho) continue;   // would only add empty blocks
+    const long long tiles = (long long)p.B * ceil_div(p.Ho, mb * g.TH) * g.tiles_w * g.n_ntiles;
+    if (mb > 1 && tiles < 4LL * num_sms) continue;     // keep every SM busy with a few tiles
+    const int box_rows = (mb * g.TH + halo) * g.P;
+    const int max_shift = (p.kh == 1) ? 0 : (g.stride2 ? g.P + 1 : 2 * g.P + 2);
+    const int need_rows = (mb - 1) * g.TH * g.P + max_shift + 128;
+    const int plane = round_up((box_rows > need_rows ? box_rows : need_rows) * g.row_bytes, 1024);
+    const int a_stage = g.nplanes * plane;
+    const int o_stage = g.tma_out ? g.n_oboxes * mb * 128 * g.o_row_bytes : 0;
+    int o_stages = g.tma_out ? 2 : 0;
+    const long long fixed = bias_bytes + 1024;
+    const bool res_ok = (g.n_ntiles == 1) && (w_res_bytes + 2LL * a_stage + o_stage + fixed <= smem_budget);
+    const long long b_bytes = res_ok ? w_res_bytes : 2LL * g.b_tile_bytes;
+    if (b_bytes + a_stage + o_stage + fixed > smem_budget) continue;  // does not fit even single-buffered
+    if (b_bytes + 2LL * a_stage + (long long)o_stages * o_stage + fixed > smem_budget) o_stages = g.tma_out ? 1 : 0;
+    best_mb = mb;
+    g.MB = mb;
+    g.plane_bytes = plane;
+    g.a_stage_bytes = a_stage;
+    g.a_tx_bytes = g.nplanes * box_rows * g.row_bytes;
+    g.o_stage_bytes = o_stage;
+    g.o_stages = o_stages;
+    g.resident = res_ok ? 1 : 0;
+    break;
+  }
+  if (!best_mb) {
+    delete pl;
+    b2y_set_error("tcgen05 conv: no tile configuration fits shared memory (BN %d, BK %d)", g.BN, g.BK);
+    return B2Y_ERR_UNSUPPORTED;
+  }
+  g.obox_bytes = g.MB * 128 * g.o_row_bytes;
+  g.blk_rows_bytes = g.TH * g.P * g.row_bytes;
+  g.tiles_h = ceil_div(p.Ho, g.MB * g.TH);
+  g.ntiles = (long long)p.B * g.tiles_h * g.tiles_w * g.n_ntiles;
+  if (g.ntiles >= (1ll << 31)) {
+    delete pl;
+    b2y_set_error("tcgen05 conv: too many tiles");
+    return B2Y_ERR_UNSUPPORTED;
+  }
+  // tap table: operand start inside the A stage (plane + row shift), 16-byte units
+  for (int r = 0; r < p.kh; ++r)
+    for (int s = 0; s < p.kw; ++s) {
+      const int t = r * p.kw + s;
+      int plane = 0, shift = 0;
+      if (p.kh == 3 && !g.stride2) shift = r * g.P + s;
+      else if (p.kh == 3) {
+        plane = ((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1);
+        shift = ((r == 0) ? 0 : 1) * g.P + ((s == 0) ? 0 : 1);
+      }
+      g.tap_off16[t] = (plane * g.plane_bytes + shift * g.row_bytes) >> 4;
+    }
+  // stage counts
+  const int out_bytes = g.o_stages * g.o_stage_bytes;
   int b_bytes_total;
   if (g.resident) {
     g.sb = 0;
     b_bytes_total = (int)w_res_bytes;
   } else {
     g.sb = 4;
+    while (g.sb > 2 && (long long)g.sb * g.b_tile_bytes + 2LL * g.a_stage_bytes + out_bytes + bias_bytes + 1024 > smem_budget) --g.sb;
     b_bytes_total = g.sb * g.b_tile_bytes;
-    while (g.sb > 2 && b_bytes_total + 2 * g.a_stage_bytes > budget) { --g.sb; b_bytes_total = g.sb * g.b_tile_bytes; }
   }
-  int sa = (budget - b_bytes_total) / g.a_stage_bytes;
+  int sa = (smem_budget - b_bytes_total - out_bytes - bias_bytes - 1024) / g.a_stage_bytes;
   if (sa > 4) sa = 4;
-  if (sa > kMaxStages) sa = kMaxStages;
-  if (sa < 1) {
-    delete pl;
-    b2y_set_error("tcgen05 conv: tile does not fit shared memory (A stage %d B, B %d B)", g.a_stage_bytes, b_bytes_total);
-    return B2Y_ERR_UNSUPPORTED;
-  }
+  if (sa < 1) sa = 1;
   g.sa = sa;
   g.o_off = g.sa * g.a_stage_bytes + b_bytes_total;
   g.bias_off = g.o_off + out_bytes;
+  pl->smem = (size_t)g.bias_off + bias_bytes + 1024;
   find_div((unsigned)g.n_ntiles, g.dv_nt_mul, g.dv_nt_shr);
   find_div((unsigned)g.tiles_w, g.dv_tw_mul, g.dv_tw_shr);
   find_div((unsigned)g.tiles_h, g.dv_th_mul, g.dv_th_shr);
-  if (g.ntiles >= (1ll << 31)) {
-    delete pl;
-    b2y_set_error("tcgen05 conv: too many tiles");
-    return B2Y_ERR_UNSUPPORTED;
-  }
   int cols = 32;
-  while (cols < 2 * g.BN) cols <<= 1;
+  while (cols < 2 * g.MB * g.BN) cols <<= 1;
   g.tmem_cols = cols;
   const unsigned layout = (g.row_bytes == 128) ? 2u : (g.row_bytes == 64) ? 4u : 6u;  // UMMA LayoutType SW128/SW64/SW32
   const unsigned sbo = (unsigned)(8 * g.row_bytes) >> 4;
@@ -616,12 +681,13 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
                                 : (g.row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
                                                       : CU_TENSOR_MAP_SWIZZLE_32B;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  const int box_h = g.MB * g.TH + halo;
   CUresult r;
   if (!g.stride2) {
     const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.in_cs * 2, (cuuint64_t)p.W * p.in_cs * 2,
                                    (cuuint64_t)p.H * p.W * p.in_cs * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)g.BK, (cuuint32_t)g.P, (cuuint32_t)(g.TH + halo), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)g.BK, (cuuint32_t)g.P, (cuuint32_t)box_h, 1};
     r = encode(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16 *>(p.in), dims, strides, box, ones,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
@@ -629,7 +695,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
                                 (cuuint64_t)p.B};
     const cuuint64_t strides[4] = {(cuuint64_t)2 * p.in_cs * 2, (cuuint64_t)p.W * p.in_cs * 2,
                                    (cuuint64_t)2 * p.W * p.in_cs * 2, (cuuint64_t)p.H * p.W * p.in_cs * 2};
-    const cuuint32_t box[5] = {(cuuint32_t)g.BK, (cuuint32_t)g.P, 1, (cuuint32_t)(g.TH + halo), 1};
+    const cuuint32_t box[5] = {(cuuint32_t)g.BK, (cuuint32_t)g.P, 1, (cuuint32_t)box_h, 1};
     r = encode(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16 *>(p.in), dims, strides, box, ones,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -657,7 +723,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
     const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.out_cs * 2, (cuuint64_t)p.Wo * p.out_cs * 2,
                                    (cuuint64_t)p.Ho * p.Wo * p.out_cs * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)g.oc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)g.oc, (cuuint32_t)g.TW, (cuuint32_t)(g.MB * g.TH), 1};
     r = encode(&pl->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.out, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                osw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -668,17 +734,11 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   } else {
     pl->tmO = pl->tmB;  // unused
   }
-  pl->smem = (size_t)g.bias_off + bias_bytes + 1024;
-  cudaDeviceProp prop;
-  B2Y_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   const int per_sm = (pl->smem <= 100 * 1024 && g.tmem_cols <= 256) ? 2 : 1;
-  const long long max_ctas = (long long)prop.multiProcessorCount * per_sm;
+  const long long max_ctas = (long long)num_sms * per_sm;
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2Y_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_done = true;
-  }
+  pl->fn = pick_kernel(g.taps, g.BK / 16);
+  B2Y_CUDA_CHECK(cudaFuncSetAttribute(pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   *out = pl;
   return B2Y_OK;
 }
@@ -686,7 +746,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
 void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
 
 int launch_conv_tc(const ConvTcPlan *pl, cudaStream_t st) {
-  conv_tc_kernel<<<pl->grid, kNumThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->tmO, pl->g);
+  pl->fn<<<pl->grid, kNumThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->tmO, pl->g);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

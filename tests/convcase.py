@@ -25,12 +25,17 @@ CASES = {
     "k3_96_96_n": dict(c1=96, c2=96, k=3, s=1, H=24, W=40),
     "k1_1536_768": dict(c1=1536, c2=768, k=1, s=1, H=16, W=16),
     "k3_768_768_s2": dict(c1=768, c2=768, k=3, s=2, H=16, W=16),
+    # large enough tile counts for multi-block (MB > 1) tiles
+    "k3_16_16_160_mb": dict(c1=16, c2=16, k=3, s=1, H=160, W=160, B=12, res="add"),
+    "k1_32_64_160_mb": dict(c1=32, c2=64, k=1, s=1, H=160, W=160, B=8),
+    "k3s2_16_32_320_mb": dict(c1=16, c2=32, k=3, s=2, H=320, W=320, B=12),
+    "k3_64_64_80_mb": dict(c1=64, c2=64, k=3, s=1, H=80, W=80, B=24),
 }
 
 
 def build_case(name: str, impl: int, seed: int = 0):
     """Returns (plan, x_view, out_view, res_view|None)."""
-    c = dict(in_total=None, in_off=0, out_total=None, out_off=0, res=None, act=True, f32=False, pad16=False)
+    c = dict(in_total=None, in_off=0, out_total=None, out_off=0, res=None, act=True, f32=False, pad16=False, B=3)
     c.update(CASES[name])
     rng = np.random.default_rng(seed)
     c1, c2, k, s, H, W = c["c1"], c["c2"], c["k"], c["s"], c["H"], c["W"]
@@ -56,12 +61,13 @@ def build_case(name: str, impl: int, seed: int = 0):
     return plan, x, out, res
 
 
-def run_case(name: str, impl: int, B: int = 3, seed: int = 0, device=0):
+def run_case(name: str, impl: int, B: int | None = None, seed: int = 0, device=0):
     """Run one case on the GPU through the engine and through the emulator; returns (gpu_out, ref_out) as float CPU."""
     from bs_yolo_b200.engine import Engine
     from plan_emulator import PlanEmulator
 
     plan, x, out, res = build_case(name, impl, seed)
+    B = B or CASES[name].get("B", 3)
     eng = Engine(None, B, 64, 64, device=device, use_graph=False, plan=plan)
     g = torch.Generator().manual_seed(seed)
     emu = PlanEmulator(plan, B, round_bf16=True)
