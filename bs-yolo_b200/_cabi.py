@@ -33,7 +33,7 @@ class Op(C.Structure):
 
 
 EXPORTS = ["b2y_abi_version", "b2y_last_error", "b2y_plan_create", "b2y_plan_destroy", "b2y_plan_run",
-           "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_preprocess",
+           "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_preprocess",
            "b2y_decode", "b2y_nms_workspace_bytes", "b2y_nms", "b2y_scale_boxes"]
 
 _lib = None
@@ -60,6 +60,7 @@ def lib():
     L.b2y_plan_run.argtypes = [vp, i32, i32, vp]
     L.b2y_plan_graph_build.argtypes = [vp, vp]
     L.b2y_plan_graph_launch.argtypes = [vp, vp]
+    L.b2y_plan_autotune.argtypes = [vp, vp]
     L.b2y_plan_num_launches.argtypes = [vp]
     L.b2y_plan_op_impl.argtypes = [vp, i32]
     L.b2y_preprocess.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]

@@ -96,8 +96,12 @@ int launch_stem(const ConvParams &p, cudaStream_t st);
 int launch_dwconv(const ConvParams &p, cudaStream_t st);
 
 struct ConvTcPlan;  // opaque: tensor maps + geometry for one tcgen05 conv
+struct TcConfig {
+  int mb;      // 128-row accumulator blocks per tile (0: heuristic)
+  int per_sm;  // CTAs meant to co-reside per SM: 1..3 (0: heuristic = 1)
+};
 bool conv_tc_supported(const ConvParams &p, char *why, int why_len);
-int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out);
+int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, ConvTcPlan **out);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 int launch_conv_tc(const ConvTcPlan *p, cudaStream_t st);
 

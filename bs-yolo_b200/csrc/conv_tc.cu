@@ -529,7 +529,7 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
   return true;
 }
 
-int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
+int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, ConvTcPlan **out) {
   char why[128];
   B2Y_REQUIRE(conv_tc_supported(p, why, sizeof(why)), B2Y_ERR_UNSUPPORTED, "tcgen05 conv: %s", why);
   EncodeTiledFn encode = get_encode_fn();
@@ -582,15 +582,17 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   }
   g.tiles_w = ceil_div(p.Wo, g.TW);
 
-  // blocks per tile (MB), stages and residency under the shared-memory / TMEM / parallelism budgets
-  const int smem_budget = 220 * 1024;
+  // blocks per tile (MB), stages and residency under the shared-memory / TMEM / parallelism budgets.
+  // cfg.per_sm CTAs are meant to co-reside on an SM: the shared-memory budget is divided accordingly.
+  const int want_per_sm = cfg.per_sm > 0 ? cfg.per_sm : 1;
+  const int smem_budget = want_per_sm == 1 ? 220 * 1024 : (want_per_sm == 2 ? 110 * 1024 : 72 * 1024);
   int best_mb = 0;
-  for (int mb = kMaxMB; mb >= 1; --mb) {
-    if (2 * mb * g.BN > 512) continue;                 // TMEM columns (double buffered)
+  for (int mb = (cfg.mb > 0 ? cfg.mb : kMaxMB); mb >= (cfg.mb > 0 ? cfg.mb : 1); --mb) {
+    if (2 * mb * g.BN * want_per_sm > 512) continue;   // TMEM columns (double buffered, per co-resident CTA)
     if (mb * g.TH + halo > 256) continue;              // TMA box limit
     if (mb > 1 && (mb - 1) * g.TH >= p.Ho) continue;   // would only add empty blocks
     const long long tiles = (long long)p.B * ceil_div(p.Ho, mb * g.TH) * g.tiles_w * g.n_ntiles;
-    if (mb > 1 && tiles < 4LL * num_sms) continue;     // keep every SM busy with a few tiles
+    if (cfg.mb <= 0 && mb > 1 && tiles < 4LL * num_sms * want_per_sm) continue;  // keep every SM busy with a few tiles
     const int box_rows = (mb * g.TH + halo) * g.P;
     const int max_shift = (p.kh == 1) ? 0 : (g.stride2 ? g.P + 1 : 2 * g.P + 2);
     const int need_rows = (mb - 1) * g.TH * g.P + max_shift + 128;
@@ -615,7 +617,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   }
   if (!best_mb) {
     delete pl;
-    b2y_set_error("tcgen05 conv: no tile configuration fits shared memory (BN %d, BK %d)", g.BN, g.BK);
+    b2y_set_error("tcgen05 conv: no tile configuration fits (BN %d, BK %d, mb %d, per_sm %d)", g.BN, g.BK, cfg.mb, cfg.per_sm);
     return B2Y_ERR_UNSUPPORTED;
   }
   g.obox_bytes = g.MB * 128 * g.o_row_bytes;
@@ -734,8 +736,13 @@ int conv_tc_plan_create(const ConvParams &p, int device, ConvTcPlan **out) {
   } else {
     pl->tmO = pl->tmB;  // unused
   }
-  const int per_sm = (pl->smem <= 100 * 1024 && g.tmem_cols <= 256) ? 2 : 1;
-  const long long max_ctas = (long long)num_sms * per_sm;
+  if (want_per_sm == 1 && pl->smem < 116 * 1024) pl->smem = 116 * 1024;  // keep the SM to one CTA as configured
+  if (g.tmem_cols * want_per_sm > 512) {
+    delete pl;
+    b2y_set_error("tcgen05 conv: TMEM over-subscribed (%d columns x %d CTAs)", g.tmem_cols, want_per_sm);
+    return B2Y_ERR_UNSUPPORTED;
+  }
+  const long long max_ctas = (long long)num_sms * want_per_sm;
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
   pl->fn = pick_kernel(g.taps, g.BK / 16);
   B2Y_CUDA_CHECK(cudaFuncSetAttribute(pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

@@ -249,7 +249,7 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
             rc = B2Y_ERR_UNSUPPORTED;
             break;
           }
-          rc = conv_tc_plan_create(r.cp, device, &r.tc);
+          rc = conv_tc_plan_create(r.cp, device, TcConfig{0, 0}, &r.tc);
         }
         r.impl = impl;
       }
@@ -318,6 +318,52 @@ extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
 extern "C" int b2y_plan_graph_launch(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl && pl->graph_exec, B2Y_ERR_INVALID, "graph_launch: graph not built");
   B2Y_CUDA_CHECK(cudaGraphLaunch(pl->graph_exec, (cudaStream_t)stream));
+  return B2Y_OK;
+}
+
+// Per-layer autotuning of the tcgen05 conv tile configuration (blocks per tile x co-resident CTAs): every candidate is
+// built and timed on the real buffers (their contents are overwritten by the next full run), the fastest is kept.
+extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
+  B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "autotune: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  B2Y_CUDA_CHECK(cudaEventCreate(&e0));
+  B2Y_CUDA_CHECK(cudaEventCreate(&e1));
+  const int mbs[3] = {1, 2, 4};
+  for (auto &r : pl->ops) {
+    if (r.op.kind != B2Y_OP_CONV || r.impl != B2Y_IMPL_TCGEN05) continue;
+    float best_ms = 1e30f;
+    ConvTcPlan *best = nullptr;
+    for (int per_sm = 1; per_sm <= 3; ++per_sm)
+      for (int mi = 0; mi < 3; ++mi) {
+        ConvTcPlan *cand = nullptr;
+        if (conv_tc_plan_create(r.cp, pl->device, TcConfig{mbs[mi], per_sm}, &cand) != B2Y_OK) continue;
+        float ms = 1e30f;
+        bool ok = launch_conv_tc(cand, st) == B2Y_OK;  // warm-up
+        if (ok) {
+          cudaEventRecord(e0, st);
+          for (int it = 0; it < 3 && ok; ++it) ok = launch_conv_tc(cand, st) == B2Y_OK;
+          cudaEventRecord(e1, st);
+          ok = ok && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess;
+        }
+        if (ok && ms < best_ms) {
+          if (best) conv_tc_plan_destroy(best);
+          best = cand;
+          best_ms = ms;
+        } else {
+          conv_tc_plan_destroy(cand);
+        }
+      }
+    if (best) {
+      conv_tc_plan_destroy(r.tc);
+      r.tc = best;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  B2Y_CUDA_CHECK(cudaGetLastError());
+  if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
+  if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
   return B2Y_OK;
 }
 

@@ -31,7 +31,7 @@ def letterbox_geometry(shape, new_shape, auto: bool, stride: int = 32):
 
 class Engine:
     def __init__(self, ir, batch: int, H: int, W: int, device: int | torch.device = 0, conv_impl: int = A.IMPL_AUTO,
-                 use_graph: bool = True, plan: Plan | None = None):
+                 use_graph: bool = True, plan: Plan | None = None, autotune: bool = True):
         if not torch.cuda.is_available():
             raise A.B2YError("bs_yolo_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = A.lib()
@@ -53,6 +53,7 @@ class Engine:
         self.handle = handle
         self.use_graph = use_graph
         self._graph_ready = False
+        self._tuned = not autotune
         self.max_det_alloc = 0
         self._nms_ws = None
 
@@ -112,6 +113,9 @@ class Engine:
     def forward(self):
         """Backbone + neck + Detect + decode for the batch already in the input buffer."""
         st = self._stream()
+        if not self._tuned:  # once: pick the fastest tile configuration per tcgen05 conv, measured on this device
+            A.check(self.lib.b2y_plan_autotune(self.handle, st))
+            self._tuned = True
         if self.use_graph:
             if not self._graph_ready:
                 A.check(self.lib.b2y_plan_run(self.handle, 0, -1, st))  # warm-up: function attributes, lazy loading

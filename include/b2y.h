@@ -98,6 +98,9 @@ B2Y_API int b2y_plan_run(b2y_plan *plan, int32_t first, int32_t last, void *stre
 /* Capture the whole plan into a CUDA graph (stream must not be capturing) / replay it. */
 B2Y_API int b2y_plan_graph_build(b2y_plan *plan, void *stream);
 B2Y_API int b2y_plan_graph_launch(b2y_plan *plan, void *stream);
+/* Time the candidate tile configurations of every tcgen05 conv on the plan's own buffers and keep the fastest
+ * (synchronises the stream; buffer contents are clobbered; an existing graph is dropped). */
+B2Y_API int b2y_plan_autotune(b2y_plan *plan, void *stream);
 /* Number of kernels one full run launches; which conv implementation op `i` resolved to (b2y_conv_impl). */
 B2Y_API int b2y_plan_num_launches(const b2y_plan *plan);
 B2Y_API int b2y_plan_op_impl(const b2y_plan *plan, int32_t i);
