@@ -186,6 +186,103 @@ __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
   else o[0] = __float2bfloat16_rn(acc[0]);
 }
 
+// Register-blocked variant for 16-byte-aligned channel groups: thread = 4 consecutive output pixels of one row x 8
+// channels.  Each input pixel of the (kw + 3*sw) wide window is loaded once and feeds up to 4 outputs; the weights of
+// the whole layer sit in shared memory ([kh*kw][c] fp32 + bias) and are read as broadcast float4s.
+template <int KW, int SW>  // KW == 0: runtime kernel width / stride
+__global__ void __launch_bounds__(256) dwconv4_kernel(ConvParams p, int wq) {
+  extern __shared__ float wsm[];
+  const int taps = p.kh * p.kw;
+  for (int i = threadIdx.x; i < taps * p.cout; i += blockDim.x) wsm[i] = reinterpret_cast<const float *>(p.w)[i];
+  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) wsm[taps * p.cout + i] = p.bias[i];
+  __syncthreads();
+  const int kw = KW ? KW : p.kw, sw = KW ? SW : p.sw;
+  const int cg = p.cout / 8;
+  const long long total = (long long)p.B * p.Ho * wq * cg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cg) * 8;
+  long long t = idx / cg;
+  const int wo0 = (int)(t % wq) * 4;
+  t /= wq;
+  const int ho = (int)(t % p.Ho);
+  const int b = (int)(t / p.Ho);
+  float acc[4][8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4 *>(wsm + taps * p.cout + c0);
+    const float4 b1 = *reinterpret_cast<const float4 *>(wsm + taps * p.cout + c0 + 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc[q][0] = b0.x; acc[q][1] = b0.y; acc[q][2] = b0.z; acc[q][3] = b0.w;
+      acc[q][4] = b1.x; acc[q][5] = b1.y; acc[q][6] = b1.z; acc[q][7] = b1.w;
+    }
+  }
+  const int span = 3 * sw + kw;
+  for (int r = 0; r < p.kh; ++r) {
+    const int hi = ho * p.sh - p.ph + r;
+    if (hi < 0 || hi >= p.H) continue;
+    const bf16 *row = p.in + ((size_t)(b * p.H + hi) * p.W) * p.in_cs + c0;
+    const float *wr = wsm + (size_t)r * kw * p.cout + c0;
+#pragma unroll
+    for (int xx = 0; xx < (KW ? 3 * SW + KW : 1); ++xx) {
+      if (!KW) break;
+      const int wi = wo0 * sw - p.pw + xx;
+      if (wi < 0 || wi >= p.W) continue;
+      float xv[8];
+      unpack8(*reinterpret_cast<const uint4 *>(row + (size_t)wi * p.in_cs), xv);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int tp = xx - q * SW;
+        if (tp >= 0 && tp < KW) {
+          const float4 w0 = *reinterpret_cast<const float4 *>(wr + tp * p.cout);
+          const float4 w1 = *reinterpret_cast<const float4 *>(wr + tp * p.cout + 4);
+          acc[q][0] = fmaf(xv[0], w0.x, acc[q][0]); acc[q][1] = fmaf(xv[1], w0.y, acc[q][1]);
+          acc[q][2] = fmaf(xv[2], w0.z, acc[q][2]); acc[q][3] = fmaf(xv[3], w0.w, acc[q][3]);
+          acc[q][4] = fmaf(xv[4], w1.x, acc[q][4]); acc[q][5] = fmaf(xv[5], w1.y, acc[q][5]);
+          acc[q][6] = fmaf(xv[6], w1.z, acc[q][6]); acc[q][7] = fmaf(xv[7], w1.w, acc[q][7]);
+        }
+      }
+    }
+    if (!KW) {
+      for (int xx = 0; xx < span; ++xx) {
+        const int wi = wo0 * sw - p.pw + xx;
+        if (wi < 0 || wi >= p.W) continue;
+        float xv[8];
+        unpack8(*reinterpret_cast<const uint4 *>(row + (size_t)wi * p.in_cs), xv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tp = xx - q * sw;
+          if (tp >= 0 && tp < kw) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(wr + tp * p.cout);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wr + tp * p.cout + 4);
+            acc[q][0] = fmaf(xv[0], w0.x, acc[q][0]); acc[q][1] = fmaf(xv[1], w0.y, acc[q][1]);
+            acc[q][2] = fmaf(xv[2], w0.z, acc[q][2]); acc[q][3] = fmaf(xv[3], w0.w, acc[q][3]);
+            acc[q][4] = fmaf(xv[4], w1.x, acc[q][4]); acc[q][5] = fmaf(xv[5], w1.y, acc[q][5]);
+            acc[q][6] = fmaf(xv[6], w1.z, acc[q][6]); acc[q][7] = fmaf(xv[7], w1.w, acc[q][7]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int wo = wo0 + q;
+    if (wo >= p.Wo) break;
+    const size_t opix = ((size_t)(b * p.Ho + ho) * p.Wo + wo);
+    if (p.act) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = silu_f(acc[q][j]);
+    }
+    if (p.res_mode) {
+      float rv[8];
+      unpack8(*reinterpret_cast<const uint4 *>(p.res + opix * p.res_cs + c0), rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = (p.res_mode == B2Y_RES_ADD) ? acc[q][j] + rv[j] : acc[q][j] * rv[j];
+    }
+    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(p.out) + opix * p.out_cs + c0) = pack8(acc[q]);
+  }
+}
+
 int launch_dwconv(const ConvParams &p, cudaStream_t st) {
   B2Y_REQUIRE(p.cin == p.cout && !p.out_f32, B2Y_ERR_UNSUPPORTED, "depthwise conv needs cin == cout and bf16 output");
   auto aligned = [&](int v) {
@@ -195,6 +292,24 @@ int launch_dwconv(const ConvParams &p, cudaStream_t st) {
     if (p.res_mode) ok = ok && (p.res_cs % v == 0) && ((reinterpret_cast<uintptr_t>(p.res) & m) == 0);
     return ok;
   };
+  const size_t wsmem = (size_t)(p.kh * p.kw + 1) * p.cout * sizeof(float);
+  if (aligned(8) && wsmem <= 96 * 1024 && p.sh == p.sw) {
+    const int wq = ceil_div(p.Wo, 4);
+    const long long total = (long long)p.B * p.Ho * wq * (p.cout / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    auto launch = [&](auto kern) -> int {
+      if (wsmem > 48 * 1024)
+        B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      kern<<<grid, 256, wsmem, st>>>(p, wq);
+      B2Y_LAUNCH_CHECK();
+      return B2Y_OK;
+    };
+    if (p.kw == 3 && p.sw == 1) return launch(dwconv4_kernel<3, 1>);
+    if (p.kw == 3 && p.sw == 2) return launch(dwconv4_kernel<3, 2>);
+    if (p.kw == 5 && p.sw == 1) return launch(dwconv4_kernel<5, 1>);
+    if (p.kw == 1 && p.sw == 1) return launch(dwconv4_kernel<1, 1>);
+    return launch(dwconv4_kernel<0, 0>);
+  }
   const int V = aligned(8) ? 8 : aligned(4) ? 4 : 1;
   const long long total = (long long)p.B * p.Ho * p.Wo * (p.cout / V);
   const unsigned grid = (unsigned)((total + 255) / 256);
