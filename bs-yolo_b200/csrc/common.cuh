@@ -88,11 +88,13 @@ struct ConvParams {
   const float *bias;    // fp32 [cout_pad]
   int B, H, W, Ho, Wo, cin, cout, cout_pad;
   int kh, kw, sh, sw, ph, pw, act;
+  int asym;                          // 1: padding only before (top/left) -- the 2x2 space-to-depth stem
+  int epi_mode, a_off, A, nc;        // fused Detect decode (0 none, 1 DFL box, 2 class sigmoid) -> y (B,4+nc,A)
+  float det_stride;
 };
 
 // launchers (one per translation unit); all enqueue on `st` and return a b2y error code
 int launch_conv_simt(const ConvParams &p, cudaStream_t st);
-int launch_stem(const ConvParams &p, cudaStream_t st);
 int launch_dwconv(const ConvParams &p, cudaStream_t st);
 
 struct ConvTcPlan;  // opaque: tensor maps + geometry for one tcgen05 conv

@@ -1,5 +1,5 @@
 // CUDA-core convolution kernels: generic dense conv (validation twin of the tcgen05 kernel and the path for
-// shapes that kernel does not take), the Cin=3 stem, and depthwise kh x kw.
+// shapes that kernel does not take) and depthwise kh x kw.
 // Reference semantics: ultralytics/nn/modules/conv.py:145-151 (act(conv(x)+b) with BN folded), DWConv :224-229.
 #include "common.cuh"
 
@@ -66,69 +66,14 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvParams p) {
 }
 
 int launch_conv_simt(const ConvParams &p, cudaStream_t st) {
+  B2Y_REQUIRE(p.epi_mode == 0, B2Y_ERR_UNSUPPORTED,
+              "fused Detect decode exists only in the tcgen05 conv epilogue (plan with fuse_decode=False for the SIMT path)");
   const long long npix = (long long)p.B * p.Ho * p.Wo;
   dim3 grid((unsigned)((npix + 127) / 128), (unsigned)ceil_div(p.cout, 8));
   const bool vec = (p.cin % 8 == 0) && (p.in_cs % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
   if (vec) conv_simt_kernel<true><<<grid, 128, 0, st>>>(p);
   else conv_simt_kernel<false><<<grid, 128, 0, st>>>(p);
-  B2Y_LAUNCH_CHECK();
-  return B2Y_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ stem (Cin = 3)
-// Input: NHWC bf16 with 4 channels per pixel (R,G,B,0) as written by the preprocess kernel (8-byte pixels).
-// thread = 1 output pixel; the 27 inputs stay in registers while output channels are produced 16 at a time.
-// weights fp32 [cout][27] (tap-major, channel fastest) staged in shared memory.
-__global__ void __launch_bounds__(128) stem_kernel(ConvParams p) {
-  extern __shared__ float sw[];  // cout*27 weights + cout bias
-  const int nw = p.cout * 27;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = reinterpret_cast<const float *>(p.w)[i];
-  for (int i = threadIdx.x; i < p.cout; i += blockDim.x) sw[nw + i] = p.bias[i];
-  __syncthreads();
-  const long long npix = (long long)p.B * p.Ho * p.Wo;
-  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  const int wo = (int)(pix % p.Wo);
-  const int ho = (int)((pix / p.Wo) % p.Ho);
-  const int b = (int)(pix / ((long long)p.Wo * p.Ho));
-  float x[27];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int hi = ho * 2 - 1 + r;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int wi = wo * 2 - 1 + s;
-      float f[4] = {0.f, 0.f, 0.f, 0.f};
-      if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)
-        unpack4(*reinterpret_cast<const uint2 *>(p.in + ((size_t)(b * p.H + hi) * p.W + wi) * 4), f);
-      x[(r * 3 + s) * 3 + 0] = f[0];
-      x[(r * 3 + s) * 3 + 1] = f[1];
-      x[(r * 3 + s) * 3 + 2] = f[2];
-    }
-  }
-  bf16 *o = reinterpret_cast<bf16 *>(p.out) + (size_t)pix * p.out_cs;
-  for (int c0 = 0; c0 < p.cout; c0 += 8) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float *wj = sw + (c0 + j) * 27;
-      float a = sw[nw + c0 + j];
-#pragma unroll
-      for (int i = 0; i < 27; ++i) a = fmaf(x[i], wj[i], a);
-      v[j] = p.act ? silu_f(a) : a;
-    }
-    *reinterpret_cast<uint4 *>(o + c0) = pack8(v);
-  }
-}
-
-int launch_stem(const ConvParams &p, cudaStream_t st) {
-  B2Y_REQUIRE(p.cin == 3 && p.kh == 3 && p.kw == 3 && p.sh == 2 && p.sw == 2 && p.ph == 1 && p.pw == 1 &&
-                  p.in_cs == 4 && p.cout % 8 == 0 && p.out_cs % 8 == 0 && !p.out_f32 && p.res_mode == 0,
-              B2Y_ERR_UNSUPPORTED, "stem kernel: unsupported configuration");
-  const long long npix = (long long)p.B * p.Ho * p.Wo;
-  const size_t smem = (size_t)p.cout * 28 * sizeof(float);
-  stem_kernel<<<(unsigned)((npix + 127) / 128), 128, smem, st>>>(p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

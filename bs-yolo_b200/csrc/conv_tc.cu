@@ -64,6 +64,10 @@ struct TcGeom {
   // bf16 outputs leave through shared memory + TMA store
   int tma_out, oc, n_oboxes, obox_bytes, o_row_bytes, o_sw_mask, o_stages, o_stage_bytes;
   int o_off, bias_off;                  // byte offsets of the output staging area / bias table in dynamic smem
+  // fused Detect decode (head.py:100-131): epi_mode 1 = DFL + dist2bbox of the box branch, 2 = class sigmoid; both
+  // write straight into y (B, 4+nc, A) fp32 -- the raw head maps are never materialised
+  int epi_mode, a_off, A, nc;
+  float det_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -349,6 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nch = g.BN >> 4, nflat = g.MB * nch;
     int as = 0, os = 0;
     uint32_t aphase = 0;
+    float dfl_first = 0.f;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(g, tile);
       const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
@@ -390,6 +395,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 bb = bp[q];
             v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
           }
+        }
+        if (g.epi_mode) {
+          // ---- fused Detect._inference: thread = one anchor (pixel); chunk c of the box conv = one box side (16 DFL bins)
+          if (g.epi_mode == 1) {
+            float mx = v[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) mx = fmaxf(mx, v[q]);
+            float se = 0.f, sk = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float e = expf(v[q] - mx);
+              se += e;
+              sk = fmaf(e, (float)q, sk);
+            }
+            const float dist = sk / se;  // DFL expectation (block.py:73-76)
+            if (c < 2) {
+              dfl_first = dist;          // left (c = 0) or top (c = 1); the partner side arrives two chunks later
+            } else if (valid) {
+              const float anc = (c == 2 ? (float)wo : (float)ho) + 0.5f;  // make_anchors (tal.py:371-383)
+              const float p1 = anc - dfl_first, p2 = anc + dist;          // dist2bbox (tal.py:386-395)
+              float *yb = reinterpret_cast<float *>(g.out) + ((size_t)tc.b * (4 + g.nc) + (c - 2)) * g.A + g.a_off +
+                          (size_t)ho * g.Wo + wo;
+              yb[0] = ((p1 + p2) * 0.5f) * g.det_stride;         // cx | cy
+              yb[(size_t)2 * g.A] = (p2 - p1) * g.det_stride;   // w  | h
+            }
+          } else if (valid) {
+            float *yb = reinterpret_cast<float *>(g.out) + ((size_t)tc.b * (4 + g.nc) + 4 + n) * g.A + g.a_off +
+                        (size_t)ho * g.Wo + wo;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (n + q < g.cout) yb[(size_t)q * g.A] = 1.f / (1.f + expf(-v[q]));
+          }
+          continue;
         }
         const bool full16 = (n + 16 <= g.cout);
         if (g.res_mode && valid) {
@@ -498,6 +536,7 @@ typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap
 
 KernelFn pick_kernel(int taps, int ksteps) {
   if (taps == 1) return ksteps == 4 ? conv_tc_kernel<1, 4> : ksteps == 2 ? conv_tc_kernel<1, 2> : conv_tc_kernel<1, 1>;
+  if (taps == 4) return ksteps == 4 ? conv_tc_kernel<4, 4> : ksteps == 2 ? conv_tc_kernel<4, 2> : conv_tc_kernel<4, 1>;
   return ksteps == 4 ? conv_tc_kernel<9, 4> : ksteps == 2 ? conv_tc_kernel<9, 2> : conv_tc_kernel<9, 1>;
 }
 
@@ -518,9 +557,12 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
   };
   if (p.kh != p.kw) return no("non-square kernel");
   const bool k1 = p.kh == 1 && p.sh == 1 && p.sw == 1 && p.ph == 0 && p.pw == 0;
-  const bool k3s1 = p.kh == 3 && p.sh == 1 && p.sw == 1 && p.ph == 1 && p.pw == 1;
+  const bool k3s1 = p.kh == 3 && p.sh == 1 && p.sw == 1 && p.ph == 1 && p.pw == 1 && !p.asym;
   const bool k3s2 = p.kh == 3 && p.sh == 2 && p.sw == 2 && p.ph == 1 && p.pw == 1 && p.H % 2 == 0 && p.W % 2 == 0;
-  if (!(k1 || k3s1 || k3s2)) return no("kernel/stride/padding combination");
+  const bool k2 = p.kh == 2 && p.sh == 1 && p.sw == 1 && p.ph == 1 && p.pw == 1 && p.asym == 1;  // space-to-depth stem
+  if (!(k1 || k3s1 || k3s2 || k2)) return no("kernel/stride/padding combination");
+  if (p.epi_mode && !(k1 && p.out_f32 && p.res_mode == 0 && !p.act)) return no("fused decode needs a plain fp32 1x1 conv");
+  if (p.epi_mode == 1 && p.cout != 64) return no("fused DFL decode needs 64 box channels");
   if (p.cin % 16) return no("cin not a multiple of 16");
   if (p.cout_pad % 16) return no("cout_pad not a multiple of 16");
   if (p.in_cs % 8 || (reinterpret_cast<uintptr_t>(p.in) & 15)) return no("input view not 16-byte aligned");
@@ -546,8 +588,8 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   g.BK = (p.cin % 64 == 0) ? 64 : (p.cin % 32 == 0) ? 32 : 16;
   g.nkc = p.cin / g.BK;
   g.row_bytes = g.BK * 2;
-  const int halo = (p.kh == 3) ? (g.stride2 ? 1 : 2) : 0;  // extra halo columns/rows per tile
-  g.ox = g.oy = (p.kh == 3) ? 1 : 0;
+  const int halo = (p.kh == 3) ? (g.stride2 ? 1 : 2) : (p.kh == 2 ? 1 : 0);  // extra halo columns/rows per tile
+  g.ox = g.oy = (p.kh >= 2) ? 1 : 0;
   g.n_ntiles = ceil_div(p.cout_pad, 256);
   g.BN = ceil_div(ceil_div(p.cout_pad, g.n_ntiles), 16) * 16;
   // bf16 outputs are staged in shared memory and leave through TMA stores (coalesced, clipped, channel-sliced by the
@@ -594,7 +636,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     const long long tiles = (long long)p.B * ceil_div(p.Ho, mb * g.TH) * g.tiles_w * g.n_ntiles;
     if (cfg.mb <= 0 && mb > 1 && tiles < 4LL * num_sms * want_per_sm) continue;  // keep every SM busy with a few tiles
     const int box_rows = (mb * g.TH + halo) * g.P;
-    const int max_shift = (p.kh == 1) ? 0 : (g.stride2 ? g.P + 1 : 2 * g.P + 2);
+    const int max_shift = (p.kh == 1) ? 0 : ((g.stride2 || p.kh == 2) ? g.P + 1 : 2 * g.P + 2);
     const int need_rows = (mb - 1) * g.TH * g.P + max_shift + 128;
     const int plane = round_up((box_rows > need_rows ? box_rows : need_rows) * g.row_bytes, 1024);
     const int a_stage = g.nplanes * plane;
@@ -634,7 +676,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     for (int s = 0; s < p.kw; ++s) {
       const int t = r * p.kw + s;
       int plane = 0, shift = 0;
-      if (p.kh == 3 && !g.stride2) shift = r * g.P + s;
+      if ((p.kh == 3 && !g.stride2) || p.kh == 2) shift = r * g.P + s;
       else if (p.kh == 3) {
         plane = ((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1);
         shift = ((r == 0) ? 0 : 1) * g.P + ((s == 0) ? 0 : 1);
@@ -672,6 +714,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   g.out = p.out; g.out_cs = p.out_cs; g.out_f32 = p.out_f32;
   g.res = p.res; g.res_cs = p.res_cs; g.res_mode = p.res_mode;
   g.bias = p.bias; g.act = p.act;
+  g.epi_mode = p.epi_mode; g.a_off = p.a_off; g.A = p.A; g.nc = p.nc; g.det_stride = p.det_stride;
   {
     const uintptr_t o = reinterpret_cast<uintptr_t>(p.out);
     bool ok = (o & 15) == 0 && (p.out_f32 ? (p.out_cs % 4 == 0) : (p.out_cs % 8 == 0));

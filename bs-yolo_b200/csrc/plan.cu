@@ -90,12 +90,32 @@ int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
   c.B = pl->B; c.H = bi->H; c.W = bi->W; c.Ho = bo->H; c.Wo = bo->W;
   c.cin = o.cin; c.cout = o.cout; c.cout_pad = o.cout_pad;
   c.kh = o.kh; c.kw = o.kw; c.sh = o.sh; c.sw = o.sw; c.ph = o.ph; c.pw = o.pw; c.act = o.act;
+  c.asym = 0; c.epi_mode = 0; c.a_off = 0; c.A = 0; c.nc = 0; c.det_stride = 0.f;
+  if (o.kind == B2Y_OP_CONV) {
+    c.asym = o.ip[0];
+    c.epi_mode = o.ip[1];
+    c.a_off = o.ip[2];
+    c.A = o.ip[3];
+    c.nc = o.ip[4];
+    c.det_stride = o.fp[0];
+  }
+  if (c.epi_mode) {  // output operand is y (B, 4+nc, A) fp32; the conv's own map is the input map (1x1)
+    B2Y_REQUIRE(bo->dtype == B2Y_F32 && bo->C == c.A && bo->H == 4 + c.nc && c.a_off + bi->H * bi->W <= c.A,
+                B2Y_ERR_INVALID, "op %d: fused decode output must be y (B,4+nc,A) fp32", idx);
+    c.Ho = bi->H; c.Wo = bi->W;
+    c.out = R.ptr(o.out, 0);
+    c.out_cs = 0;
+    B2Y_REQUIRE(bi->dtype == B2Y_BF16 && c.w && c.bias && o.in_coff[0] + o.cin <= bi->C, B2Y_ERR_INVALID,
+                "op %d: fused decode conv operands", idx);
+    return B2Y_OK;
+  }
   B2Y_REQUIRE(bi->dtype == B2Y_BF16, B2Y_ERR_INVALID, "op %d: conv input must be bf16", idx);
   B2Y_REQUIRE(c.w && c.bias, B2Y_ERR_INVALID, "op %d: conv needs weights and bias", idx);
   B2Y_REQUIRE(o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C, B2Y_ERR_INVALID,
               "op %d: channel view out of range", idx);
-  B2Y_REQUIRE(o.sh > 0 && o.sw > 0 && c.Ho == (c.H + 2 * c.ph - c.kh) / c.sh + 1 &&
-                  c.Wo == (c.W + 2 * c.pw - c.kw) / c.sw + 1,
+  const int padf = c.asym ? 1 : 2;
+  B2Y_REQUIRE(o.sh > 0 && o.sw > 0 && c.Ho == (c.H + padf * c.ph - c.kh) / c.sh + 1 &&
+                  c.Wo == (c.W + padf * c.pw - c.kw) / c.sw + 1,
               B2Y_ERR_INVALID, "op %d: output map %dx%d inconsistent with input %dx%d k%dx%d s%d p%d", idx, c.Ho, c.Wo,
               c.H, c.W, c.kh, c.kw, c.sh, c.ph);
   return B2Y_OK;
@@ -109,8 +129,6 @@ int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
       return r.impl == B2Y_IMPL_TCGEN05 ? launch_conv_tc(r.tc, st) : launch_conv_simt(r.cp, st);
     case B2Y_OP_DWCONV:
       return launch_dwconv(r.cp, st);
-    case B2Y_OP_STEM:
-      return launch_stem(r.cp, st);
     case B2Y_OP_SPPF_POOL: {
       const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
       if (!R.ok) return B2Y_ERR_INVALID;
@@ -235,7 +253,7 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
     ResolvedOp &r = pl->ops[i];
     r.op = ops[i];
     const int k = r.op.kind;
-    if (k == B2Y_OP_CONV || k == B2Y_OP_DWCONV || k == B2Y_OP_STEM) {
+    if (k == B2Y_OP_CONV || k == B2Y_OP_DWCONV) {
       rc = resolve_conv(pl, r, i);
       if (rc != B2Y_OK) break;
       if (k == B2Y_OP_CONV) {
@@ -330,10 +348,18 @@ extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
   B2Y_CUDA_CHECK(cudaEventCreate(&e0));
   B2Y_CUDA_CHECK(cudaEventCreate(&e1));
   const int mbs[3] = {1, 2, 4};
+  const char *vb = getenv("B2Y_VERBOSE");
+  const bool verbose = vb && vb[0] == '1';
+  int op_index = -1;
   for (auto &r : pl->ops) {
+    ++op_index;
     if (r.op.kind != B2Y_OP_CONV || r.impl != B2Y_IMPL_TCGEN05) continue;
     float best_ms = 1e30f;
     ConvTcPlan *best = nullptr;
+    int best_mb = 0, best_ps = 0;
+    if (verbose)
+      fprintf(stderr, "[b2y autotune] op %3d %dx%d s%d cin %4d cout %4d map %dx%d:", op_index, r.cp.kh, r.cp.kw, r.cp.sh,
+              r.cp.cin, r.cp.cout, r.cp.Ho, r.cp.Wo);
     for (int per_sm = 1; per_sm <= 3; ++per_sm)
       for (int mi = 0; mi < 3; ++mi) {
         ConvTcPlan *cand = nullptr;
@@ -346,14 +372,18 @@ extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
           cudaEventRecord(e1, st);
           ok = ok && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess;
         }
+        if (verbose && ok) fprintf(stderr, " (%d,%d)=%.1fus", mbs[mi], per_sm, ms * 1000.f / 3.f);
         if (ok && ms < best_ms) {
           if (best) conv_tc_plan_destroy(best);
           best = cand;
           best_ms = ms;
+          best_mb = mbs[mi];
+          best_ps = per_sm;
         } else {
           conv_tc_plan_destroy(cand);
         }
       }
+    if (verbose) fprintf(stderr, "  -> mb %d per_sm %d\n", best_mb, best_ps);
     if (best) {
       conv_tc_plan_destroy(r.tc);
       r.tc = best;

@@ -51,9 +51,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
       }
     }
   }
-  if (p.fmt == 0) {
+  if (p.fmt == 0) {  // space-to-depth: pixel (y,x) -> super-pixel (y/2, x/2), channel group (y&1)*2 + (x&1)
     float f[4] = {__fdiv_rn((float)bgr[2], 255.f), __fdiv_rn((float)bgr[1], 255.f), __fdiv_rn((float)bgr[0], 255.f), 0.f};
-    reinterpret_cast<uint2 *>(p.dst)[idx] = pack4(f);
+    const size_t sp = ((size_t)b * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+    reinterpret_cast<uint2 *>(p.dst)[sp * 4 + ((y & 1) * 2 + (x & 1))] = pack4(f);
   } else if (p.fmt == 1) {
     float *o = reinterpret_cast<float *>(p.dst) + (size_t)b * 3 * p.H * p.W + (size_t)y * p.W + x;
     const size_t plane = (size_t)p.H * p.W;
@@ -73,6 +74,7 @@ extern "C" int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, 
   B2Y_REQUIRE(top >= 0 && left >= 0 && top + uh <= H && left + uw <= W && uh > 0 && uw > 0, B2Y_ERR_INVALID,
               "preprocess: letterbox geometry (%d,%d,%dx%d) does not fit %dx%d", top, left, uh, uw, H, W);
   B2Y_REQUIRE(dst_format >= 0 && dst_format <= 2, B2Y_ERR_INVALID, "preprocess: unknown dst_format %d", dst_format);
+  B2Y_REQUIRE(dst_format != 0 || (H % 2 == 0 && W % 2 == 0), B2Y_ERR_INVALID, "preprocess: network input needs even H, W");
   PreParams p;
   p.src = reinterpret_cast<const uint8_t *>(src);
   p.dst = dst;

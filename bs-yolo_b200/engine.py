@@ -29,15 +29,22 @@ def letterbox_geometry(shape, new_shape, auto: bool, stride: int = 32):
     return uh + top + bottom, uw + left + right, top, left, uh, uw
 
 
+def space_to_depth(x: torch.Tensor) -> torch.Tensor:
+    """(B,3,H,W) -> (B,H/2,W/2,16): channel ((y&1)*2 + (x&1))*4 + {R,G,B,0}, the network-input layout of b2y_preprocess."""
+    B, _, H, W = x.shape
+    x4 = torch.cat([x, torch.zeros_like(x[:, :1])], 1)
+    return x4.view(B, 4, H // 2, 2, W // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, H // 2, W // 2, 16)
+
+
 class Engine:
     def __init__(self, ir, batch: int, H: int, W: int, device: int | torch.device = 0, conv_impl: int = A.IMPL_AUTO,
-                 use_graph: bool = True, plan: Plan | None = None, autotune: bool = True):
+                 use_graph: bool = True, plan: Plan | None = None, autotune: bool = True, fuse_decode: bool = True):
         if not torch.cuda.is_available():
             raise A.B2YError("bs_yolo_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = A.lib()
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.B, self.H, self.W = batch, H, W
-        self.plan = plan if plan is not None else Plan(ir, H, W, conv_impl)
+        self.plan = plan if plan is not None else Plan(ir, H, W, conv_impl, fuse_decode=fuse_decode)
         self.nc, self.A = self.plan.nc, self.plan.A
         ops, bufs, ws_bytes = self.plan.c_arrays(batch)
         self._ops, self._bufs = ops, bufs  # keep alive
@@ -85,7 +92,10 @@ class Engine:
         return self.buffer(self.plan.y_buf).view(self.B, 4 + self.nc, self.A)
 
     def raw(self, level: int) -> torch.Tensor:
-        """(B, H_l, W_l, 64+nc) fp32 NHWC head map (permute(0,3,1,2) gives the reference's x[i], head.py:70)."""
+        """(B, H_l, W_l, 64+nc) fp32 NHWC head map (permute(0,3,1,2) gives the reference's x[i], head.py:70).
+        Only materialised by plans built with fuse_decode=False."""
+        if not self.plan.head_bufs:
+            raise A.B2YError("raw head maps are not materialised when Detect decode is fused (use fuse_decode=False)")
         return self.buffer(self.plan.head_bufs[level])
 
     def _stream(self) -> int:
@@ -95,9 +105,7 @@ class Engine:
     def set_input(self, x: torch.Tensor):
         """Tensor source (predictor.py:123-134 skips LetterBox for tensors): (B,3,H,W) float RGB in [0,1]."""
         assert tuple(x.shape) == (self.B, 3, self.H, self.W), (x.shape, (self.B, 3, self.H, self.W))
-        buf = self.input_nhwc
-        buf[..., :3] = x.to(self.device).permute(0, 2, 3, 1).to(torch.bfloat16)
-        buf[..., 3] = 0
+        self.input_nhwc.copy_(space_to_depth(x.to(self.device)).to(torch.bfloat16))
 
     def preprocess(self, src: torch.Tensor, auto: bool = False):
         """uint8 (B,h,w,3) BGR device tensor -> letterboxed, normalised NHWC bf16 network input (one kernel)."""

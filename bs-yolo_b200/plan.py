@@ -7,7 +7,10 @@ ultralytics/nn/tasks.py:138-165):
     Concat conv.py:455, Detect head.py:70) cost nothing: producers write straight into their slice of the concat
     buffer and consumers read slices through strided TMA descriptors;
   * BatchNorm is already folded (ir.py); bias + SiLU + residual add/mul happen in the conv epilogue;
-  * the Detect output convs emit fp32 so DFL / dist2bbox / sigmoid run in fp32 (decode.cu);
+  * DFL / dist2bbox / sigmoid run in fp32 on the fp32 accumulators of the Detect output convs: by default inside
+    those convs' epilogues (``fuse_decode``: the raw head maps never reach HBM), otherwise in decode.cu over fp32 maps;
+  * the 3-channel 3x3 stride-2 stem runs on the tensor cores as a 2x2 conv over the space-to-depth input the
+    preprocess kernel writes ((B, H/2, W/2, 16): four pixels x (R,G,B,0));
   * hidden channel counts that are not a multiple of 16 (the 8-channel Bottleneck of yolo11n layer 2) are
     zero-padded to 16 so the tensor-core path takes them.
 """
@@ -107,19 +110,23 @@ def _bf16_bits(t: torch.Tensor) -> np.ndarray:
 class Plan:
     """Flat op list + buffers + packed weights for one (H, W) input size (batch is bound later)."""
 
-    def __init__(self, ir: Node, H: int, W: int, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False):
+    def __init__(self, ir: Node, H: int, W: int, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
+                 fuse_decode: bool = True):
         if H % 32 or W % 32:
             raise ValueError(f"input {H}x{W} must be a multiple of the max stride 32 (utils/checks.py:120-171)")
         self.ir, self.H, self.W = ir, H, W
         self.conv_impl = conv_impl
         self.keep_fp32 = keep_fp32  # tests only: keep unrounded packed conv weights next to the bf16 blob
+        # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
+        self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
         self.bufs: list[BufSpec] = []
         self.ops: list[OpSpec] = []
         self.blob = WeightBlob()
         self.nc = ir["nc"]
         self.layer_out: dict[int, View] = {}
         self.layer_op_range: dict[int, tuple[int, int]] = {}
-        self.input_buf = self.new_buf(4, H, W, name="input_rgb0", exact=True)  # 8-byte pixels (R,G,B,0)
+        # network input, space-to-depth: channel ((y&1)*2 + (x&1))*4 + {R,G,B,0} of super-pixel (y/2, x/2)
+        self.input_buf = self.new_buf(16, H // 2, W // 2, name="input_s2d", exact=True)
         self.head_bufs: list[int] = []
         self.y_buf = -1
         self.A = 0
@@ -127,9 +134,10 @@ class Plan:
             self._lower()
 
     @classmethod
-    def empty(cls, H: int, W: int, nc: int = 1, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False) -> "Plan":
+    def empty(cls, H: int, W: int, nc: int = 1, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
+              fuse_decode: bool = True) -> "Plan":
         """A plan with no ops (unit tests append single ops through the same lowering helpers)."""
-        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32)
+        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode)
 
     # ------------------------------------------------------------------ buffers / views
     def new_buf(self, C, H, W, dtype=A.BF16, name="", exact=False) -> int:
@@ -147,8 +155,10 @@ class Plan:
 
     # ------------------------------------------------------------------ conv family
     def conv(self, n: Node, x: View, dest: View | None = None, res: View | None = None, res_mode=A.RES_NONE,
-             out_dtype=A.BF16, pad16=False, wb=None) -> View:
-        """Conv / DWConv node -> one op. ``wb``: optional (weight, bias) override (used for folded variants)."""
+             out_dtype=A.BF16, pad16=False, wb=None, decode=None) -> View:
+        """Conv / DWConv node -> one op. ``wb``: optional (weight, bias) override (used for folded variants).
+        ``decode`` = (mode, anchor offset, stride): the conv is a Detect output conv whose epilogue applies
+        Detect._inference (head.py:100-131) and writes rows of y (B, 4+nc, A) instead of a raw map."""
         w, b = wb if wb is not None else (n["weight"], n["bias"])
         c1, c2, (kh, kw), (sh, sw), (ph, pw), g = n["c1"], n["c2"], n["k"], n["s"], n["p"], n["g"]
         assert x.real == c1, (n["name"], x, c1)
@@ -157,11 +167,14 @@ class Plan:
         if g == 1:
             cpad = _r(c2, 16)
             cstore = cpad if (pad16 and dest is None) else c2
-            if dest is None:
+            if decode is not None:
+                assert (kh, kw, sh, sw) == (1, 1, 1, 1) and not act and res is None and self.y_buf >= 0
+                dest = self.y_buf
+            elif dest is None:
                 dest = self.full(self.new_buf(cstore, Ho, Wo, out_dtype, n["name"]), cstore)
                 if cstore != c2:
                     dest = View(dest.buf, 0, cstore, Ho, Wo, creal=c2)
-            assert dest.c == cstore and (dest.H, dest.W) == (Ho, Wo), (n["name"], dest, cstore, Ho, Wo)
+            assert decode is not None or (dest.c == cstore and (dest.H, dest.W) == (Ho, Wo)), (n["name"], dest, cstore, Ho, Wo)
             wp = torch.zeros(cpad, kh * kw, x.c)
             wp[:c2, :, :c1] = w.permute(0, 2, 3, 1).reshape(c2, kh * kw, c1)
             bp = torch.zeros(cpad)
@@ -174,6 +187,11 @@ class Plan:
             op.flops = 2 * c2 * c1 * kh * kw * Ho * Wo
             esz = 4 if out_dtype == A.F32 else 2
             op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * esz + c2 * c1 * kh * kw * 2
+            if decode is not None:
+                mode, a_off, stride = decode
+                op.ip, op.fp = (0, mode, a_off, self.A, self.nc), (float(stride),)
+                rows = 4 if mode == 1 else c2
+                op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + c2 * c1 * 2
         else:
             assert g == c1 == c2, f"{n['name']}: only depthwise grouped convs are on the hot path"
             if dest is None:
@@ -189,17 +207,29 @@ class Plan:
         return dest
 
     def stem(self, n: Node, dest: View | None) -> View:
+        """3-channel 3x3 s2 p1 stem as a 2x2 s1 conv over the space-to-depth input (K = 4 taps x 16), padded before
+        only: input row 2*ho-1+r lies in super-row ho-1+R with parity py, (r -> R,py) = (0 -> 0,1), (1 -> 1,0), (2 -> 1,1)."""
         c2 = n["c2"]
-        assert n["c1"] == 3 and n["k"] == (3, 3) and n["s"] == (2, 2) and n["g"] == 1
+        assert n["c1"] == 3 and n["k"] == (3, 3) and n["s"] == (2, 2) and n["p"] == (1, 1) and n["g"] == 1
         Ho, Wo = self.H // 2, self.W // 2
+        cpad = _r(c2, 16)
         if dest is None:
             dest = self.full(self.new_buf(c2, Ho, Wo, name=n["name"]), c2)
-        wp = n["weight"].permute(0, 2, 3, 1).reshape(c2, 27)  # [(r*3+s)*3 + rgb]
-        op = OpSpec(A.OP_STEM, n["name"], [View(self.input_buf, 0, 3, self.H, self.W)], dest, None, A.RES_NONE, 3, c2, c2,
-                    (3, 3), (2, 2), (1, 1), 1 if n["act"] == "silu" else 0, A.IMPL_SIMT,
-                    self.blob.add(wp.numpy().astype(np.float32)), self.blob.add(n["bias"].numpy().astype(np.float32)))
+        rp = ((0, 1), (1, 0), (1, 1))
+        wp = torch.zeros(cpad, 2, 2, 4, 4)  # [co][R][S][py*2+px][rgb0]
+        for r in range(3):
+            for s_ in range(3):
+                (R, py), (S, px) = rp[r], rp[s_]
+                wp[:c2, R, S, py * 2 + px, :3] = n["weight"][:, :, r, s_]
+        bp = torch.zeros(cpad)
+        bp[:c2] = n["bias"]
+        op = OpSpec(A.OP_CONV, n["name"], [View(self.input_buf, 0, 16, Ho, Wo)], dest, None, A.RES_NONE, 16, c2, cpad,
+                    (2, 2), (1, 1), (1, 1), 1 if n["act"] == "silu" else 0, self.conv_impl,
+                    self.blob.add(_bf16_bits(wp.reshape(cpad, -1))), self.blob.add(bp.numpy().astype(np.float32)), ip=(1,))
+        if self.keep_fp32:
+            op.w_fp32 = wp.reshape(cpad, -1).clone()
         op.flops = 2 * c2 * 27 * Ho * Wo
-        op.bytes_alg = 3 * self.H * self.W * 2 + c2 * Ho * Wo * 2
+        op.bytes_alg = 3 * self.H * self.W * 2 + c2 * Ho * Wo * 2 + c2 * 27 * 2
         self.ops.append(op)
         return dest
 
@@ -342,22 +372,30 @@ class Plan:
     def detect(self, n, xs):
         nc = n["nc"]
         no = 64 + nc
+        self.A = sum(x.H * x.W for x in xs)
+        self.y_buf = self.new_buf(self.A, 4 + nc, 1, A.F32, n["name"] + ".y")
+        a_off = 0
         for i, x in enumerate(xs):
-            hb = self.new_buf(no, x.H, x.W, A.F32, f"{n['name']}.raw{i}")
-            self.head_bufs.append(hb)
-            head = View(hb, 0, no, x.H, x.W)
             t = self.conv(n["cv2"][i][1], self.conv(n["cv2"][i][0], x))
-            self.conv(n["cv2"][i][2], t, self.sub(head, 0, 64), out_dtype=A.F32)
             c3 = n["cv3"][i]
             s = self.conv(c3[0][1], self.conv(c3[0][0], x))
             s = self.conv(c3[1][1], self.conv(c3[1][0], s))
-            self.conv(c3[2], s, self.sub(head, 64, nc), out_dtype=A.F32)
-        self.A = sum(x.H * x.W for x in xs)
-        self.y_buf = self.new_buf(self.A, 4 + nc, 1, A.F32, n["name"] + ".y")
-        op = OpSpec(A.OP_DECODE, n["name"] + ".decode", list(self.head_bufs), self.y_buf, cin=no, cout=4 + nc,
-                    ip=(nc, len(xs)), fp=tuple(float(s) for s in n["stride"]))
-        op.bytes_alg = self.A * (no * 4 + (4 + nc) * 4)
-        self.ops.append(op)
+            if self.fuse_decode:
+                stride = float(n["stride"][i])
+                self.conv(n["cv2"][i][2], t, out_dtype=A.F32, decode=(1, a_off, stride))
+                self.conv(c3[2], s, out_dtype=A.F32, decode=(2, a_off, stride))
+            else:
+                hb = self.new_buf(no, x.H, x.W, A.F32, f"{n['name']}.raw{i}")
+                self.head_bufs.append(hb)
+                head = View(hb, 0, no, x.H, x.W)
+                self.conv(n["cv2"][i][2], t, self.sub(head, 0, 64), out_dtype=A.F32)
+                self.conv(c3[2], s, self.sub(head, 64, nc), out_dtype=A.F32)
+            a_off += x.H * x.W
+        if not self.fuse_decode:
+            op = OpSpec(A.OP_DECODE, n["name"] + ".decode", list(self.head_bufs), self.y_buf, cin=no, cout=4 + nc,
+                        ip=(nc, len(xs)), fp=tuple(float(s) for s in n["stride"]))
+            op.bytes_alg = self.A * (no * 4 + (4 + nc) * 4)
+            self.ops.append(op)
 
     # ------------------------------------------------------------------ whole graph
     def _lower(self):

@@ -38,9 +38,11 @@ enum {
 enum b2y_dtype { B2Y_BF16 = 0, B2Y_F32 = 1 };
 
 enum b2y_op_kind {
-  B2Y_OP_CONV = 1,      /* dense conv k{1,3} s{1,2} + bias (+SiLU) (+residual add|mul); conv.py:145-151         */
+  B2Y_OP_CONV = 1,      /* dense conv k{1,3} s{1,2} + bias (+SiLU) (+residual add|mul); conv.py:145-151.  ip[0]=1: 2x2
+                           conv padded before only (the 3x3 s2 stem on the space-to-depth input); ip[1]: fused Detect
+                           decode epilogue 1 = DFL+dist2bbox, 2 = class sigmoid (head.py:100-131) writing y (B,4+nc,A):
+                           ip[2] anchor offset, ip[3] A, ip[4] nc, fp[0] stride                                      */
   B2Y_OP_DWCONV = 2,    /* depthwise kh x kw conv + bias (+SiLU) (+residual add); conv.py:224-229, MSCA.py:24-39  */
-  B2Y_OP_STEM = 3,      /* Cin=3 3x3 s2 first conv on the 4-channel-padded preprocess output                     */
   B2Y_OP_SPPF_POOL = 4, /* three chained MaxPool2d(5,1,2) written to three channel slices; block.py:3145-3149   */
   B2Y_OP_RESAMPLE = 5,  /* channel-slice copy, optionally nearest 2x upsample (nn.Upsample, Concat conv.py:455)  */
   B2Y_OP_ATTN = 6,      /* softmax(q^T k * kd^-0.5) v per head; block.py:4280-4286                               */
@@ -108,7 +110,8 @@ B2Y_API int b2y_plan_op_impl(const b2y_plan *plan, int32_t i);
 /* ---- preprocess: LetterBox + BGR->RGB + /255 (ultralytics/data/augment.py:1535-1601,
  *      engine/predictor.py:116-134).  src: B x h x w x 3 uint8 (device).  The resized image (uw x uh, OpenCV
  *      INTER_LINEAR fixed-point semantics; identity when uw==w && uh==h) is placed at (top,left) of an H x W canvas
- *      padded with 114.  dst_format 0: NHWC bf16 with 4 channels (R,G,B,0) feeding the stem; 1: NCHW fp32 (the
+ *      padded with 114.  dst_format 0: the network input, NHWC bf16 space-to-depth: (B, H/2, W/2, 16) with channel
+ *      ((y&1)*2 + (x&1))*4 + {R,G,B,0} -- the 3x3 s2 stem becomes a 2x2 tensor-core conv over it; 1: NCHW fp32 (the
  *      reference's tensor); 2: HWC uint8 letterboxed BGR (LetterBox output, for bit-exact tests). */
 B2Y_API int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, void *dst, int32_t H, int32_t W, int32_t top,
                    int32_t left, int32_t uh, int32_t uw, int32_t dst_format, void *stream);

@@ -38,7 +38,8 @@ class PlanEmulator:
         self.bufs[v.buf][..., v.coff:v.coff + c] = val[..., :c]
 
     def set_input(self, x):  # (B,3,H,W) float
-        self.bufs[self.plan.input_buf][..., :3] = x.permute(0, 2, 3, 1)
+        from bs_yolo_b200.engine import space_to_depth
+        self.bufs[self.plan.input_buf] = space_to_depth(x).clone()
         if self.round:
             self.bufs[self.plan.input_buf] = self.bufs[self.plan.input_buf].to(torch.bfloat16).float()
 
@@ -61,7 +62,25 @@ class PlanEmulator:
         wflat = op.w_fp32 if (op.w_fp32 is not None and not self.round) else self.bf16(op.w_off, op.cout_pad * kh * kw * op.cin)
         w = wflat.reshape(op.cout_pad, kh, kw, op.cin).permute(0, 3, 1, 2)
         b = self.f32(op.b_off, op.cout_pad)
-        y = F.conv2d(x, w, b, stride=op.s, padding=op.p).permute(0, 2, 3, 1)
+        ip = tuple(op.ip) + (0,) * 5
+        if ip[0]:  # padding before (top/left) only: the 2x2 space-to-depth stem
+            y = F.conv2d(F.pad(x, (op.p[1], 0, op.p[0], 0)), w, b, stride=op.s).permute(0, 2, 3, 1)
+        else:
+            y = F.conv2d(x, w, b, stride=op.s, padding=op.p).permute(0, 2, 3, 1)
+        if ip[1]:  # fused Detect._inference epilogue (head.py:100-131): writes rows of y (B, 4+nc, A)
+            mode, a_off, nc = ip[1], ip[2], ip[4]
+            B, H, W, _ = y.shape
+            ybuf = self.bufs[op.out][:, :, 0, :]
+            if mode == 1:
+                d = torch.softmax(y[..., :64].reshape(B, H, W, 4, 16), -1) @ torch.arange(16, dtype=torch.float32)
+                ax = (torch.arange(W, dtype=torch.float32) + 0.5).view(1, 1, W)
+                ay = (torch.arange(H, dtype=torch.float32) + 0.5).view(1, H, 1)
+                x1, y1, x2, y2 = ax - d[..., 0], ay - d[..., 1], ax + d[..., 2], ay + d[..., 3]
+                box = torch.stack([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], 1) * op.fp[0]  # (B,4,H,W)
+                ybuf[:, 0:4, a_off:a_off + H * W] = box.reshape(B, 4, H * W)
+            else:
+                ybuf[:, 4:4 + nc, a_off:a_off + H * W] = torch.sigmoid(y[..., :nc]).permute(0, 3, 1, 2).reshape(B, nc, H * W)
+            return
         self._epilogue(op, y)
 
     def op_dwconv(self, op):
@@ -70,13 +89,6 @@ class PlanEmulator:
         x = self.get(op.ins[0]).permute(0, 3, 1, 2)
         w = self.f32(op.w_off, kh * kw * c).view(kh, kw, c).permute(2, 0, 1).unsqueeze(1)
         y = F.conv2d(x, w, self.f32(op.b_off, c), stride=op.s, padding=op.p, groups=c).permute(0, 2, 3, 1)
-        self._epilogue(op, y)
-
-    def op_stem(self, op):
-        c = op.cout
-        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
-        w = self.f32(op.w_off, c * 27).view(c, 3, 3, 3).permute(0, 3, 1, 2)
-        y = F.conv2d(x, w, self.f32(op.b_off, c), stride=2, padding=1).permute(0, 2, 3, 1)
         self._epilogue(op, y)
 
     def op_sppf_pool(self, op):

@@ -133,7 +133,7 @@ def _run_engine(g, x, **kw):
 def test_network_heads_vs_reference_golden(case, golden_dir):
     gld = np.load(os.path.join(golden_dir, f"net_{case}.npz"))
     g = _graph(kat.NET_CASES[case][0])
-    eng = _run_engine(g, torch.from_numpy(kat.net_input(case)))
+    eng = _run_engine(g, torch.from_numpy(kat.net_input(case)), fuse_decode=False)
     for i in range(3):
         ref = torch.from_numpy(gld[f"raw{i}"])
         got = eng.raw(i).permute(0, 3, 1, 2).float().cpu()
@@ -165,16 +165,23 @@ def test_end_to_end_640_vs_oracle(model, B):
     from bs_yolo_b200.engine import Engine
     g = _graph(model)
     imgs = np.random.default_rng(9).integers(0, 256, (B, 640, 640, 3), dtype=np.uint8)
-    eng = Engine(g, B, 640, 640)
+    eng = Engine(g, B, 640, 640)  # the product path: Detect decode fused into the head convs' epilogues
     eng.preprocess(torch.from_numpy(imgs).cuda())
     y = eng.forward()
     dets, counts = eng.nms(0.25, 0.7, 300)
     torch.cuda.synchronize()
     x = torch.from_numpy(oracle_post.preprocess(list(imgs), (640, 640)))
     y_ref, raws_ref = oracle_net.forward(g, x)
+    raw_eng = Engine(g, B, 640, 640, fuse_decode=False)  # same kernels, raw head maps materialised for the 1e-2 gate
+    raw_eng.preprocess(torch.from_numpy(imgs).cuda())
+    y_unfused = raw_eng.forward()
+    torch.cuda.synchronize()
     for i, r in enumerate(raws_ref):
-        got = eng.raw(i).permute(0, 3, 1, 2).float().cpu()
+        got = raw_eng.raw(i).permute(0, 3, 1, 2).float().cpu()
         assert float((got - r).norm() / r.norm()) < 1e-2
+    # fused epilogue == decode kernel on the same fp32 accumulators (expf / summation-order noise only)
+    assert float((y[:, :4] - y_unfused[:, :4]).abs().max()) < 2e-2
+    assert float((y[:, 4:] - y_unfused[:, 4:]).abs().max()) < 1e-5
     # NMS bit-exact on the identical decoded tensor the GPU produced
     ref_same = oracle_post.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
     n = counts.cpu().tolist()
@@ -199,6 +206,56 @@ def test_end_to_end_640_vs_oracle(model, B):
                 matched += 1
     # bf16 can flip candidates sitting within 1e-2 of the conf threshold or reorder near-tied NMS decisions
     assert matched >= 0.9 * total, (matched, total)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("c2,hw", [(16, (64, 96)), (96, (128, 64)), (16, (640, 640))])
+def test_stem_space_to_depth_conv(impl, c2, hw):
+    """3x3 s2 stem (conv.py:145-151 on the 3-channel input) lowered to a 2x2 conv over the space-to-depth input."""
+    import torch.nn.functional as F
+    from bs_yolo_b200.engine import Engine
+    from bs_yolo_b200.plan import Plan
+    rng = np.random.default_rng(c2)
+    w = torch.from_numpy(rng.standard_normal((c2, 3, 3, 3)).astype(np.float32) / 5)
+    b = torch.from_numpy(rng.standard_normal(c2).astype(np.float32) * 0.1)
+    node = dict(type="Conv", name="stem", c1=3, c2=c2, k=(3, 3), s=(2, 2), p=(1, 1), g=1, act="silu", weight=w, bias=b)
+    plan = Plan.empty(*hw, conv_impl=A.IMPL_SIMT if impl == "simt" else A.IMPL_TCGEN05)
+    out = plan.stem(node, None)
+    B = 3
+    eng = Engine(None, B, *hw, use_graph=False, plan=plan)
+    x = torch.from_numpy(rng.random((B, 3, *hw), dtype=np.float32))
+    eng.set_input(x)
+    eng.forward()
+    torch.cuda.synchronize()
+    assert eng.op_impl(0) == (A.IMPL_SIMT if impl == "simt" else A.IMPL_TCGEN05)
+    ref = F.silu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride=2, padding=1))
+    got = eng.view_tensor(out).permute(0, 3, 1, 2).float().cpu()
+    assert float((got - ref).norm() / ref.norm()) < 4e-3
+
+
+def test_preprocess_writes_space_to_depth_input():
+    from bs_yolo_b200.engine import Engine, space_to_depth
+    g = _graph("yolo11n")
+    imgs = np.random.default_rng(4).integers(0, 256, (2, 96, 128, 3), dtype=np.uint8)
+    eng = Engine(g, 2, 96, 128, use_graph=False)
+    eng.preprocess(torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    ref = space_to_depth(torch.from_numpy(oracle_post.preprocess(list(imgs), (96, 128)))).bfloat16()
+    assert torch.equal(eng.input_nhwc.cpu(), ref)
+
+
+@pytest.mark.parametrize("model", ["yolo11n", "bsyolo_n"])
+def test_fused_decode_equals_decode_kernel(model):
+    """Detect._inference in the head convs' epilogues vs raw fp32 maps + decode.cu, odd map sizes, several tiles."""
+    g = _graph(model)
+    x = torch.from_numpy(np.random.default_rng(6).random((3, 3, 224, 352), dtype=np.float32))
+    a = _run_engine(g, x, fuse_decode=False).y.clone()
+    e = _run_engine(g, x, fuse_decode=True)
+    assert not e.plan.head_bufs and A.OP_DECODE not in [o.kind for o in e.plan.ops]
+    assert float((e.y[:, :4] - a[:, :4]).abs().max()) < 2e-2
+    assert float((e.y[:, 4:] - a[:, 4:]).abs().max()) < 1e-5
+    y_ref, _ = oracle_net.forward(g, x)
+    assert float((e.y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) < 5e-2  # bf16 network vs fp32 oracle, scores
 
 
 def test_graph_replay_equals_eager():

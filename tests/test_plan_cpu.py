@@ -17,10 +17,11 @@ def _graph(model, seed=0):
     return ir.build_ir(spec, arch.synth_state_dict(spec, seed))
 
 
+@pytest.mark.parametrize("fuse_decode", [False, True])
 @pytest.mark.parametrize("model,hw", [("yolo11n", (64, 96)), ("bsyolo_n", (64, 96)), ("yolo11x", (64, 64))])
-def test_lowered_plan_matches_oracle_fp32(model, hw):
+def test_lowered_plan_matches_oracle_fp32(model, hw, fuse_decode):
     g = _graph(model)
-    plan = Plan(g, *hw, keep_fp32=True)
+    plan = Plan(g, *hw, keep_fp32=True, fuse_decode=fuse_decode)
     B = 2
     x = torch.from_numpy(np.random.default_rng(7).random((B, 3, *hw), dtype=np.float32))
     emu = PlanEmulator(plan, B)
@@ -28,6 +29,7 @@ def test_lowered_plan_matches_oracle_fp32(model, hw):
     emu.run()
     cap = {}
     y, raws = oracle_net.forward(g, x, capture=cap)
+    assert len(emu.raws()) == (0 if fuse_decode else 3)
     for a, b in zip(emu.raws(), raws):
         assert float((a - b).norm() / b.norm()) < 2e-5
     assert float((emu.y() - y).abs().max()) < 1e-3
@@ -43,7 +45,7 @@ def test_plan_matches_golden_reference_outputs(golden_dir):
     import os
     case = "yolo11n_64x96"
     gld = np.load(os.path.join(golden_dir, f"net_{case}.npz"))
-    plan = Plan(_graph("yolo11n"), 64, 96, keep_fp32=True)
+    plan = Plan(_graph("yolo11n"), 64, 96, keep_fp32=True, fuse_decode=False)
     emu = PlanEmulator(plan, 2)
     emu.set_input(torch.from_numpy(kat.net_input(case)))
     emu.run()
@@ -55,7 +57,7 @@ def test_plan_matches_golden_reference_outputs(golden_dir):
 def test_bf16_storage_error_budget():
     """Rounding every bf16 buffer and weight (what the CUDA path stores) stays inside the 1e-2 head-output gate."""
     g = _graph("yolo11n")
-    plan = Plan(g, 64, 96)
+    plan = Plan(g, 64, 96, fuse_decode=False)
     x = torch.from_numpy(np.random.default_rng(8).random((2, 3, 64, 96), dtype=np.float32))
     emu = PlanEmulator(plan, 2, round_bf16=True)
     emu.set_input(x)
@@ -66,11 +68,17 @@ def test_bf16_storage_error_budget():
 
 
 def test_structure_and_alignment():
+    unfused = Plan(_graph("yolo11n"), 640, 640, fuse_decode=False)
+    assert unfused.ops[-1].kind == A.OP_DECODE and len(unfused.head_bufs) == 3
     plan = Plan(_graph("yolo11n"), 640, 640)
     kinds = [o.kind for o in plan.ops]
-    assert kinds[0] == A.OP_STEM and kinds[-1] == A.OP_DECODE
+    assert len(plan.ops) == len(unfused.ops) - 1 and A.OP_DECODE not in kinds and not plan.head_bufs
+    assert [tuple(o.ip[1:3]) for o in plan.ops if o.kind == A.OP_CONV and len(o.ip) > 1 and o.ip[1]] == [(1, 0), (2, 0), (1, 6400), (2, 6400), (1, 8000), (2, 8000)]
+    stem = plan.ops[0]  # 3x3 s2 stem as a 2x2 conv over the space-to-depth input
+    assert stem.kind == A.OP_CONV and stem.k == (2, 2) and stem.cin == 16 and stem.ip[0] == 1
+    assert (plan.bufs[plan.input_buf].C, plan.bufs[plan.input_buf].H) == (16, 320)
     assert plan.A == 8400 and plan.bufs[plan.y_buf].H == 84
-    n_conv = sum(k in (A.OP_CONV, A.OP_DWCONV, A.OP_STEM) for k in kinds)
+    n_conv = sum(k in (A.OP_CONV, A.OP_DWCONV) for k in kinds)
     assert n_conv == 88  # SURVEY C.1 lists 88 convs incl. DFL's (fused into decode here); pe is split per head (+1)
     assert sum(k == A.OP_RESAMPLE for k in kinds) == 2  # only the two nearest-2x upsamples; every concat is fused away
     for o in plan.ops:
