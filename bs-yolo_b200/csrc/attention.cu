@@ -37,6 +37,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __global__ void __launch_bounds__(NT) attention_kernel(const bf16 *__restrict__ qkv, int cs, bf16 *__restrict__ out,
                                                        int out_cs, int N, float scale_log2e) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) uint8_t Ksm[2][KT * KPITCH];
   __shared__ __align__(16) uint8_t Vsm[2][KT * VPITCH];
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
@@ -174,7 +176,7 @@ int launch_attention(const bf16 *qkv, int qkv_cs, bf16 *out, int out_cs, int B, 
               B2Y_ERR_UNSUPPORTED, "attention: qkv must be 16-byte aligned, out 4-byte aligned");
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)kd);
   dim3 grid(ceil_div(N, QT), nh, B);
-  attention_kernel<<<grid, NT, 0, st>>>(qkv, qkv_cs, out, out_cs, N, scale_log2e);
+  b2y_launch(attention_kernel, dim3(grid), dim3(NT), 0, st, qkv, qkv_cs, out, out_cs, N, scale_log2e);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

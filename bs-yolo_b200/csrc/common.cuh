@@ -39,6 +39,37 @@ void b2y_set_error(const char *fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Every kernel of the library is launched through b2y_launch with programmatic stream serialization: kernel N+1 may
+// become resident (and run its prologue: barrier init, TMEM alloc, weight loads) while kernel N is still draining.
+// Contract for every kernel launched this way:
+//   * pdl_launch_dependents() as early as the kernel's own resources are secured (after tcgen05.alloc);
+//   * pdl_wait() before the first access to memory another kernel may have written or may still read.  It returns only
+//     when the preceding grid has completed and flushed; because every grid executes it, completion is transitive.
+// B2Y_PDL=0 in the environment turns the launch attribute off (the device-side instructions are then no-ops).
+bool b2y_pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b2y_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = b2y_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // A strided NHWC view: element (b,h,w,c) lives at base[((b*H + h)*W + w)*cs + c].
 struct View {
   void *base;   // already offset to the view's first channel

@@ -7,6 +7,8 @@
 // thread = 1 output pixel x 8 output channels; weights [cout_pad][kh*kw*cin] bf16 are warp-uniform (broadcast loads).
 template <bool VEC>
 __global__ void __launch_bounds__(128) conv_simt_kernel(ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long npix = (long long)p.B * p.Ho * p.Wo;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
@@ -72,8 +74,8 @@ int launch_conv_simt(const ConvParams &p, cudaStream_t st) {
   dim3 grid((unsigned)((npix + 127) / 128), (unsigned)ceil_div(p.cout, 8));
   const bool vec = (p.cin % 8 == 0) && (p.in_cs % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0);
-  if (vec) conv_simt_kernel<true><<<grid, 128, 0, st>>>(p);
-  else conv_simt_kernel<false><<<grid, 128, 0, st>>>(p);
+  if (vec) b2y_launch(conv_simt_kernel<true>, dim3(grid), dim3(128), 0, st, p);
+  else b2y_launch(conv_simt_kernel<false>, dim3(grid), dim3(128), 0, st, p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -82,6 +84,8 @@ int launch_conv_simt(const ConvParams &p, cudaStream_t st) {
 // thread = 1 output pixel x V channels (V = 8: 16-byte, 4: 8-byte, 1: scalar accesses); weights fp32 [kh*kw][c].
 template <int V>
 __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cg = p.cout / V;
   const long long total = (long long)p.B * p.Ho * p.Wo * cg;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,11 +140,13 @@ __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
 // the whole layer sit in shared memory ([kh*kw][c] fp32 + bias) and are read as broadcast float4s.
 template <int KW, int SW>  // KW == 0: runtime kernel width / stride
 __global__ void __launch_bounds__(256) dwconv4_kernel(ConvParams p, int wq) {
+  pdl_launch_dependents();
   extern __shared__ float wsm[];
   const int taps = p.kh * p.kw;
   for (int i = threadIdx.x; i < taps * p.cout; i += blockDim.x) wsm[i] = reinterpret_cast<const float *>(p.w)[i];
   for (int i = threadIdx.x; i < p.cout; i += blockDim.x) wsm[taps * p.cout + i] = p.bias[i];
   __syncthreads();
+  pdl_wait();
   const int kw = KW ? KW : p.kw, sw = KW ? SW : p.sw;
   const int cg = p.cout / 8;
   const long long total = (long long)p.B * p.Ho * wq * cg;
@@ -228,6 +234,97 @@ __global__ void __launch_bounds__(256) dwconv4_kernel(ConvParams p, int wq) {
   }
 }
 
+// Row-strip variant for stride-1 kernels whose taps fit the register file (3x3, 1xk, kx1, 5x5):
+// thread = 4 channels x one output column x a strip of R output rows.  The KH*KW*4 weights live in registers for the
+// whole strip; every input row of the strip is loaded ONCE per thread (KW 8-byte pixels, column neighbours hit in L1) and
+// scattered into KH rolling fp32 accumulators (slot r holds output row i + ph - r), so per 4-channel output there are
+// KW loads, KH*KW*4 FMAs, one tanh.approx SiLU per channel and one 8-byte store.  Consecutive lanes cover consecutive
+// channel groups, then consecutive columns: every warp access is one contiguous segment of the NHWC row.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(256, (KH * KW <= 9) ? 3 : 1) dwconv_strip_kernel(ConvParams p, int R, int nstrips) {
+  pdl_launch_dependents();
+  const int cg = p.cout >> 2;
+  const long long total = (long long)p.B * nstrips * p.Wo * cg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c0 = (int)(idx % cg) * 4;
+  long long t = idx / cg;
+  const int wo = (int)(t % p.Wo);
+  t /= p.Wo;
+  const int strip = (int)(t % nstrips);
+  const int b = (int)(t / nstrips);
+  float4 w[KH * KW];
+  const float *wp = reinterpret_cast<const float *>(p.w) + c0;
+#pragma unroll
+  for (int i = 0; i < KH * KW; ++i) w[i] = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)i * p.cout));
+  const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + c0));
+  pdl_wait();  // weights are constants: only the activations depend on the preceding kernel
+  const int ho0 = strip * R, ho1 = min(ho0 + R, p.Ho);
+  float4 acc[KH];
+#pragma unroll
+  for (int r = 0; r < KH; ++r) acc[r] = bias;
+  const bf16 *img = p.in + (size_t)b * p.H * p.W * p.in_cs + c0;
+  for (int i = ho0 - p.ph; i < ho1 - p.ph + KH - 1; ++i) {
+    if (i >= 0 && i < p.H) {
+      const bf16 *row = img + (size_t)i * p.W * p.in_cs;
+#pragma unroll
+      for (int s_ = 0; s_ < KW; ++s_) {
+        const int wi = wo - p.pw + s_;
+        if (wi < 0 || wi >= p.W) continue;
+        float x[4];
+        unpack4(__ldg(reinterpret_cast<const uint2 *>(row + (size_t)wi * p.in_cs)), x);
+#pragma unroll
+        for (int r = 0; r < KH; ++r) {
+          const float4 ww = w[r * KW + s_];
+          acc[r].x = fmaf(x[0], ww.x, acc[r].x);
+          acc[r].y = fmaf(x[1], ww.y, acc[r].y);
+          acc[r].z = fmaf(x[2], ww.z, acc[r].z);
+          acc[r].w = fmaf(x[3], ww.w, acc[r].w);
+        }
+      }
+    }
+    const int ho = i + p.ph - (KH - 1);  // slot KH-1 is complete after input row i
+    if (ho >= ho0) {
+      float v[4] = {acc[KH - 1].x, acc[KH - 1].y, acc[KH - 1].z, acc[KH - 1].w};
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = silu_tanh(v[j]);
+      }
+      const size_t opix = ((size_t)(b * p.Ho + ho) * p.Wo + wo);
+      if (p.res_mode) {
+        float rv[4];
+        unpack4(__ldg(reinterpret_cast<const uint2 *>(p.res + opix * p.res_cs + c0)), rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (p.res_mode == B2Y_RES_ADD) ? v[j] + rv[j] : v[j] * rv[j];
+      }
+      *reinterpret_cast<uint2 *>(reinterpret_cast<bf16 *>(p.out) + opix * p.out_cs + c0) = pack4(v);
+    }
+#pragma unroll
+    for (int r = KH - 1; r > 0; --r) acc[r] = acc[r - 1];
+    acc[0] = bias;
+  }
+}
+
+template <int KH, int KW>
+static int launch_dw_strip(const ConvParams &p, cudaStream_t st) {
+  // strips of R output rows: long enough to amortise the weight loads and the KH-1 halo rows, short enough to fill the GPU
+  const long long cols = (long long)p.B * p.Wo * (p.cout >> 2);
+  int R = 16;
+  while (R > 2 && cols * ceil_div(p.Ho, R) < 148LL * 1536) R >>= 1;
+  const int nstrips = ceil_div(p.Ho, R);
+  const long long total = cols * nstrips;
+  b2y_launch(dwconv_strip_kernel<KH, KW>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, R, nstrips);
+  B2Y_LAUNCH_CHECK();
+  return B2Y_OK;
+}
+
 int launch_dwconv(const ConvParams &p, cudaStream_t st) {
   B2Y_REQUIRE(p.cin == p.cout && !p.out_f32, B2Y_ERR_UNSUPPORTED, "depthwise conv needs cin == cout and bf16 output");
   auto aligned = [&](int v) {
@@ -237,6 +334,16 @@ int launch_dwconv(const ConvParams &p, cudaStream_t st) {
     if (p.res_mode) ok = ok && (p.res_cs % v == 0) && ((reinterpret_cast<uintptr_t>(p.res) & m) == 0);
     return ok;
   };
+  if (aligned(4) && p.sh == 1 && p.sw == 1 && p.Ho == p.H + 2 * p.ph - p.kh + 1) {
+    if (p.kh == 3 && p.kw == 3) return launch_dw_strip<3, 3>(p, st);
+    if (p.kh == 5 && p.kw == 5) return launch_dw_strip<5, 5>(p, st);
+    if (p.kh == 1 && p.kw == 5) return launch_dw_strip<1, 5>(p, st);
+    if (p.kh == 5 && p.kw == 1) return launch_dw_strip<5, 1>(p, st);
+    if (p.kh == 1 && p.kw == 7) return launch_dw_strip<1, 7>(p, st);
+    if (p.kh == 7 && p.kw == 1) return launch_dw_strip<7, 1>(p, st);
+    if (p.kh == 1 && p.kw == 11) return launch_dw_strip<1, 11>(p, st);
+    if (p.kh == 11 && p.kw == 1) return launch_dw_strip<11, 1>(p, st);
+  }
   const size_t wsmem = (size_t)(p.kh * p.kw + 1) * p.cout * sizeof(float);
   if (aligned(8) && wsmem <= 96 * 1024 && p.sh == p.sw) {
     const int wq = ceil_div(p.Wo, 4);
@@ -245,7 +352,7 @@ int launch_dwconv(const ConvParams &p, cudaStream_t st) {
     auto launch = [&](auto kern) -> int {
       if (wsmem > 48 * 1024)
         B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      kern<<<grid, 256, wsmem, st>>>(p, wq);
+      b2y_launch(kern, dim3(grid), dim3(256), wsmem, st, p, wq);
       B2Y_LAUNCH_CHECK();
       return B2Y_OK;
     };
@@ -258,9 +365,9 @@ int launch_dwconv(const ConvParams &p, cudaStream_t st) {
   const int V = aligned(8) ? 8 : aligned(4) ? 4 : 1;
   const long long total = (long long)p.B * p.Ho * p.Wo * (p.cout / V);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (V == 8) dwconv_kernel<8><<<grid, 256, 0, st>>>(p);
-  else if (V == 4) dwconv_kernel<4><<<grid, 256, 0, st>>>(p);
-  else dwconv_kernel<1><<<grid, 256, 0, st>>>(p);
+  if (V == 8) b2y_launch(dwconv_kernel<8>, dim3(grid), dim3(256), 0, st, p);
+  else if (V == 4) b2y_launch(dwconv_kernel<4>, dim3(grid), dim3(256), 0, st, p);
+  else b2y_launch(dwconv_kernel<1>, dim3(grid), dim3(256), 0, st, p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

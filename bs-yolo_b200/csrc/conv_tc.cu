@@ -143,16 +143,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-  uint32_t r[16];
+// split form: issue several loads, then one wait that the compiler cannot move the consumers across (the registers are
+// read-write operands of the wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
 }
 
 // SiLU with one MUFU op on a pre-halved argument h = (x + bias)/2:  x*sigmoid(x) = h + h*tanh(h)
@@ -184,7 +189,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcGeom &g, uint32_t tile)
 // starts at any 16-byte-aligned row of a swizzle-aligned tile needs NO base_offset (bits [49,52) stay 0); setting
 // base_offset = (addr >> 7) & 7 for shifted starts produces garbage (profiles/r01_notes.md).
 template <int TAPS, int KSTEPS>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -228,6 +233,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // PDL: this CTA owns its shared memory and TMEM columns now, so the next kernel of the stream may become resident and
+  // run its own prologue under our main loop (triggering before the TMEM allocation could let a later kernel starve it)
+  pdl_launch_dependents();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t ntiles = (uint32_t)g.ntiles;
   const int rows_tile = g.MB * g.TH;
@@ -241,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(wfull, (uint32_t)g.w_bytes_tx);
         for (int t = 0; t < TAPS * g.nkc; ++t) tma_load_2d(b_base + t * g.b_tile_bytes, &tmB, wfull, t * g.BK, 0);
       }
+      pdl_wait();  // weights are constants; the activations below were written by the preceding kernel(s)
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -354,28 +363,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0, os = 0;
     uint32_t aphase = 0;
     float dfl_first = 0.f;
+    pdl_wait();  // residual reads / output writes touch buffers of preceding kernels
+    const int oc_shift = g.oc == 64 ? 6 : (g.oc == 32 ? 5 : 4);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(g, tile);
       const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
       const int ho0 = tc.th_i * rows_tile + th;
-      mbar_wait(tfull0 + 8 * as, aphase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (g.tma_out) {
-        // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
-        if (elected) {
-          if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        named_bar_sync(1, kEpiThreads);
-      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * g.MB * g.BN);
       const uint32_t o_stage = o_base + (uint32_t)(os * g.o_stage_bytes);
-      for (int f = half; f < nflat; f += 2) {  // f = block j * nch + 16-column chunk c
-        const int j = f / nch, c = f - j * nch;
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)(j * g.BN + c * 16), v);  // warp-collective: every lane, valid or not
+
+      // one 16-column chunk of accumulator block j: +bias, SiLU, then fused decode | residual + store
+      auto chunk = [&](float(&v)[16], const int j, const int c) {
         const int col = c * 16, n = n0 + col;
-        if (n >= g.cout) continue;  // warp-uniform
+        if (n >= g.cout) return;  // warp-uniform
         const int ho = ho0 + j * g.TH;
         const bool valid = row_ok && ho < g.Ho && wo < g.Wo;
         const size_t pix = ((size_t)tc.b * g.Ho + ho) * g.Wo + wo;
@@ -411,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const float dist = sk / se;  // DFL expectation (block.py:73-76)
             if (c < 2) {
-              dfl_first = dist;          // left (c = 0) or top (c = 1); the partner side arrives two chunks later
+              dfl_first = dist;          // left (c = 0) or top (c = 1); the partner side is this warp's next chunk
             } else if (valid) {
               const float anc = (c == 2 ? (float)wo : (float)ho) + 0.5f;  // make_anchors (tal.py:371-383)
               const float p1 = anc - dfl_first, p2 = anc + dist;          // dist2bbox (tal.py:386-395)
@@ -427,7 +427,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int q = 0; q < 16; ++q)
               if (n + q < g.cout) yb[(size_t)q * g.A] = 1.f / (1.f + expf(-v[q]));
           }
-          continue;
+          return;
         }
         const bool full16 = (n + 16 <= g.cout);
         if (g.res_mode && valid) {
@@ -439,15 +439,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = (g.res_mode == B2Y_RES_ADD) ? v[q] + r[q] : v[q] * r[q];
           } else {
-            for (int q = 0; q < 16 && n + q < g.cout; ++q) {
-              const float r = __bfloat162float(g.res[pix * g.res_cs + n + q]);
-              v[q] = (g.res_mode == B2Y_RES_ADD) ? v[q] + r : v[q] * r;
-            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)  // static indices only: v[] must stay in registers
+              if (n + q < g.cout) {
+                const float r = __bfloat162float(g.res[pix * g.res_cs + n + q]);
+                v[q] = (g.res_mode == B2Y_RES_ADD) ? v[q] + r : v[q] * r;
+              }
           }
         }
         if (g.tma_out) {
           if (row_ok) {
-            const int bx = col / g.oc, cb = (col - bx * g.oc) * 2;  // 64-channel box, byte offset of the chunk in the row
+            const int bx = col >> oc_shift, cb = (col - (bx << oc_shift)) * 2;  // channel box, byte offset of the chunk in the row
             uint32_t off = (rr0 + (uint32_t)j * blk_out_rows) * (uint32_t)g.o_row_bytes + (uint32_t)cb;
             const uint32_t off2 = off + 16;
             off ^= ((off >> 7) & (uint32_t)g.o_sw_mask) << 4;
@@ -469,15 +471,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               op[1] = pack8(v + 8);
             }
           } else {
-            for (int q = 0; q < 16 && n + q < g.cout; ++q) {
-              if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + q] = v[q];
-              else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + q] = __float2bfloat16_rn(v[q]);
-            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              if (n + q < g.cout) {
+                if (g.out_f32) reinterpret_cast<float *>(g.out)[pix * g.out_cs + n + q] = v[q];
+                else reinterpret_cast<bf16 *>(g.out)[pix * g.out_cs + n + q] = __float2bfloat16_rn(v[q]);
+              }
           }
         }
+      };
+
+      mbar_wait(tfull0 + 8 * as, aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // this warp's chunks f = half, half+2, ... (f = block j * nch + 16-column chunk c), two per round: both TMEM loads
+      // are in flight while the staging buffer is being reclaimed; the accumulator stage is released to the MMA warp as
+      // soon as the last load has landed in registers, before the math and the stores.
+      int j = 0, c = half;
+      while (c >= nch) { c -= nch; ++j; }
+      bool reclaimed = false, released = false;
+      for (int f = half; f < nflat; f += 4) {
+        const int j0 = j, c0 = c;
+        c += 2;
+        while (c >= nch) { c -= nch; ++j; }
+        const int j1 = j, c1 = c;
+        c += 2;
+        while (c >= nch) { c -= nch; ++j; }
+        const bool two = f + 2 < nflat;  // warp-uniform
+        float v0[16], v1[16];
+        tmem_ld16_issue(taddr + (uint32_t)(j0 * g.BN + c0 * 16), v0);  // warp-collective: every lane, valid or not
+        if (two) tmem_ld16_issue(taddr + (uint32_t)(j1 * g.BN + c1 * 16), v1);
+        if (!reclaimed && g.tma_out) {
+          // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
+          if (elected) {
+            if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          named_bar_sync(1, kEpiThreads);
+        }
+        reclaimed = true;
+        tmem_ld_wait(v0);
+        if (two) tmem_ld_wait(v1);
+        if (f + 4 >= nflat) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tempty0 + 8 * as);  // accumulator stage drained: the MMA warp may overwrite it
+          released = true;
+        }
+        chunk(v0, j0, c0);
+        if (two) chunk(v1, j1, c1);
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(tempty0 + 8 * as);  // accumulator stage drained: the MMA warp may overwrite it
+      if (!reclaimed && g.tma_out) {  // a warp without chunks still takes part in the barrier protocol
+        if (elected) {
+          if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        named_bar_sync(1, kEpiThreads);
+      }
+      if (!released) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(tempty0 + 8 * as);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
       if (g.tma_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
@@ -779,7 +831,9 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   } else {
     pl->tmO = pl->tmB;  // unused
   }
-  if (want_per_sm == 1 && pl->smem < 116 * 1024) pl->smem = 116 * 1024;  // keep the SM to one CTA as configured
+  // without PDL keep the SM to one CTA as configured; with PDL the request stays minimal so that the next kernel's CTA
+  // can become resident beside this one (the persistent grid is one CTA per SM, placed breadth-first)
+  if (want_per_sm == 1 && pl->smem < 116 * 1024 && !b2y_pdl_enabled()) pl->smem = 116 * 1024;
   if (g.tmem_cols * want_per_sm > 512) {
     delete pl;
     b2y_set_error("tcgen05 conv: TMEM over-subscribed (%d columns x %d CTAs)", g.tmem_cols, want_per_sm);
@@ -796,7 +850,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
 void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
 
 int launch_conv_tc(const ConvTcPlan *pl, cudaStream_t st) {
-  pl->fn<<<pl->grid, kNumThreads, pl->smem, st>>>(pl->tmA, pl->tmB, pl->tmO, pl->g);
+  b2y_launch(pl->fn, dim3(pl->grid), dim3(kNumThreads), pl->smem, st, pl->tmA, pl->tmB, pl->tmO, pl->g);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

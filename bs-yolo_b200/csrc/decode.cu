@@ -17,6 +17,8 @@ struct DecodeParams {
 };
 
 __global__ void __launch_bounds__(128) decode_kernel(DecodeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float tile[];  // [32][no+1] raw values, then [32][4] distances
   const int no = 64 + p.nc, pitch = no + 1;
   float *dist = tile + 32 * pitch;
@@ -94,7 +96,7 @@ int decode_launch(const void *const *raw, const int32_t *hs, const int32_t *ws, 
   B2Y_REQUIRE(smem <= 200 * 1024, B2Y_ERR_UNSUPPORTED, "decode: nc=%d too large", nc);
   if (smem > 48 * 1024)
     B2Y_CUDA_CHECK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  decode_kernel<<<dim3(blk, B), 128, smem, st>>>(p);
+  b2y_launch(decode_kernel, dim3(dim3(blk, B)), dim3(128), smem, st, p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

@@ -8,6 +8,8 @@
 // passes, each stage written to its own channel slice of the concat buffer: out[:, j*c + ch], j = 0..2.
 __global__ void __launch_bounds__(256) sppf_pool_kernel(const bf16 *__restrict__ in, int in_cs, bf16 *__restrict__ out,
                                                         int out_cs, int c, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint4 tile[];  // [2][H*W] of 8 x bf16
   uint4 *cur = tile, *tmp = tile + H * W;
   const int ngrp = c / 8;
@@ -60,7 +62,7 @@ int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, in
   B2Y_REQUIRE(smem <= 200 * 1024, B2Y_ERR_UNSUPPORTED, "sppf pool: %dx%d map does not fit shared memory", H, W);
   if (smem > 48 * 1024)
     B2Y_CUDA_CHECK(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sppf_pool_kernel<<<B * (c / 8), 256, smem, st>>>(in, in_cs, out, out_cs, c, H, W);
+  b2y_launch(sppf_pool_kernel, dim3(B * (c / 8)), dim3(256), smem, st, in, in_cs, out, out_cs, c, H, W);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -70,6 +72,8 @@ int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, in
 template <int V>
 __global__ void __launch_bounds__(256) resample_kernel(const bf16 *__restrict__ in, int in_cs, bf16 *__restrict__ out,
                                                        int out_cs, int c, long long total, int Ho, int Wo, int scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = c / V;
@@ -96,9 +100,9 @@ int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int
   const int V = ok(8) ? 8 : ok(4) ? 4 : 1;
   const long long total = (long long)B * H * W * (c / V);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (V == 8) resample_kernel<8><<<grid, 256, 0, st>>>(in, in_cs, out, out_cs, c, total, H, W, scale);
-  else if (V == 4) resample_kernel<4><<<grid, 256, 0, st>>>(in, in_cs, out, out_cs, c, total, H, W, scale);
-  else resample_kernel<1><<<grid, 256, 0, st>>>(in, in_cs, out, out_cs, c, total, H, W, scale);
+  if (V == 8) b2y_launch(resample_kernel<8>, dim3(grid), dim3(256), 0, st, in, in_cs, out, out_cs, c, total, H, W, scale);
+  else if (V == 4) b2y_launch(resample_kernel<4>, dim3(grid), dim3(256), 0, st, in, in_cs, out, out_cs, c, total, H, W, scale);
+  else b2y_launch(resample_kernel<1>, dim3(grid), dim3(256), 0, st, in, in_cs, out, out_cs, c, total, H, W, scale);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -107,6 +111,8 @@ int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int
 // rowm[b,h,c] = mean_w x[b,h,w,c]; colm[b,w,c] = mean_h x[b,h,w,c]   (ELA.py:74-84).  thread = channel.
 __global__ void rowcol_mean_kernel(const bf16 *__restrict__ x, int cs, int c, int H, int W, float *__restrict__ rowm,
                                    float *__restrict__ colm) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z, ch = blockIdx.y * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const int line = blockIdx.x;  // [0,H): row means; [H,H+W): column means
@@ -125,7 +131,7 @@ __global__ void rowcol_mean_kernel(const bf16 *__restrict__ x, int cs, int c, in
 int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, float *rowm, float *colm, cudaStream_t st) {
   const int bt = c >= 128 ? 128 : 64;
   dim3 grid(H + W, ceil_div(c, bt), B);
-  rowcol_mean_kernel<<<grid, bt, 0, st>>>(x, cs, c, H, W, rowm, colm);
+  b2y_launch(rowcol_mean_kernel, dim3(grid), dim3(bt), 0, st, x, cs, c, H, W, rowm, colm);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -137,6 +143,8 @@ __global__ void __launch_bounds__(256) ela_gate_kernel(const float *__restrict__
                                                        const float *__restrict__ params, int c, int H, int W, int ks,
                                                        int groups, float eps, float *__restrict__ hgate,
                                                        float *__restrict__ wgate, float *__restrict__ chgate) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // conv outputs for this group: [cpg][L]
   __shared__ float red[64];
   const int b = blockIdx.x / groups, g = blockIdx.x % groups;
@@ -200,7 +208,7 @@ int launch_ela_gate(const float *rowm, const float *colm, const float *params, i
   const int L = H > W ? H : W;
   const size_t smem = (size_t)(c / groups) * L * sizeof(float);
   B2Y_REQUIRE(smem <= 48 * 1024, B2Y_ERR_UNSUPPORTED, "ELA gate: group tile too large");
-  ela_gate_kernel<<<B * groups, 256, smem, st>>>(rowm, colm, params, c, H, W, ks, groups, eps, hgate, wgate, chgate);
+  b2y_launch(ela_gate_kernel, dim3(B * groups), dim3(256), smem, st, rowm, colm, params, c, H, W, ks, groups, eps, hgate, wgate, chgate);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -211,6 +219,8 @@ __global__ void __launch_bounds__(256) ela_apply_kernel(const bf16 *__restrict__
                                                         const float *__restrict__ hgate, const float *__restrict__ wgate,
                                                         const float *__restrict__ chgate, float ch_c, float sp_c,
                                                         float res_c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = c / 8;
@@ -233,7 +243,7 @@ int launch_ela_apply(const bf16 *x, int cs, bf16 *out, int out_cs, int c, int B,
                      const float *wgate, const float *chgate, float ch_c, float sp_c, float res_c, cudaStream_t st) {
   B2Y_REQUIRE(c % 8 == 0 && cs % 8 == 0 && out_cs % 8 == 0, B2Y_ERR_UNSUPPORTED, "ELA apply: channels must be x8");
   const long long total = (long long)B * H * W * (c / 8);
-  ela_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, cs, out, out_cs, c, total, H, W, hgate, wgate,
+  b2y_launch(ela_apply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, cs, out, out_cs, c, total, H, W, hgate, wgate,
                                                                     chgate, ch_c, sp_c, res_c);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
@@ -247,6 +257,8 @@ struct Ptr4 {
 
 // gap[b, j, ch] = mean over pixels of branch j (MSCA.py:71-74).  block = (image, branch), thread = channel.
 __global__ void gap4_kernel(Ptr4 br, int c, int HW, float *__restrict__ gap) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, j = blockIdx.y;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const bf16 *x = br.p[j] + (size_t)b * HW * br.cs[j] + ch;
@@ -262,7 +274,7 @@ int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, f
     q.p[j] = br[j];
     q.cs[j] = br_cs[j];
   }
-  gap4_kernel<<<dim3(B, 4), 256, 0, st>>>(q, c, HW, gap);
+  b2y_launch(gap4_kernel, dim3(dim3(B, 4)), dim3(256), 0, st, q, c, HW, gap);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -271,6 +283,8 @@ int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, f
 // block = (image, 32 output channels): one warp per output channel does the 4 dot products.
 __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict__ gap, const float *__restrict__ se_w,
                                                         const float *__restrict__ se_b, int c, float *__restrict__ gate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int ch = blockIdx.y * 32 + warp; ch < min(c, (int)blockIdx.y * 32 + 32); ch += 8) {
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict_
 
 int launch_msca_gate(const float *gap, const float *se_w, const float *se_b, int c, int B, float *gate,
                      cudaStream_t st) {
-  msca_gate_kernel<<<dim3(B, ceil_div(c, 32)), 256, 0, st>>>(gap, se_w, se_b, c, gate);
+  b2y_launch(msca_gate_kernel, dim3(dim3(B, ceil_div(c, 32))), dim3(256), 0, st, gap, se_w, se_b, c, gate);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -308,6 +322,8 @@ int launch_msca_gate(const float *gap, const float *se_w, const float *se_b, int
 // out[b,p,ch] = sum_j gate[b,j,ch] * br_j[b,p,ch]   (MSCA.py:84)
 __global__ void __launch_bounds__(256) wsum4_kernel(Ptr4 br, const float *__restrict__ gate, bf16 *__restrict__ out,
                                                     int out_cs, int c, long long total, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = c / 8;
@@ -336,7 +352,7 @@ int launch_wsum4(const bf16 *const *br, const int *br_cs, const float *gate, bf1
     B2Y_REQUIRE(br_cs[j] % 8 == 0, B2Y_ERR_UNSUPPORTED, "wsum4: branch stride must be x8");
   }
   const long long total = (long long)B * HW * (c / 8);
-  wsum4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, gate, out, out_cs, c, total, HW);
+  b2y_launch(wsum4_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, q, gate, out, out_cs, c, total, HW);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

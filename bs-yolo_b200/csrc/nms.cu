@@ -44,6 +44,8 @@ __device__ __forceinline__ bool class_ok(const ClassMask &cm, int c) {
 }
 
 __global__ void __launch_bounds__(256) nms_score_kernel(NmsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (a >= p.A) return;
   const float *cls = p.pred + ((size_t)b * (4 + p.nc) + 4) * p.A + a;
@@ -96,6 +98,8 @@ __device__ void bitonic_sort(unsigned long long *k, int P) {
 }
 
 __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ unsigned long long skeys[];  // SMEM_SORT keys
   __shared__ int scan[NT / 32];
   __shared__ int s_total;
@@ -138,6 +142,9 @@ __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
   const int n = s_total;
   if (n == 0) {
     if (tid == 0) p.counts[b] = 0;
+    for (int i = tid; i < p.max_det * 6; i += NT) p.dets[(size_t)b * p.max_det * 6 + i] = 0.f;  // padded rows are defined
+    if (p.kept_anchor)
+      for (int i = tid; i < p.max_det; i += NT) p.kept_anchor[(size_t)b * p.max_det + i] = 0;
     return;
   }
   int P = 1;
@@ -230,7 +237,11 @@ __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
     }
     __syncthreads();
   }
-  if (tid == 0) p.counts[b] = s_nk;
+  const int nk_final = s_nk;
+  if (tid == 0) p.counts[b] = nk_final;
+  for (int i = nk_final * 6 + tid; i < p.max_det * 6; i += NT) p.dets[(size_t)b * p.max_det * 6 + i] = 0.f;
+  if (p.kept_anchor)
+    for (int i = nk_final + tid; i < p.max_det; i += NT) p.kept_anchor[(size_t)b * p.max_det + i] = 0;
 }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -241,6 +252,8 @@ inline int pow2_ge(long long v) {
 }
 
 __global__ void scale_boxes_kernel(float *dets, const int *counts, const float *geom, int B, int max_det) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * max_det) return;
   const int b = idx / max_det, k = idx % max_det;
@@ -307,7 +320,7 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
       if (classes[i] >= 0 && classes[i] < nc) p.cm.bits[classes[i] >> 5] |= (1u << (classes[i] & 31));
   }
   cudaStream_t st = (cudaStream_t)stream;
-  nms_score_kernel<<<dim3(ceil_div(A, 256), B), 256, 0, st>>>(p);
+  b2y_launch(nms_score_kernel, dim3(dim3(ceil_div(A, 256), B)), dim3(256), 0, st, p);
   B2Y_LAUNCH_CHECK();
   const size_t smem = SMEM_SORT * sizeof(unsigned long long);
   static bool attr_set = false;
@@ -315,7 +328,7 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
     B2Y_CUDA_CHECK(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  nms_select_kernel<<<B, NT, smem, st>>>(p);
+  b2y_launch(nms_select_kernel, dim3(B), dim3(NT), smem, st, p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -323,7 +336,7 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
 extern "C" int b2y_scale_boxes(void *dets, const void *counts, const void *geom, int32_t B, int32_t max_det,
                                void *stream) {
   B2Y_REQUIRE(dets && counts && geom && B > 0 && max_det > 0, B2Y_ERR_INVALID, "scale_boxes: bad arguments");
-  scale_boxes_kernel<<<ceil_div(B * max_det, 256), 256, 0, (cudaStream_t)stream>>>(
+  b2y_launch(scale_boxes_kernel, dim3(ceil_div(B * max_det, 256)), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<float *>(dets), reinterpret_cast<const int *>(counts), reinterpret_cast<const float *>(geom), B,
       max_det);
   B2Y_LAUNCH_CHECK();

@@ -18,6 +18,15 @@ void b2y_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+bool b2y_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("B2Y_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 extern "C" const char *b2y_last_error(void) { return g_err; }
 extern "C" int b2y_abi_version(void) { return B2Y_ABI_VERSION; }
 

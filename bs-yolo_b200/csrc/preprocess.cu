@@ -24,6 +24,8 @@ __device__ __forceinline__ void axis_coeff(int d, double scale, int src, int &s,
 }
 
 __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)p.B * p.H * p.W;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -66,6 +68,58 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
     o[0] = (uint8_t)bgr[0]; o[1] = (uint8_t)bgr[1]; o[2] = (uint8_t)bgr[2];
   }
 }
+// Network-input fast path (no resize): thread = one space-to-depth super-pixel = 2 x 2 source pixels.
+// Reads 2 x 6 source bytes (three 16-bit loads per row: x is even, so the BGR pair is 2-byte aligned whenever the row
+// pitch and the placement are even), looks v/255 up in a 256-entry bf16 table (built per block with the same
+// correctly-rounded divide as the generic path, so both write identical bits) and stores the 16 channels
+// ((y&1)*2 + (x&1))*4 + {R,G,B,0} as two 16-byte vectors: consecutive lanes write consecutive 32-byte super-pixels.
+__global__ void __launch_bounds__(256) preprocess_s2d_kernel(PreParams p) {
+  pdl_launch_dependents();
+  __shared__ uint16_t lut[256];
+  {
+    const __nv_bfloat16 v = __float2bfloat16_rn(__fdiv_rn((float)threadIdx.x, 255.f));
+    lut[threadIdx.x] = *reinterpret_cast<const uint16_t *>(&v);
+  }
+  __syncthreads();
+  pdl_wait();
+  const int W2 = p.W >> 1, H2 = p.H >> 1;
+  const long long total = (long long)p.B * H2 * W2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int xs = (int)(idx % W2);
+  const int ys = (int)((idx / W2) % H2);
+  const int b = (int)(idx / ((long long)W2 * H2));
+  const uint8_t *img = p.src + (size_t)b * p.h * p.w * 3;
+  uint32_t o[8];
+#pragma unroll
+  for (int row = 0; row < 2; ++row) {
+    const int uy = 2 * ys + row - p.top, ux = 2 * xs - p.left;
+    uint32_t px[2][3] = {{114, 114, 114}, {114, 114, 114}};  // B, G, R of the two pixels
+    if (uy >= 0 && uy < p.uh) {
+      const uint8_t *s = img + ((size_t)uy * p.w + ux) * 3;
+      if (ux >= 0 && ux + 1 < p.uw && ((reinterpret_cast<uintptr_t>(s) & 1) == 0)) {
+        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(s);
+        const uint32_t a = __ldg(s16), c = __ldg(s16 + 1), d = __ldg(s16 + 2);  // B0G0 | R0B1 | G1R1
+        px[0][0] = a & 255u; px[0][1] = a >> 8; px[0][2] = c & 255u;
+        px[1][0] = c >> 8; px[1][1] = d & 255u; px[1][2] = d >> 8;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          if (ux + q >= 0 && ux + q < p.uw) {
+            px[q][0] = s[q * 3]; px[q][1] = s[q * 3 + 1]; px[q][2] = s[q * 3 + 2];
+          }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      o[row * 4 + q * 2] = (uint32_t)lut[px[q][2]] | ((uint32_t)lut[px[q][1]] << 16);  // R, G
+      o[row * 4 + q * 2 + 1] = (uint32_t)lut[px[q][0]];                                 // B, 0
+    }
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(p.dst) + (size_t)idx * 2;
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
 }  // namespace
 
 extern "C" int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, void *dst, int32_t H, int32_t W,
@@ -82,8 +136,14 @@ extern "C" int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, 
   p.resize = !(uh == h && uw == w);
   p.scale_x = 1.0 / ((double)uw / (double)w);
   p.scale_y = 1.0 / ((double)uh / (double)h);
+  if (dst_format == 0 && !p.resize && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const long long nsp = (long long)B * (H >> 1) * (W >> 1);
+    b2y_launch(preprocess_s2d_kernel, dim3((unsigned)((nsp + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, p);
+    B2Y_LAUNCH_CHECK();
+    return B2Y_OK;
+  }
   const long long total = (long long)B * H * W;
-  preprocess_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  b2y_launch(preprocess_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }

@@ -46,9 +46,10 @@ def nms_raw(pred: torch.Tensor, conf=0.25, iou=0.7, max_det=300, classes=None, a
     L = A.lib()
     nbytes = L.b2y_nms_workspace_bytes(B, nc, An, int(bool(multi_label)), max_nms)
     ws = _workspace(pred.device, nbytes)
-    dets = torch.zeros(B, max_det, 6, dtype=torch.float32, device=pred.device)
-    counts = torch.zeros(B, dtype=torch.int32, device=pred.device)
-    anchors = torch.zeros(B, max_det, dtype=torch.int32, device=pred.device) if return_anchors else None
+    # b2y_nms writes every element (rows past counts[b] are zero-filled by the kernel): no torch fill launches
+    dets = torch.empty(B, max_det, 6, dtype=torch.float32, device=pred.device)
+    counts = torch.empty(B, dtype=torch.int32, device=pred.device)
+    anchors = torch.empty(B, max_det, dtype=torch.int32, device=pred.device) if return_anchors else None
     if classes is not None:
         cl = (C.c_int32 * len(classes))(*[int(c) for c in classes])
         ncl = len(classes)
@@ -110,7 +111,7 @@ def _letterbox_call(images, imgsz, auto, stride, device, fmt):
     elif fmt == 2:
         dst = torch.empty(B, H, W, 3, dtype=torch.uint8, device=device)
     else:
-        dst = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=device)
+        dst = torch.empty(B, H // 2, W // 2, 16, dtype=torch.bfloat16, device=device)
     A.check(A.lib().b2y_preprocess(src.data_ptr(), B, h, w, dst.data_ptr(), H, W, top, left, uh, uw, fmt, _stream(device)))
     return dst
 

@@ -8,7 +8,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("B2Y_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """$B2Y_REFERENCE_ROOT, else /root/reference (build container), else baseline/_ref: the unmodified reference
+    pip-installed from /root/reference by __graft_entry__.build() (git-ignored, travels to the GPU box)."""
+    cands = [os.environ.get("B2Y_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "ultralytics")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -118,6 +118,58 @@ def test_conv_kernels_vs_emulator(case, impl):
     assert rel < 4e-3, rel  # same bf16 inputs/weights, fp32 accumulation; only bf16 output rounding + sum order
 
 
+DW_CASES = {  # name -> (C, k, s, H, W, act, res, in_total, in_off)
+    "dw3_64_80": (64, (3, 3), 1, 80, 80, True, None, None, 0),
+    "dw3_80_40_res": (80, (3, 3), 1, 40, 40, True, "add", None, 0),
+    "dw3_64_slice_pe": (64, (3, 3), 1, 20, 20, False, "add", 256, 64),
+    "dw3_128_s2": (128, (3, 3), 2, 40, 40, False, None, None, 0),
+    "dw5_16_odd": (16, (5, 5), 1, 37, 53, True, None, None, 0),
+    "dw7_8": (8, (7, 7), 1, 40, 40, True, None, None, 0),
+    "dw1x11_256": (256, (1, 11), 1, 20, 20, False, None, None, 0),
+    "dw21x1_256": (256, (21, 1), 1, 20, 20, False, None, None, 0),
+    "dw3_12_c4": (12, (3, 3), 1, 33, 21, True, "mul", None, 0),
+    "dw3_6_scalar": (6, (3, 3), 1, 16, 16, True, None, None, 0),
+}
+
+
+@pytest.mark.parametrize("case", list(DW_CASES))
+def test_depthwise_conv_vs_torch(case):
+    """DWConv (conv.py:224-229) / MSCA strips (MSCA.py:24-39) / Attention.pe (block.py:4286) through OP_DWCONV."""
+    import torch.nn.functional as F
+    from bs_yolo_b200.engine import Engine
+    from bs_yolo_b200.plan import Plan, View
+    C, k, s, H, W, act, res, in_total, in_off = DW_CASES[case]
+    rng = np.random.default_rng(sum(map(ord, case)))
+    p = (k[0] // 2, k[1] // 2)
+    node = dict(type="Conv", name=case, c1=C, c2=C, k=k, s=(s, s), p=p, g=C, act="silu" if act else "none",
+                weight=torch.from_numpy((rng.standard_normal((C, 1, *k)) / np.sqrt(k[0] * k[1])).astype(np.float32)),
+                bias=torch.from_numpy(rng.standard_normal(C).astype(np.float32) * 0.1))
+    plan = Plan.empty(64, 64)
+    xb = plan.new_buf(in_total or C, H, W, name="x")
+    x = View(xb, in_off, C, H, W)
+    Ho, Wo = (H + 2 * p[0] - k[0]) // s + 1, (W + 2 * p[1] - k[1]) // s + 1
+    rv, mode = None, A.RES_NONE
+    if res:
+        rv, mode = View(plan.new_buf(C, Ho, Wo, name="res"), 0, C, Ho, Wo), (A.RES_ADD if res == "add" else A.RES_MUL)
+    out = plan.conv(node, x, res=rv, res_mode=mode)
+    B = 3
+    eng = Engine(None, B, 64, 64, use_graph=False, plan=plan)
+    gen = torch.Generator().manual_seed(1)
+    for i, bspec in enumerate(plan.bufs):
+        eng.buffer(i).copy_(torch.randn(B, bspec.H, bspec.W, bspec.C, generator=gen).to(torch.bfloat16))
+    eng.forward()
+    torch.cuda.synchronize()
+    xin = eng.view_tensor(x).float().cpu().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, node["weight"], node["bias"], stride=s, padding=p, groups=C)
+    if act:
+        ref = F.silu(ref)
+    if res:
+        r = eng.view_tensor(rv).float().cpu().permute(0, 3, 1, 2)
+        ref = ref + r if res == "add" else ref * r
+    got = eng.view_tensor(out).float().cpu().permute(0, 3, 1, 2)
+    assert float((got - ref).norm() / ref.norm()) < 4e-3
+
+
 # ----------------------------------------------------------------------------- whole network
 def _run_engine(g, x, **kw):
     from bs_yolo_b200.engine import Engine
@@ -233,14 +285,21 @@ def test_stem_space_to_depth_conv(impl, c2, hw):
     assert float((got - ref).norm() / ref.norm()) < 4e-3
 
 
-def test_preprocess_writes_space_to_depth_input():
-    from bs_yolo_b200.engine import Engine, space_to_depth
+@pytest.mark.parametrize("src,dst,auto", [((96, 128), (96, 128), False), ((270, 480), (160, 160), False),
+                                          ((270, 480), (160, 160), True), ((100, 75), (128, 128), False),
+                                          ((90, 126), (96, 128), False)])
+def test_preprocess_writes_space_to_depth_input(src, dst, auto):
+    """Network-input format of b2y_preprocess: identity fast path, padded placements (even and odd offsets) and the
+    resizing path all write the bf16 space-to-depth layout of the oracle's preprocess output, bit for bit."""
+    from bs_yolo_b200.engine import Engine, letterbox_geometry, space_to_depth
     g = _graph("yolo11n")
-    imgs = np.random.default_rng(4).integers(0, 256, (2, 96, 128, 3), dtype=np.uint8)
-    eng = Engine(g, 2, 96, 128, use_graph=False)
-    eng.preprocess(torch.from_numpy(imgs).cuda())
+    imgs = np.random.default_rng(4).integers(0, 256, (2, *src, 3), dtype=np.uint8)
+    H, W = letterbox_geometry(src, dst, auto)[:2]
+    eng = Engine(g, 2, H, W, use_graph=False)
+    eng.preprocess(torch.from_numpy(imgs).cuda(), auto=auto)
     torch.cuda.synchronize()
-    ref = space_to_depth(torch.from_numpy(oracle_post.preprocess(list(imgs), (96, 128)))).bfloat16()
+    ref = space_to_depth(ops.preprocess(list(imgs), dst, auto=auto).cpu()).bfloat16()  # fp32 path: bit-exact vs the oracle (above)
+    assert ref.shape[1:3] == (H // 2, W // 2)
     assert torch.equal(eng.input_nhwc.cpu(), ref)
 
 

@@ -47,3 +47,24 @@ def test_scale_boxes_matches_reference():
     for s1, s0 in [((640, 640), (640, 640)), ((384, 640), (1080, 1920)), ((160, 128), (481, 321))]:
         ref = ops.scale_boxes(s1, torch.from_numpy(b.copy()), s0).numpy()
         assert np.array_equal(oracle_post.scale_boxes(s1, b, s0), ref)
+
+
+def test_dropin_predictor_plugs_into_predict_and_refuses_cpu(tmp_path):
+    """The plug point (engine/model.py:549-551) accepts the class; without a CUDA device it raises instead of falling back."""
+    ref_import.import_reference()
+    from ultralytics import YOLO
+    from ultralytics.models.yolo.detect.predict import DetectionPredictor
+
+    from bs_yolo_b200 import _cabi as A
+    from bs_yolo_b200.predictor import B200DetectionPredictor
+
+    assert issubclass(B200DetectionPredictor, DetectionPredictor)
+    spec = arch.build_spec("yolo11n")
+    m = ref_import.reference_model("yolo11n", arch.synth_state_dict(spec, 0))
+    m.names = {k: f"class{k}" for k in range(spec["nc"])}
+    m.args = {"task": "detect", "imgsz": 64}
+    path = str(tmp_path / "y.pt")
+    torch.save({"model": m, "ema": None, "train_args": {"task": "detect", "imgsz": 64}}, path)
+    with pytest.raises(A.B2YError, match="no CPU fallback"):
+        YOLO(path).predict([np.zeros((64, 64, 3), np.uint8)], predictor=B200DetectionPredictor, device="cpu", imgsz=64,
+                           verbose=False)
