@@ -110,21 +110,71 @@ def cpu_port_throughput(model, imgsz, n_images, batch, threads, steps=1, warmup=
     return steps * n_images / dt, dt / steps
 
 
+def cpu_reference_throughput(model, imgsz, n_images, batch, threads, steps=1, warmup=1):
+    """Times the UNMODIFIED reference (baseline/_ref, pip-installed from /root/reference by __graft_entry__.build()):
+    YOLO(<synthetic checkpoint>).predict(list of ndarrays, device="cpu") -- LetterBox + preprocess + fp32 torch forward
+    + NMS + Results, through its own public API -- on `threads` host threads.  Returns None if it is not importable."""
+    from oracle import ref_import
+    if not ref_import.available():
+        return None
+    import tempfile
+    from bs_yolo_b200 import arch
+    ref_import.import_reference()
+    from ultralytics import YOLO
+    spec = arch.build_spec(model)
+    m = ref_import.reference_model(model, arch.synth_state_dict(spec, 0))
+    m.names = {k: f"class{k}" for k in range(spec["nc"])}
+    m.args = {"task": "detect", "imgsz": imgsz}
+    path = os.path.join(tempfile.mkdtemp(prefix="b2y_ref_"), f"{model}.pt")
+    torch.save({"model": m, "ema": None, "train_args": {"task": "detect", "imgsz": imgsz}}, path)
+    yolo = YOLO(path)
+    frames = synth_frames(n_images, imgsz, 1234)
+    kw = dict(device="cpu", imgsz=imgsz, conf=0.25, iou=0.7, max_det=300, verbose=False)
+    yolo.predict([frames[0]], **kw)   # first call: settings / predictor setup (SURVEY Appendix A: ~9 s in a fresh env)
+    torch.set_num_threads(threads)    # the reference caps itself at min(8, ncpu-1) threads (torch_utils.py:229); use them all
+
+    def one_pass():
+        for i in range(0, n_images, batch):
+            yolo.predict(list(frames[i:i + batch]), **kw)
+
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = time.perf_counter() - t0
+    return steps * n_images / dt, dt / steps
+
+
+def cpu_arm(model, imgsz, n_img, cb, cores, steps, warmup):
+    """(value, step seconds, kind): the reference itself when importable, else the oracle port."""
+    r = None
+    try:
+        r = cpu_reference_throughput(model, imgsz, n_img, cb, cores, steps=steps, warmup=warmup)
+    except Exception as e:  # noqa: BLE001 -- a broken reference install must not take the bench down
+        sys.stderr.write(f"[bench] reference package unusable ({type(e).__name__}: {e}); timing the oracle port instead\n")
+    if r is not None:
+        return r[0], r[1], "reference"
+    v, s_ = cpu_port_throughput(model, imgsz, n_img, cb, cores, steps=steps, warmup=warmup)
+    return v, s_, "port"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     model, batch, imgsz = MODEL_CFG[args.workload]
     cores = os.cpu_count() or 1
-    n_img, cb = 16, 8
-    val, step_s = cpu_port_throughput(model, imgsz, n_img, cb, cores, steps=args.steps, warmup=min(args.warmup, 1))
+    n_img, cb = 32, 16
+    val, step_s, kind = cpu_arm(model, imgsz, n_img, cb, cores, args.steps, min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{model} detect forward + DFL decode + NMS, batch {batch} @ {imgsz}x{imgsz}",
-                   "note": "CPU port (oracle) of the reference torch path; each step = bounded sample of the workload"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                   "note": ("the unmodified reference (baseline/_ref): YOLO(ckpt).predict(list, device='cpu')" if kind == "reference"
+                            else "CPU port (oracle) of the reference torch path") + "; each step = bounded sample of the workload"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{n_img} synthetic {imgsz}x{imgsz} frames per step in batches of {cb}, torch fp32, {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -182,15 +232,12 @@ def main():
     n_rot = 4  # rotate over 4 distinct input batches (4 x 78.6 MB > 126 MB L2); activations add ~GBs of traffic per step
     host = [torch.from_numpy(synth_frames(batch, imgsz, 100 + rank * 16 + j)).pin_memory() for j in range(n_rot)]
     devf = [h.to(dev) for h in host]
-    gather_buf = None
-    if world > 1:
-        gather_buf = (torch.empty(world * batch, pipe.max_det, 6, device=dev), torch.empty(world * batch, dtype=torch.int32, device=dev))
+    from bs_yolo_b200 import shard
 
     def step_resident(j):
         dets, counts = pipe(devf[j % n_rot])
-        if world > 1:  # only the final detections cross GPUs
-            dist.all_gather_into_tensor(gather_buf[0], dets)
-            dist.all_gather_into_tensor(gather_buf[1], counts)
+        if world > 1:  # only the final detections cross GPUs (one all-gather of padded rows + counts)
+            dets, counts = shard.gather_detections(dets, counts)
         return dets, counts
 
     def barrier():
@@ -225,9 +272,7 @@ def main():
 
     # ---- end to end through the public API with host buffers
     def step_e2e(j):
-        out = pipe.predict_host(host[j % n_rot])
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf[1], out[1].to(dev, non_blocking=True))
+        out = pipe.predict_host(host[j % n_rot], gather=world > 1)
         return out
 
     for j in range(3):
@@ -235,6 +280,23 @@ def main():
     ms_e2e, wall_e2e = timed(step_e2e, K)
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * batch * K / (max(ms_e2e, wall_e2e) * 1e-3)
+
+    # ---- stage split of one resident step (rank 0): preprocess | CUDA-graphed network (+ fused decode) | NMS
+    stages = None
+    if rank == 0:
+        from bs_yolo_b200.ops import nms_raw
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+        for j in range(K):
+            evs[j][0].record()
+            eng.preprocess(devf[j % n_rot], auto=pipe.auto)
+            evs[j][1].record()
+            eng.forward()
+            evs[j][2].record()
+            nms_raw(eng.y, pipe.conf, pipe.iou, pipe.max_det)
+            evs[j][3].record()
+        torch.cuda.synchronize()
+        stages = {n: float(np.median([evs[j][i].elapsed_time(evs[j][i + 1]) for j in range(K)]))
+                  for i, n in enumerate(("preprocess_ms", "network_graph_ms", "nms_ms"))}
 
     # ---- per-op timing -> roofline of the dominant kernel (rank 0)
     roof, layers = None, None
@@ -270,9 +332,11 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, s = cpu_port_throughput(model, imgsz, 16, 8, cores, steps=1, warmup=0)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"16 synthetic {imgsz}x{imgsz} frames (2 batches of 8), oracle torch-fp32 port, {cores} threads, {s:.1f} s"}
+        v, s_, kind = cpu_arm(model, imgsz, 64, 16, cores, 1, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"64 synthetic {imgsz}x{imgsz} frames (4 batches of 16) after one warm-up pass, "
+                         + ("reference YOLO.predict(device='cpu')" if kind == "reference" else "oracle torch-fp32 port")
+                         + f", {cores} threads, {s_:.1f} s"}
 
     if rank == 0:
         line = {
@@ -287,7 +351,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * imgsz * imgsz * 3,
                     "d2h_bytes_per_step": batch * (pipe.max_det * 6 * 4 + 4), "ms_per_step": max(ms_e2e, wall_e2e) / K},
             "gpu_launches": pipe.launches_per_batch * K, "launches_per_step": pipe.launches_per_batch,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "wall_ms_per_step": wall / K,
+            "clocks": clocks, "stages": stages, "roofline": roof, "cpu_baseline": cpu, "wall_ms_per_step": wall / K,
         }
         print(json.dumps(line))
     if world > 1:

@@ -339,6 +339,21 @@ extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
   }
   pl->graph = g;
   B2Y_CUDA_CHECK(cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
+  {
+    const char *vb = getenv("B2Y_VERBOSE");
+    if (vb && vb[0] == '1') {  // how many kernel->kernel edges were captured as programmatic (PDL) dependencies
+      size_t ne = 0;
+      if (cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne > 0) {
+        std::vector<cudaGraphNode_t> from(ne), to(ne);
+        std::vector<cudaGraphEdgeData> ed(ne);
+        size_t prog = 0;
+        if (cudaGraphGetEdges_v2(g, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
+          for (size_t i = 0; i < ne; ++i) prog += (ed[i].type == cudaGraphDependencyTypeProgrammatic);
+        fprintf(stderr, "[b2y graph] %zu edges, %zu programmatic\n", ne, prog);
+      }
+      (void)cudaGetLastError();
+    }
+  }
   return B2Y_OK;
 }
 

@@ -40,14 +40,19 @@ class DetectPipeline:
             scale_boxes_batched(dets, counts, (self.H, self.W), [self.src_shape] * self.B)
         return dets, counts
 
-    def predict_host(self, frames: torch.Tensor, rescale: bool = False):
-        """frames: pinned host uint8 (B,h,w,3). Returns host (dets, counts); blocks until they are valid."""
+    def predict_host(self, frames: torch.Tensor, rescale: bool = False, gather: bool = False):
+        """frames: pinned host uint8 (B,h,w,3). Returns host (dets, counts); blocks until they are valid.
+        gather=True (multi-GPU): every rank receives the detections of all ranks' shards (shard.gather_detections)."""
         if self._staging is None:
             self._staging = torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
-            self._out = (torch.empty(self.B, self.max_det, 6, dtype=torch.float32).pin_memory(),
-                         torch.empty(self.B, dtype=torch.int32).pin_memory())
         self._staging.copy_(frames, non_blocking=True)
         dets, counts = self(self._staging, rescale)
+        if gather:
+            from .shard import gather_detections
+            dets, counts = gather_detections(dets, counts)
+        if getattr(self, "_out", None) is None or self._out[0].shape != dets.shape:
+            self._out = (torch.empty(dets.shape, dtype=torch.float32).pin_memory(),
+                         torch.empty(counts.shape, dtype=torch.int32).pin_memory())
         self._out[0].copy_(dets, non_blocking=True)
         self._out[1].copy_(counts, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -111,7 +111,7 @@ class Plan:
     """Flat op list + buffers + packed weights for one (H, W) input size (batch is bound later)."""
 
     def __init__(self, ir: Node, H: int, W: int, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
-                 fuse_decode: bool = True):
+                 fuse_decode: bool = True, dw_dense: bool = True):
         if H % 32 or W % 32:
             raise ValueError(f"input {H}x{W} must be a multiple of the max stride 32 (utils/checks.py:120-171)")
         self.ir, self.H, self.W = ir, H, W
@@ -119,6 +119,7 @@ class Plan:
         self.keep_fp32 = keep_fp32  # tests only: keep unrounded packed conv weights next to the bf16 blob
         # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
         self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
+        self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
         self.bufs: list[BufSpec] = []
         self.ops: list[OpSpec] = []
         self.blob = WeightBlob()
@@ -135,9 +136,9 @@ class Plan:
 
     @classmethod
     def empty(cls, H: int, W: int, nc: int = 1, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
-              fuse_decode: bool = True) -> "Plan":
+              fuse_decode: bool = True, dw_dense: bool = True) -> "Plan":
         """A plan with no ops (unit tests append single ops through the same lowering helpers)."""
-        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode)
+        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode, dw_dense)
 
     # ------------------------------------------------------------------ buffers / views
     def new_buf(self, C, H, W, dtype=A.BF16, name="", exact=False) -> int:
@@ -192,6 +193,19 @@ class Plan:
                 op.ip, op.fp = (0, mode, a_off, self.A, self.nc), (float(stride),)
                 rows = 4 if mode == 1 else c2
                 op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + c2 * c1 * 2
+        elif (self.dw_dense and g == c1 == c2 and (kh, kw, sh, sw) == (3, 3, 1, 1) and c1 % 16 == 0 and c1 <= 128
+              and x.c == c1 and self.conv_impl != A.IMPL_SIMT):
+            # Depthwise 3x3 on the tensor cores: the same implicit-GEMM kernel with a block-diagonal weight matrix
+            # (W[co][tap][ci] = w[co][tap] iff ci == co).  It wastes C x the MACs of a pipe that idles anyway on these
+            # memory-bound layers and inherits the TMA halo loads / TMA stores (measured: 2x the CUDA-core kernel).
+            dense = torch.zeros(c2, c1, kh, kw)
+            dense[torch.arange(c2), torch.arange(c1)] = w[:, 0]
+            node = dict(n, g=1, weight=dense, bias=b)
+            out = self.conv(node, x, dest, res, res_mode, out_dtype)
+            op = self.ops[-1]
+            op.flops = 2 * c2 * kh * kw * Ho * Wo
+            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + c2 * kh * kw * 2
+            return out
         else:
             assert g == c1 == c2, f"{n['name']}: only depthwise grouped convs are on the hot path"
             if dest is None:
