@@ -50,7 +50,8 @@ struct TcGeom {
   int sa, sb, resident;                 // A stages, B stages (streamed), weights resident flag
   int plane_bytes, a_stage_bytes, a_tx_bytes, b_tile_bytes, b_tx_bytes, w_bytes_tx;
   int row_bytes, blk_rows_bytes;        // bytes per halo row; byte offset between consecutive blocks' A operands
-  int tap_off16[9];                     // tap -> operand start offset inside the A stage, in 16-byte units
+  int tap_off16[9];                     // tap sequence position -> operand start offset inside its A stage, 16-byte units
+  int tap_seq[9];                       // tap sequence position -> tap index r*kw+s (stride 2: grouped by parity plane)
   int tmem_cols;
   unsigned desc_hi;                     // descriptor bits [32,64): SBO, version, layout type
   unsigned idesc;
@@ -60,6 +61,7 @@ struct TcGeom {
   const bf16 *res; int res_cs, res_mode;
   const float *bias;
   int act, vec_ok;
+  int fast_epi;                         // bf16 TMA-store output, whole 16-column chunks, vectorisable residual: lean epilogue
   unsigned dv_nt_mul, dv_nt_shr, dv_tw_mul, dv_tw_shr, dv_th_mul, dv_th_shr;  // tile decode by multiply-shift
   // bf16 outputs leave through shared memory + TMA store
   int tma_out, oc, n_oboxes, obox_bytes, o_row_bytes, o_sw_mask, o_stages, o_stage_bytes;
@@ -152,6 +154,16 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) 
         "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&a)[16], float (&b)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]), "=f"(a[8]),
+        "=f"(a[9]), "=f"(a[10]), "=f"(a[11]), "=f"(a[12]), "=f"(a[13]), "=f"(a[14]), "=f"(a[15]), "=f"(b[0]), "=f"(b[1]),
+        "=f"(b[2]), "=f"(b[3]), "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]), "=f"(b[8]), "=f"(b[9]), "=f"(b[10]),
+        "=f"(b[11]), "=f"(b[12]), "=f"(b[13]), "=f"(b[14]), "=f"(b[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
@@ -188,7 +200,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcGeom &g, uint32_t tile)
 // swizzle XOR is applied to the absolute shared-memory address bits (exactly like the TMA write side), so a view that
 // starts at any 16-byte-aligned row of a swizzle-aligned tile needs NO base_offset (bits [49,52) stay 0); setting
 // base_offset = (addr >> 7) & 7 for shifted starts produces garbage (profiles/r01_notes.md).
-template <int TAPS, int KSTEPS>
+// Stride-2 3x3 convs (S2): the four parity planes of a tile are four separate pipeline stages (taps grouped by plane:
+// {centre}, {left,right}, {up,down}, {corners}), so the TMA producer runs several planes ahead of the MMAs instead of
+// the whole 4-plane tile being one (single-buffered) stage.
+template <int TAPS, int KSTEPS, bool S2>
 __global__ void __launch_bounds__(kNumThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGeom g) {
@@ -257,23 +272,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h0 = tc.th_i * rows_tile - g.oy, w0 = tc.tw_i * g.TW - g.ox, n0 = tc.nt * g.BN;
         for (int kc = 0; kc < g.nkc; ++kc) {
           const int c0 = kc * g.BK;
-          mbar_wait(emptyA + 8 * sa, pha ^ 1);
-          const uint32_t dst = a_base + sa * g.a_stage_bytes;
-          mbar_expect_tx(fullA + 8 * sa, (uint32_t)g.a_tx_bytes);
-          if (!g.stride2) {
-            tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, tc.b);
-          } else {
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl)
-              tma_load_5d(dst + pl * g.plane_bytes, &tmA, fullA + 8 * sa, (pl & 1) * g.in_cs + c0, w0, pl >> 1, h0, tc.b);
-          }
-          if (++sa == g.sa) { sa = 0; pha ^= 1; }
-          if (!g.resident) {
-            for (int tap = 0; tap < TAPS; ++tap) {
-              mbar_wait(emptyB + 8 * sb, phb ^ 1);
-              mbar_expect_tx(fullB + 8 * sb, (uint32_t)g.b_tx_bytes);
-              tma_load_2d(b_base + sb * g.b_tile_bytes, &tmB, fullB + 8 * sb, tap * g.cin + c0, n0);
-              if (++sb == g.sb) { sb = 0; phb ^= 1; }
+          for (int sub = 0; sub < (S2 ? 4 : 1); ++sub) {
+            mbar_wait(emptyA + 8 * sa, pha ^ 1);
+            const uint32_t dst = a_base + sa * g.a_stage_bytes;
+            mbar_expect_tx(fullA + 8 * sa, (uint32_t)g.a_tx_bytes);
+            if (!S2) tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, tc.b);
+            else tma_load_5d(dst, &tmA, fullA + 8 * sa, (sub & 1) * g.in_cs + c0, w0, sub >> 1, h0, tc.b);
+            if (++sa == g.sa) { sa = 0; pha ^= 1; }
+            if (!g.resident) {  // this stage's weight tiles, in the tap order the MMA warp consumes
+              constexpr int kT0[5] = {0, 1, 3, 5, 9};
+              const int t0 = S2 ? kT0[sub] : 0, t1 = S2 ? kT0[sub + 1] : TAPS;
+              for (int t = t0; t < t1; ++t) {
+                mbar_wait(emptyB + 8 * sb, phb ^ 1);
+                mbar_expect_tx(fullB + 8 * sb, (uint32_t)g.b_tx_bytes);
+                tma_load_2d(b_base + sb * g.b_tile_bytes, &tmB, fullB + 8 * sb, g.tap_seq[t] * g.cin + c0, n0);
+                if (++sb == g.sb) { sb = 0; phb ^= 1; }
+              }
             }
           }
         }
@@ -283,11 +298,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== MMA issuer
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, aphase = 0;
-    uint32_t tap_off[TAPS];  // registers: the tap loop below is fully unrolled
+    uint32_t tap_off[TAPS], tap_b[TAPS];  // registers: the tap loops below are fully unrolled
+    const uint32_t btile16 = (uint32_t)g.b_tile_bytes >> 4;
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) tap_off[t] = (uint32_t)g.tap_off16[t];
+    for (int t = 0; t < TAPS; ++t) {
+      tap_off[t] = (uint32_t)g.tap_off16[t];
+      tap_b[t] = (uint32_t)(g.tap_seq[t] * g.nkc) * btile16;  // resident weights: tile (tap, chunk) sits at tap*nkc + chunk
+    }
     const uint64_t desc0 = ((uint64_t)g.desc_hi << 32) | (uint64_t)(1u << 16);
-    const uint32_t blk16 = (uint32_t)g.blk_rows_bytes >> 4, btile16 = (uint32_t)g.b_tile_bytes >> 4;
+    const uint32_t blk16 = (uint32_t)g.blk_rows_bytes >> 4;
     const uint32_t idesc = g.idesc;
     const int MB = g.MB, nkc = g.nkc;
     if (g.resident) {
@@ -299,53 +318,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d0 = tmem_base + (uint32_t)(as * MB * g.BN);
       for (int kc = 0; kc < nkc; ++kc) {
-        mbar_wait(fullA + 8 * sa, pha);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a16 = ((a_base + sa * g.a_stage_bytes) & 0x3FFFFu) >> 4;
-        if (g.resident) {
-          if (lane == 0) {
-            const uint32_t b16 = ((b_base & 0x3FFFFu) >> 4) + (uint32_t)kc * btile16;
-            for (int j = 0; j < MB; ++j) {
-              const uint32_t tmem_d = tmem_d0 + (uint32_t)(j * g.BN);
-              const uint32_t aj = a16 + (uint32_t)j * blk16;
 #pragma unroll
-              for (int tap = 0; tap < TAPS; ++tap) {
-                const uint64_t da = desc0 | (uint64_t)(aj + tap_off[tap]);
-                const uint64_t db = desc0 | (uint64_t)(b16 + (uint32_t)(tap * nkc) * btile16);
-#pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                            (tap | k) ? 1u : (uint32_t)(kc != 0));
-              }
-            }
-          }
-          __syncwarp();
-        } else {
-#pragma unroll 1
-          for (int tap = 0; tap < TAPS; ++tap) {
-            mbar_wait(fullB + 8 * sb, phb);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int sub = 0; sub < (S2 ? 4 : 1); ++sub) {
+          // taps served by this A stage: all of them, or one parity plane's {1, 2, 2, 4}
+          constexpr int kT0[4] = {0, 1, 3, 5};
+          const int t0 = S2 ? kT0[sub] : 0;
+          const int nt = S2 ? (sub == 0 ? 1 : (sub == 3 ? 4 : 2)) : TAPS;
+          mbar_wait(fullA + 8 * sa, pha);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a16 = ((a_base + sa * g.a_stage_bytes) & 0x3FFFFu) >> 4;
+          if (g.resident) {
             if (lane == 0) {
-              const uint64_t db = desc0 | (uint64_t)(((b_base + sb * g.b_tile_bytes) & 0x3FFFFu) >> 4);
+              const uint32_t b16 = ((b_base & 0x3FFFFu) >> 4) + (uint32_t)kc * btile16;
               for (int j = 0; j < MB; ++j) {
-                const uint64_t da = desc0 | (uint64_t)(a16 + (uint32_t)j * blk16 + (uint32_t)g.tap_off16[tap]);
+                const uint32_t tmem_d = tmem_d0 + (uint32_t)(j * g.BN);
+                const uint32_t aj = a16 + (uint32_t)j * blk16;
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  umma_bf16(tmem_d0 + (uint32_t)(j * g.BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                            (uint32_t)((kc | tap | k) != 0));
+                for (int q = 0; q < TAPS; ++q) {
+                  if (q >= nt) break;
+                  const int t = t0 + q;
+                  const uint64_t da = desc0 | (uint64_t)(aj + tap_off[t]);
+                  const uint64_t db = desc0 | (uint64_t)(b16 + tap_b[t]);
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (t | k) ? 1u : (uint32_t)(kc != 0));
+                }
               }
-              umma_commit(emptyB + 8 * sb);
             }
             __syncwarp();
-            if (++sb == g.sb) { sb = 0; phb ^= 1; }
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < nt; ++q) {
+              const int t = t0 + q;
+              mbar_wait(fullB + 8 * sb, phb);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              if (lane == 0) {
+                const uint64_t db = desc0 | (uint64_t)(((b_base + sb * g.b_tile_bytes) & 0x3FFFFu) >> 4);
+                for (int j = 0; j < MB; ++j) {
+                  const uint64_t da = desc0 | (uint64_t)(a16 + (uint32_t)j * blk16 + (uint32_t)g.tap_off16[t]);
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_bf16(tmem_d0 + (uint32_t)(j * g.BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (uint32_t)((kc | t | k) != 0));
+                }
+                umma_commit(emptyB + 8 * sb);
+              }
+              __syncwarp();
+              if (++sb == g.sb) { sb = 0; phb ^= 1; }
+            }
           }
+          if (lane == 0) {
+            umma_commit(emptyA + 8 * sa);  // frees the halo tile / plane when the MMAs retire
+            if (kc == nkc - 1 && sub == (S2 ? 3 : 0)) umma_commit(tfull0 + 8 * as);  // accumulators complete
+          }
+          __syncwarp();
+          if (++sa == g.sa) { sa = 0; pha ^= 1; }
         }
-        if (lane == 0) {
-          umma_commit(emptyA + 8 * sa);                      // frees the halo tile when the MMAs retire
-          if (kc == nkc - 1) umma_commit(tfull0 + 8 * as);   // accumulators complete
-        }
-        __syncwarp();
-        if (++sa == g.sa) { sa = 0; pha ^= 1; }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -365,6 +394,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float dfl_first = 0.f;
     pdl_wait();  // residual reads / output writes touch buffers of preceding kernels
     const int oc_shift = g.oc == 64 ? 6 : (g.oc == 32 ? 5 : 4);
+    if (g.fast_epi) {
+      // ---- lean epilogue (the common case: bf16 output through the staging buffer + TMA store, no ragged chunks).
+      // Each warp owns a contiguous range of 16-column chunks and drains them 32 columns per TMEM load; everything that
+      // does not depend on the chunk (staging row address, swizzle term, residual row pointer) is hoisted out of it.
+      const int c_lo = half ? (nch + 1) >> 1 : 0, c_hi = half ? nch : (nch + 1) >> 1;
+      const uint32_t oc_mask = (uint32_t)g.oc - 1u, sw_mask = (uint32_t)g.o_sw_mask, orb = (uint32_t)g.o_row_bytes;
+      const int act = g.act, res_mode = g.res_mode, MBq = g.MB, BNq = g.BN, THq = g.TH;
+      const uint32_t obox = (uint32_t)g.obox_bytes;
+      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * BNq;
+        const int ho0 = tc.th_i * rows_tile + th;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * MBq * BNq);
+        const uint32_t o_stage = o_base + (uint32_t)(os * g.o_stage_bytes);
+        mbar_wait(tfull0 + 8 * as, aphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        bool reclaimed = false, released = false;
+
+        auto epi16 = [&](float(&v)[16], const int c, const uint32_t rowaddr, const uint32_t xr, const bf16 *resrow) {
+          const int col = c * 16;
+          const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0 + col);
+          if (act) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 hb = bp[q];
+              v[4 * q] = silu_half(fmaf(v[4 * q], 0.5f, hb.x));
+              v[4 * q + 1] = silu_half(fmaf(v[4 * q + 1], 0.5f, hb.y));
+              v[4 * q + 2] = silu_half(fmaf(v[4 * q + 2], 0.5f, hb.z));
+              v[4 * q + 3] = silu_half(fmaf(v[4 * q + 3], 0.5f, hb.w));
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bb = bp[q];
+              v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+            }
+          }
+          if (resrow) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(resrow + n0 + col);
+            float r[16];
+            unpack8(__ldg(rp), r);
+            unpack8(__ldg(rp + 1), r + 8);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = (res_mode == B2Y_RES_ADD) ? v[q] + r[q] : v[q] * r[q];
+          }
+          if (row_ok) {
+            const uint32_t dst = rowaddr + (uint32_t)(col >> oc_shift) * obox;
+            const uint32_t u = (((uint32_t)col & oc_mask) * 2u);  // byte offset of the chunk inside the staging row
+            const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (u ^ xr)), "r"(p0.x), "r"(p0.y), "r"(p0.z), "r"(p0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((u + 16u) ^ xr)), "r"(p1.x), "r"(p1.y), "r"(p1.z), "r"(p1.w) : "memory");
+          }
+        };
+
+        for (int j = 0; j < MBq; ++j) {
+          const uint32_t rowoff = (rr0 + (uint32_t)j * blk_out_rows) * orb;
+          const uint32_t xr = ((rowoff >> 7) & sw_mask) << 4;
+          const uint32_t rowaddr = o_stage + rowoff;
+          const bf16 *resrow = nullptr;
+          if (res_mode) {
+            const int ho = ho0 + j * THq;
+            if (row_ok && ho < g.Ho && wo < g.Wo) resrow = g.res + (((size_t)tc.b * g.Ho + ho) * g.Wo + wo) * g.res_cs;
+          }
+          for (int c = c_lo; c < c_hi; c += 2) {
+            const bool two = c + 1 < c_hi;  // warp-uniform
+            float va[16], vb[16];
+            const uint32_t ta = taddr + (uint32_t)(j * BNq + c * 16);
+            if (two) tmem_ld32_issue(ta, va, vb);
+            else tmem_ld16_issue(ta, va);
+            if (!reclaimed) {
+              // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
+              if (elected) {
+                if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              named_bar_sync(1, kEpiThreads);
+              reclaimed = true;
+            }
+            tmem_ld_wait(va);
+            if (two) tmem_ld_wait(vb);
+            if (j == MBq - 1 && c + 2 >= c_hi) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(tempty0 + 8 * as);  // last load of this tile landed: the MMA warp may overwrite the stage
+              released = true;
+            }
+            epi16(va, c, rowaddr, xr, resrow);
+            if (two) epi16(vb, c + 1, rowaddr, xr, resrow);
+          }
+        }
+        if (!reclaimed) {  // a warp without chunks still takes part in the barrier protocol
+          if (elected) {
+            if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          named_bar_sync(1, kEpiThreads);
+        }
+        if (!released) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tempty0 + 8 * as);
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
+        named_bar_sync(2, kEpiThreads);
+        if (elected) {
+          for (int bx = 0; bx < g.n_oboxes; ++bx)
+            if (n0 + bx * g.oc < g.cout)
+              tma_store_4d(&tmO, o_stage + (uint32_t)bx * obox, n0 + bx * g.oc, tc.tw_i * g.TW, tc.th_i * rows_tile, tc.b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++os == g.o_stages) os = 0;
+      }
+    } else
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(g, tile);
       const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
@@ -586,10 +727,15 @@ void find_div(unsigned d, unsigned &mul, unsigned &shr) {  // n / d == umulhi(n,
 
 typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcGeom);
 
-KernelFn pick_kernel(int taps, int ksteps) {
-  if (taps == 1) return ksteps == 4 ? conv_tc_kernel<1, 4> : ksteps == 2 ? conv_tc_kernel<1, 2> : conv_tc_kernel<1, 1>;
-  if (taps == 4) return ksteps == 4 ? conv_tc_kernel<4, 4> : ksteps == 2 ? conv_tc_kernel<4, 2> : conv_tc_kernel<4, 1>;
-  return ksteps == 4 ? conv_tc_kernel<9, 4> : ksteps == 2 ? conv_tc_kernel<9, 2> : conv_tc_kernel<9, 1>;
+template <int TAPS, bool S2>
+KernelFn pick_ksteps(int ksteps) {
+  return ksteps == 4 ? conv_tc_kernel<TAPS, 4, S2> : ksteps == 2 ? conv_tc_kernel<TAPS, 2, S2> : conv_tc_kernel<TAPS, 1, S2>;
+}
+
+KernelFn pick_kernel(int taps, int ksteps, bool stride2) {
+  if (taps == 1) return pick_ksteps<1, false>(ksteps);
+  if (taps == 4) return pick_ksteps<4, false>(ksteps);
+  return stride2 ? pick_ksteps<9, true>(ksteps) : pick_ksteps<9, false>(ksteps);
 }
 
 }  // namespace
@@ -690,20 +836,22 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     const int box_rows = (mb * g.TH + halo) * g.P;
     const int max_shift = (p.kh == 1) ? 0 : ((g.stride2 || p.kh == 2) ? g.P + 1 : 2 * g.P + 2);
     const int need_rows = (mb - 1) * g.TH * g.P + max_shift + 128;
-    const int plane = round_up((box_rows > need_rows ? box_rows : need_rows) * g.row_bytes, 1024);
-    const int a_stage = g.nplanes * plane;
+    // one A stage = one halo box (stride 2: one parity plane; a k-chunk of a tile is nsub consecutive stages)
+    const int a_stage = round_up((box_rows > need_rows ? box_rows : need_rows) * g.row_bytes, 1024);
+    const int nsub = g.stride2 ? 4 : 1;
     const int o_stage = g.tma_out ? g.n_oboxes * mb * 128 * g.o_row_bytes : 0;
     int o_stages = g.tma_out ? 2 : 0;
     const long long fixed = bias_bytes + 1024;
-    const bool res_ok = (g.n_ntiles == 1) && (w_res_bytes + 2LL * a_stage + o_stage + fixed <= smem_budget);
+    const bool res_ok = (g.n_ntiles == 1) && (w_res_bytes + (long long)(nsub + 1) * a_stage + o_stage + fixed <= smem_budget);
     const long long b_bytes = res_ok ? w_res_bytes : 2LL * g.b_tile_bytes;
-    if (b_bytes + a_stage + o_stage + fixed > smem_budget) continue;  // does not fit even single-buffered
-    if (b_bytes + 2LL * a_stage + (long long)o_stages * o_stage + fixed > smem_budget) o_stages = g.tma_out ? 1 : 0;
+    if (b_bytes + (long long)nsub * a_stage + o_stage + fixed > smem_budget) continue;  // does not fit even single-buffered
+    if (b_bytes + (long long)(nsub + 1) * a_stage + (long long)o_stages * o_stage + fixed > smem_budget)
+      o_stages = g.tma_out ? 1 : 0;
     best_mb = mb;
     g.MB = mb;
-    g.plane_bytes = plane;
+    g.plane_bytes = a_stage;
     g.a_stage_bytes = a_stage;
-    g.a_tx_bytes = g.nplanes * box_rows * g.row_bytes;
+    g.a_tx_bytes = box_rows * g.row_bytes;
     g.o_stage_bytes = o_stage;
     g.o_stages = o_stages;
     g.resident = res_ok ? 1 : 0;
@@ -723,31 +871,39 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     b2y_set_error("tcgen05 conv: too many tiles");
     return B2Y_ERR_UNSUPPORTED;
   }
-  // tap table: operand start inside the A stage (plane + row shift), 16-byte units
-  for (int r = 0; r < p.kh; ++r)
-    for (int s = 0; s < p.kw; ++s) {
-      const int t = r * p.kw + s;
-      int plane = 0, shift = 0;
-      if ((p.kh == 3 && !g.stride2) || p.kh == 2) shift = r * g.P + s;
-      else if (p.kh == 3) {
-        plane = ((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1);
-        shift = ((r == 0) ? 0 : 1) * g.P + ((s == 0) ? 0 : 1);
-      }
-      g.tap_off16[t] = (plane * g.plane_bytes + shift * g.row_bytes) >> 4;
-    }
-  // stage counts
+  // tap sequence: position -> (tap index, operand start inside its A stage = row shift, 16-byte units).  Stride 2: taps
+  // grouped by parity plane pl = rowpar*2 + colpar (one stage each): {centre}, {left,right}, {up,down}, {corners}.
+  {
+    int pos = 0;
+    for (int pl = 0; pl < (g.stride2 ? 4 : 1); ++pl)
+      for (int r = 0; r < p.kh; ++r)
+        for (int s = 0; s < p.kw; ++s) {
+          int shift;
+          if (g.stride2) {
+            if ((((r == 1) ? 0 : 1) * 2 + ((s == 1) ? 0 : 1)) != pl) continue;
+            shift = ((r == 0) ? 0 : 1) * g.P + ((s == 0) ? 0 : 1);
+          } else {
+            shift = (p.kh == 1) ? 0 : r * g.P + s;
+          }
+          g.tap_seq[pos] = r * p.kw + s;
+          g.tap_off16[pos] = (shift * g.row_bytes) >> 4;
+          ++pos;
+        }
+  }
+  // stage counts: as many A stages as fit (<= 8): bytes in flight per SM are what hides the HBM latency on these layers
   const int out_bytes = g.o_stages * g.o_stage_bytes;
+  const int nsub = g.stride2 ? 4 : 1;
   int b_bytes_total;
   if (g.resident) {
     g.sb = 0;
     b_bytes_total = (int)w_res_bytes;
   } else {
     g.sb = 4;
-    while (g.sb > 2 && (long long)g.sb * g.b_tile_bytes + 2LL * g.a_stage_bytes + out_bytes + bias_bytes + 1024 > smem_budget) --g.sb;
+    while (g.sb > 2 && (long long)g.sb * g.b_tile_bytes + (long long)(nsub + 1) * g.a_stage_bytes + out_bytes + bias_bytes + 1024 > smem_budget) --g.sb;
     b_bytes_total = g.sb * g.b_tile_bytes;
   }
   int sa = (smem_budget - b_bytes_total - out_bytes - bias_bytes - 1024) / g.a_stage_bytes;
-  if (sa > 4) sa = 4;
+  if (sa > kMaxStages) sa = kMaxStages;
   if (sa < 1) sa = 1;
   g.sa = sa;
   g.o_off = g.sa * g.a_stage_bytes + b_bytes_total;
@@ -773,6 +929,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     if (p.res_mode) ok = ok && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (p.res_cs % 8 == 0);
     g.vec_ok = ok ? 1 : 0;
   }
+  g.fast_epi = (g.tma_out && !g.epi_mode && p.cout % 16 == 0 && (!p.res_mode || g.vec_ok)) ? 1 : 0;
 
   const CUtensorMapSwizzle sw = (g.row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : (g.row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -841,7 +998,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   }
   const long long max_ctas = (long long)num_sms * want_per_sm;
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
-  pl->fn = pick_kernel(g.taps, g.BK / 16);
+  pl->fn = pick_kernel(g.taps, g.BK / 16, g.stride2 != 0);
   B2Y_CUDA_CHECK(cudaFuncSetAttribute(pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   *out = pl;
   return B2Y_OK;
