@@ -120,6 +120,7 @@ struct ConvParams {
   int B, H, W, Ho, Wo, cin, cout, cout_pad;
   int kh, kw, sh, sw, ph, pw, act;
   int asym;                          // 1: padding only before (top/left) -- the 2x2 space-to-depth stem
+  int grouped;                       // 1: block-diagonal weights in groups of 16 channels (depthwise on the tensor cores)
   int epi_mode, a_off, A, nc;        // fused Detect decode (0 none, 1 DFL box, 2 class sigmoid) -> y (B,4+nc,A)
   float det_stride;
 };
@@ -137,6 +138,7 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len);
 int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, ConvTcPlan **out);
 void conv_tc_plan_destroy(ConvTcPlan *p);
 int launch_conv_tc(const ConvTcPlan *p, cudaStream_t st);
+int conv_tc_plan_trace(ConvTcPlan *p, cudaStream_t st);  // debug: one traced launch, timeline printed to stderr
 
 int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, cudaStream_t st);
 int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, int scale,

@@ -61,6 +61,9 @@ struct TcGeom {
   const bf16 *res; int res_cs, res_mode;
   const float *bias;
   int act, vec_ok;
+  int grouped;                          // groups of 16 channels: chunk kc only feeds accumulator columns [16kc, 16kc+16)
+  int flat, real_hw, real_w;            // 1x1 convs run over the flattened pixel axis; real map size for the fused decode
+  unsigned long long *trace;            // debug (B2Y_TRACE_OP): CTA 0 logs %globaltimer at pipeline events, 3 x 64 slots
   int fast_epi;                         // bf16 TMA-store output, whole 16-column chunks, vectorisable residual: lean epilogue
   unsigned dv_nt_mul, dv_nt_shr, dv_tw_mul, dv_tw_shr, dv_th_mul, dv_th_shr;  // tile decode by multiply-shift
   // bf16 outputs leave through shared memory + TMA store
@@ -96,6 +99,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) break;
     if (++spins > kWaitSpinLimit) __trap();  // a broken pipeline must fault, not hang the GPU
   }
+}
+// one lane of a converged warp (the form ptxas recognises: code guarded by it issues warp-uniform instructions such as
+// tcgen05.mma once, without a per-lane serialisation loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
   return mul ? (__umulhi(n, mul) >> shr) : n;
@@ -180,6 +194,14 @@ __device__ __forceinline__ float silu_half(float h) {
   return fmaf(h, t, h);
 }
 
+__device__ __forceinline__ void trace_evt(const TcGeom &g, int role, int &slot) {
+  if (g.trace != nullptr && blockIdx.x == 0 && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g.trace[role * 64 + slot++] = t;
+  }
+}
+
 struct TileCoord {
   int b, th_i, tw_i, nt;
 };
@@ -203,7 +225,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcGeom &g, uint32_t tile)
 // Stride-2 3x3 convs (S2): the four parity planes of a tile are four separate pipeline stages (taps grouped by plane:
 // {centre}, {left,right}, {up,down}, {corners}), so the TMA producer runs several planes ahead of the MMAs instead of
 // the whole 4-plane tile being one (single-buffered) stage.
-template <int TAPS, int KSTEPS, bool S2>
+// EPI selects the epilogue compiled into the instantiation (keeps each kernel's code small: the thin layers run a code
+// path once or twice per launch, so instruction-cache misses are a first-order cost): 0 generic (fp32 / ragged / unaligned
+// outputs), 1 lean bf16 (staging + TMA store), 2 lean fused Detect decode.
+template <int TAPS, int KSTEPS, bool S2, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcGeom g) {
@@ -257,14 +282,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-      if (g.resident) {
-        mbar_expect_tx(wfull, (uint32_t)g.w_bytes_tx);
-        for (int t = 0; t < TAPS * g.nkc; ++t) tma_load_2d(b_base + t * g.b_tile_bytes, &tmB, wfull, t * g.BK, 0);
+    // the whole warp walks the tile list (converged waits); one elected lane issues the TMA instructions
+    {
+      if (elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        if (g.resident) {
+          mbar_expect_tx(wfull, (uint32_t)g.w_bytes_tx);
+          for (int t = 0; t < TAPS * g.nkc; ++t)  // tile (tap, chunk); grouped: only the chunk's own 16 output rows
+            tma_load_2d(b_base + t * g.b_tile_bytes, &tmB, wfull, t * g.BK, g.grouped ? (t % g.nkc) * 16 : 0);
+        }
       }
+      __syncwarp();
+      int tslot = 0;
+      if (lane == 0) trace_evt(g, 0, tslot);  // [0] producer start (prologue done)
       pdl_wait();  // weights are constants; the activations below were written by the preceding kernel(s)
+      if (lane == 0) trace_evt(g, 0, tslot);  // [1] dependency satisfied
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -275,18 +308,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int sub = 0; sub < (S2 ? 4 : 1); ++sub) {
             mbar_wait(emptyA + 8 * sa, pha ^ 1);
+            if (kc == 0 && sub == 0 && lane == 0) trace_evt(g, 0, tslot);  // [2+i] first load of tile i issued
             const uint32_t dst = a_base + sa * g.a_stage_bytes;
-            mbar_expect_tx(fullA + 8 * sa, (uint32_t)g.a_tx_bytes);
-            if (!S2) tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, tc.b);
-            else tma_load_5d(dst, &tmA, fullA + 8 * sa, (sub & 1) * g.in_cs + c0, w0, sub >> 1, h0, tc.b);
+            if (elect_one()) {
+              mbar_expect_tx(fullA + 8 * sa, (uint32_t)g.a_tx_bytes);
+              if (!S2) tma_load_4d(dst, &tmA, fullA + 8 * sa, c0, w0, h0, tc.b);
+              else tma_load_5d(dst, &tmA, fullA + 8 * sa, (sub & 1) * g.in_cs + c0, w0, sub >> 1, h0, tc.b);
+            }
+            __syncwarp();
             if (++sa == g.sa) { sa = 0; pha ^= 1; }
             if (!g.resident) {  // this stage's weight tiles, in the tap order the MMA warp consumes
               constexpr int kT0[5] = {0, 1, 3, 5, 9};
               const int t0 = S2 ? kT0[sub] : 0, t1 = S2 ? kT0[sub + 1] : TAPS;
               for (int t = t0; t < t1; ++t) {
                 mbar_wait(emptyB + 8 * sb, phb ^ 1);
-                mbar_expect_tx(fullB + 8 * sb, (uint32_t)g.b_tx_bytes);
-                tma_load_2d(b_base + sb * g.b_tile_bytes, &tmB, fullB + 8 * sb, g.tap_seq[t] * g.cin + c0, n0);
+                if (elect_one()) {
+                  mbar_expect_tx(fullB + 8 * sb, (uint32_t)g.b_tx_bytes);
+                  tma_load_2d(b_base + sb * g.b_tile_bytes, &tmB, fullB + 8 * sb, g.tap_seq[t] * g.cin + c0, n0);
+                }
+                __syncwarp();
                 if (++sb == g.sb) { sb = 0; phb ^= 1; }
               }
             }
@@ -313,9 +353,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(wfull, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    int tslot = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (g.trace != nullptr && lane == 0) trace_evt(g, 1, tslot);  // [2i] accumulator stage free
       const uint32_t tmem_d0 = tmem_base + (uint32_t)(as * MB * g.BN);
       for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll
@@ -328,10 +370,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a16 = ((a_base + sa * g.a_stage_bytes) & 0x3FFFFu) >> 4;
           if (g.resident) {
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t b16 = ((b_base & 0x3FFFFu) >> 4) + (uint32_t)kc * btile16;
+              const uint32_t gcol = g.grouped ? (uint32_t)kc * 16u : 0u;      // grouped: this chunk's own 16 columns,
+              const uint32_t acc0 = g.grouped ? 0u : (uint32_t)(kc != 0);     // each started afresh by its first tap
               for (int j = 0; j < MB; ++j) {
-                const uint32_t tmem_d = tmem_d0 + (uint32_t)(j * g.BN);
+                const uint32_t tmem_d = tmem_d0 + (uint32_t)(j * g.BN) + gcol;
                 const uint32_t aj = a16 + (uint32_t)j * blk16;
 #pragma unroll
                 for (int q = 0; q < TAPS; ++q) {
@@ -341,8 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const uint64_t db = desc0 | (uint64_t)(b16 + tap_b[t]);
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k)
-                    umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                              (t | k) ? 1u : (uint32_t)(kc != 0));
+                    umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (t | k) ? 1u : acc0);
                 }
               }
             }
@@ -353,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int t = t0 + q;
               mbar_wait(fullB + 8 * sb, phb);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              if (lane == 0) {
+              if (elect_one()) {
                 const uint64_t db = desc0 | (uint64_t)(((b_base + sb * g.b_tile_bytes) & 0x3FFFFu) >> 4);
                 for (int j = 0; j < MB; ++j) {
                   const uint64_t da = desc0 | (uint64_t)(a16 + (uint32_t)j * blk16 + (uint32_t)g.tap_off16[t]);
@@ -368,9 +411,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (++sb == g.sb) { sb = 0; phb ^= 1; }
             }
           }
-          if (lane == 0) {
+          if (elect_one()) {
             umma_commit(emptyA + 8 * sa);  // frees the halo tile / plane when the MMAs retire
-            if (kc == nkc - 1 && sub == (S2 ? 3 : 0)) umma_commit(tfull0 + 8 * as);  // accumulators complete
+            if (kc == nkc - 1 && sub == (S2 ? 3 : 0)) {
+              umma_commit(tfull0 + 8 * as);  // accumulators complete
+              trace_evt(g, 1, tslot);        // [2i+1] all MMAs of tile i issued
+            }
           }
           __syncwarp();
           if (++sa == g.sa) { sa = 0; pha ^= 1; }
@@ -392,27 +438,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0, os = 0;
     uint32_t aphase = 0;
     float dfl_first = 0.f;
+    int eslot = 0;
     pdl_wait();  // residual reads / output writes touch buffers of preceding kernels
     const int oc_shift = g.oc == 64 ? 6 : (g.oc == 32 ? 5 : 4);
-    if (g.fast_epi) {
+    if constexpr (EPI == 1) {
       // ---- lean epilogue (the common case: bf16 output through the staging buffer + TMA store, no ragged chunks).
-      // Each warp owns a contiguous range of 16-column chunks and drains them 32 columns per TMEM load; everything that
-      // does not depend on the chunk (staging row address, swizzle term, residual row pointer) is hoisted out of it.
-      const int c_lo = half ? (nch + 1) >> 1 : 0, c_hi = half ? nch : (nch + 1) >> 1;
+      // A warp's work items are (block j, pair of 16-column chunks): it owns a contiguous half of the chunk range (or,
+      // for 16-channel outputs, every other block), drains 32 columns per TMEM load, and has the NEXT item's residual
+      // rows in flight while it does the math of the current one.  Everything that does not depend on the chunk
+      // (staging row address, swizzle term, residual row pointer) is hoisted out of it.
+      const bool by_block = (nch == 1);  // one chunk per block: split the blocks between the two warps of a quadrant
+      const int c_lo = by_block ? 0 : (half ? (nch + 1) >> 1 : 0);
+      const int c_hi = by_block ? 1 : (half ? nch : (nch + 1) >> 1);
+      const int j_lo = by_block ? half : 0, j_step = by_block ? 2 : 1;
       const uint32_t oc_mask = (uint32_t)g.oc - 1u, sw_mask = (uint32_t)g.o_sw_mask, orb = (uint32_t)g.o_row_bytes;
       const int act = g.act, res_mode = g.res_mode, MBq = g.MB, BNq = g.BN, THq = g.TH;
       const uint32_t obox = (uint32_t)g.obox_bytes;
+      const bool has_items = (c_lo < c_hi) && (j_lo < MBq);
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
         const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * BNq;
         const int ho0 = tc.th_i * rows_tile + th;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * MBq * BNq);
         const uint32_t o_stage = o_base + (uint32_t)(os * g.o_stage_bytes);
+        const bool col_ok = row_ok && wo < g.Wo;
+
+        // residual rows of item (j, c): 2 x 32 B per chunk, requested one item ahead
+        auto res_ptr = [&](int j, int c) -> const uint4 * {
+          const int ho = ho0 + j * THq;
+          if (!(col_ok && ho < g.Ho)) return nullptr;
+          return reinterpret_cast<const uint4 *>(g.res + (((size_t)tc.b * g.Ho + ho) * g.Wo + wo) * g.res_cs + n0 + c * 16);
+        };
+        uint4 rc[4];  // residual of the current item
+        bool rc_ok = false;
+        auto res_load = [&](int j, int c) {
+          const uint4 *rp = res_ptr(j, c);
+          rc_ok = rp != nullptr;
+          if (rc_ok) {
+            rc[0] = __ldg(rp);
+            rc[1] = __ldg(rp + 1);
+            if (c + 1 < c_hi) {
+              rc[2] = __ldg(rp + 2);
+              rc[3] = __ldg(rp + 3);
+            }
+          }
+        };
+        auto res_prefetch = [&](int j, int c) {  // next item: pull its rows into L1 without holding registers
+          const uint4 *rp = res_ptr(j, c);
+          if (rp) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+            if (c + 1 < c_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 2));
+          }
+        };
+        if (res_mode && has_items) res_load(j_lo, c_lo);  // independent of the MMAs: in flight across the wait below
+
         mbar_wait(tfull0 + 8 * as, aphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elected) trace_evt(g, 2, eslot);  // [5i] accumulators ready
         bool reclaimed = false, released = false;
 
-        auto epi16 = [&](float(&v)[16], const int c, const uint32_t rowaddr, const uint32_t xr, const bf16 *resrow) {
+        auto epi16 = [&](float(&v)[16], const int c, const uint32_t rowaddr, const uint32_t xr, const uint4 *r, const bool r_ok) {
           const int col = c * 16;
           const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0 + col);
           if (act) {
@@ -431,13 +516,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
             }
           }
-          if (resrow) {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(resrow + n0 + col);
-            float r[16];
-            unpack8(__ldg(rp), r);
-            unpack8(__ldg(rp + 1), r + 8);
+          if (r_ok) {
+            float rf[16];
+            unpack8(r[0], rf);
+            unpack8(r[1], rf + 8);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = (res_mode == B2Y_RES_ADD) ? v[q] + r[q] : v[q] * r[q];
+            for (int q = 0; q < 16; ++q) v[q] = (res_mode == B2Y_RES_ADD) ? v[q] + rf[q] : v[q] * rf[q];
           }
           if (row_ok) {
             const uint32_t dst = rowaddr + (uint32_t)(col >> oc_shift) * obox;
@@ -448,43 +532,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         };
 
-        for (int j = 0; j < MBq; ++j) {
+        for (int j = j_lo; j < MBq && has_items; j += j_step) {
           const uint32_t rowoff = (rr0 + (uint32_t)j * blk_out_rows) * orb;
           const uint32_t xr = ((rowoff >> 7) & sw_mask) << 4;
           const uint32_t rowaddr = o_stage + rowoff;
-          const bf16 *resrow = nullptr;
-          if (res_mode) {
-            const int ho = ho0 + j * THq;
-            if (row_ok && ho < g.Ho && wo < g.Wo) resrow = g.res + (((size_t)tc.b * g.Ho + ho) * g.Wo + wo) * g.res_cs;
-          }
           for (int c = c_lo; c < c_hi; c += 2) {
             const bool two = c + 1 < c_hi;  // warp-uniform
+            const bool last = (j + j_step >= MBq) && (c + 2 >= c_hi);
             float va[16], vb[16];
             const uint32_t ta = taddr + (uint32_t)(j * BNq + c * 16);
             if (two) tmem_ld32_issue(ta, va, vb);
             else tmem_ld16_issue(ta, va);
+            const bool first = (j == j_lo) && (c == c_lo);
+            const int jn = (c + 2 < c_hi) ? j : j + j_step, cn = (c + 2 < c_hi) ? c + 2 : c_lo;  // next item
+            if (res_mode) {
+              if (!first) res_load(j, c);           // (the first item's rows were requested before the accumulator wait)
+              if (!last) res_prefetch(jn, cn);
+            }
             if (!reclaimed) {
               // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
-              if (elected) {
+              if (warp == 2) {
                 if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
               }
               named_bar_sync(1, kEpiThreads);
               reclaimed = true;
+              if (elected) trace_evt(g, 2, eslot);  // [5i+1] staging buffer reclaimed (all warps arrived)
             }
             tmem_ld_wait(va);
             if (two) tmem_ld_wait(vb);
-            if (j == MBq - 1 && c + 2 >= c_hi) {
+            if (last) {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               mbar_arrive(tempty0 + 8 * as);  // last load of this tile landed: the MMA warp may overwrite the stage
               released = true;
             }
-            epi16(va, c, rowaddr, xr, resrow);
-            if (two) epi16(vb, c + 1, rowaddr, xr, resrow);
+            epi16(va, c, rowaddr, xr, rc, res_mode && rc_ok);
+            if (two) epi16(vb, c + 1, rowaddr, xr, rc + 2, res_mode && rc_ok);
           }
         }
-        if (!reclaimed) {  // a warp without chunks still takes part in the barrier protocol
-          if (elected) {
+        if (!reclaimed) {  // a warp without items still takes part in the barrier protocol
+          if (warp == 2) {
             if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
@@ -495,17 +582,131 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive(tempty0 + 8 * as);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
+        if (elected) trace_evt(g, 2, eslot);  // [5i+2] this thread's math + staging writes done
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
         named_bar_sync(2, kEpiThreads);
-        if (elected) {
-          for (int bx = 0; bx < g.n_oboxes; ++bx)
-            if (n0 + bx * g.oc < g.cout)
-              tma_store_4d(&tmO, o_stage + (uint32_t)bx * obox, n0 + bx * g.oc, tc.tw_i * g.TW, tc.th_i * rows_tile, tc.b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (elected) trace_evt(g, 2, eslot);  // [5i+3] every warp's staging writes done
+        if (warp == 2) {
+          if (elect_one()) {
+            for (int bx = 0; bx < g.n_oboxes; ++bx)
+              if (n0 + bx * g.oc < g.cout)
+                tma_store_4d(&tmO, o_stage + (uint32_t)bx * obox, n0 + bx * g.oc, tc.tw_i * g.TW, tc.th_i * rows_tile, tc.b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
+          if (elected) trace_evt(g, 2, eslot);  // [5i+4] TMA store issued
         }
         if (++os == g.o_stages) os = 0;
       }
-    } else
+    } else if constexpr (EPI == 2) {
+      // ---- lean fused Detect._inference (head.py:100-131) for the 1x1 output convs of a level: thread = anchor.
+      // epi_mode 1 (box conv, 64 = 4 sides x 16 DFL bins): the warp pair of a lane quadrant splits the sides, half 0 takes
+      // left/right (-> cx, w), half 1 top/bottom (-> cy, h): softmax-expectation (block.py:73-76), make_anchors +0.5
+      // (tal.py:371-383), dist2bbox xywh (tal.py:386-395), * stride.  epi_mode 2 (class conv): sigmoid of nc columns,
+      // contiguous column ranges per warp.  Results go straight to y (B, 4+nc, A) fp32: 32 lanes = 32 consecutive anchors.
+      const int MBq = g.MB, BNq = g.BN, THq = g.TH, mode = g.epi_mode;
+      const int c_lo = (mode == 1) ? half : (half ? (nch + 1) >> 1 : 0);
+      const int c_hi = (mode == 1) ? 4 : (half ? nch : (nch + 1) >> 1);
+      const int c_step = (mode == 1) ? 4 : 2;  // mode 1: one item = chunks (half, half + 2)
+      const float kLog2e = 1.4426950408889634f;
+      const size_t An = (size_t)g.A;
+      for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * BNq;
+        const int ho0 = tc.th_i * rows_tile + th;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * MBq * BNq);
+        mbar_wait(tfull0 + 8 * as, aphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        bool released = false;
+        for (int j = 0; j < MBq; ++j) {
+          const int ho = ho0 + j * THq;
+          const bool valid = row_ok && ho < g.Ho && wo < g.Wo;
+          // image / anchor coordinates (1x1 convs run over the flattened pixel axis)
+          int rb = tc.b, rho = ho, rwo = wo;
+          size_t apix = (size_t)ho * g.Wo + wo;
+          if (g.flat) {
+            rb = (int)(apix / (size_t)g.real_hw);
+            apix -= (size_t)rb * g.real_hw;
+            rho = (int)apix / g.real_w;
+            rwo = (int)apix - rho * g.real_w;
+          }
+          float *yrow = reinterpret_cast<float *>(g.out) + (size_t)rb * (4 + g.nc) * An + g.a_off + apix;
+          for (int c = c_lo; c < c_hi; c += c_step) {
+            const bool two = (mode == 1) || (c + 1 < c_hi);
+            const bool last = (j == MBq - 1) && (c + c_step >= c_hi);
+            float va[16], vb[16];
+            const uint32_t ta = taddr + (uint32_t)(j * BNq + c * 16);
+            if (mode == 1) {
+              tmem_ld16_issue(ta, va);
+              tmem_ld16_issue(ta + 32u, vb);
+            } else if (two) {
+              tmem_ld32_issue(ta, va, vb);
+            } else {
+              tmem_ld16_issue(ta, va);
+            }
+            tmem_ld_wait(va);
+            if (two) tmem_ld_wait(vb);
+            if (last) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(tempty0 + 8 * as);
+              released = true;
+            }
+            if (mode == 1) {
+              auto dfl = [&](float(&v)[16], const int cc) -> float {
+                const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0 + cc * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 bb = bp[q];
+                  v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+                }
+                float mx = v[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) mx = fmaxf(mx, v[q]);
+                float se = 0.f, sk = 0.f;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const float e = exp2f((v[q] - mx) * kLog2e);
+                  se += e;
+                  sk = fmaf(e, (float)q, sk);
+                }
+                return __fdividef(sk, se);
+              };
+              const float d1 = dfl(va, c), d2 = dfl(vb, c + 2);  // (left, right) or (top, bottom)
+              if (valid) {
+                const float anc = (half == 0 ? (float)rwo : (float)rho) + 0.5f;
+                const float p1 = anc - d1, p2 = anc + d2;
+                yrow[(size_t)half * An] = ((p1 + p2) * 0.5f) * g.det_stride;        // cx | cy
+                yrow[(size_t)(2 + half) * An] = (p2 - p1) * g.det_stride;          // w  | h
+              }
+            } else {
+              auto sig16 = [&](float(&v)[16], const int cc) {
+                const int n = n0 + cc * 16;
+                if (n >= g.cout) return;
+                const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n);
+                float *yp = yrow + (size_t)(4 + n) * An;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 bb = bp[q];
+                  v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+                }
+                if (valid) {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q)
+                    if (n + q < g.cout) yp[(size_t)q * An] = __fdividef(1.f, 1.f + exp2f(-v[q] * kLog2e));
+                }
+              };
+              sig16(va, c);
+              if (two) sig16(vb, c + 1);
+            }
+          }
+        }
+        if (!released) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tempty0 + 8 * as);
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    } else {
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(g, tile);
       const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * g.BN;
@@ -539,6 +740,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (g.epi_mode) {
           // ---- fused Detect._inference: thread = one anchor (pixel); chunk c of the box conv = one box side (16 DFL bins)
+          // image / anchor coordinates (the conv itself may run over the flattened pixel axis)
+          int rb = tc.b, rho = ho, rwo = wo;
+          size_t apix = (size_t)ho * g.Wo + wo;
+          if (g.flat) {
+            rb = (int)(apix / (size_t)g.real_hw);
+            apix -= (size_t)rb * g.real_hw;
+            rho = (int)apix / g.real_w;
+            rwo = (int)apix - rho * g.real_w;
+          }
           if (g.epi_mode == 1) {
             float mx = v[0];
 #pragma unroll
@@ -554,16 +764,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (c < 2) {
               dfl_first = dist;          // left (c = 0) or top (c = 1); the partner side is this warp's next chunk
             } else if (valid) {
-              const float anc = (c == 2 ? (float)wo : (float)ho) + 0.5f;  // make_anchors (tal.py:371-383)
-              const float p1 = anc - dfl_first, p2 = anc + dist;          // dist2bbox (tal.py:386-395)
-              float *yb = reinterpret_cast<float *>(g.out) + ((size_t)tc.b * (4 + g.nc) + (c - 2)) * g.A + g.a_off +
-                          (size_t)ho * g.Wo + wo;
+              const float anc = (c == 2 ? (float)rwo : (float)rho) + 0.5f;  // make_anchors (tal.py:371-383)
+              const float p1 = anc - dfl_first, p2 = anc + dist;            // dist2bbox (tal.py:386-395)
+              float *yb = reinterpret_cast<float *>(g.out) + ((size_t)rb * (4 + g.nc) + (c - 2)) * g.A + g.a_off + apix;
               yb[0] = ((p1 + p2) * 0.5f) * g.det_stride;         // cx | cy
               yb[(size_t)2 * g.A] = (p2 - p1) * g.det_stride;   // w  | h
             }
           } else if (valid) {
-            float *yb = reinterpret_cast<float *>(g.out) + ((size_t)tc.b * (4 + g.nc) + 4 + n) * g.A + g.a_off +
-                        (size_t)ho * g.Wo + wo;
+            float *yb = reinterpret_cast<float *>(g.out) + ((size_t)rb * (4 + g.nc) + 4 + n) * g.A + g.a_off + apix;
 #pragma unroll
             for (int q = 0; q < 16; ++q)
               if (n + q < g.cout) yb[(size_t)q * g.A] = 1.f / (1.f + expf(-v[q]));
@@ -643,7 +851,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (two) tmem_ld16_issue(taddr + (uint32_t)(j1 * g.BN + c1 * 16), v1);
         if (!reclaimed && g.tma_out) {
           // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
-          if (elected) {
+          if (warp == 2) {
             if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
@@ -661,7 +869,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (two) chunk(v1, j1, c1);
       }
       if (!reclaimed && g.tma_out) {  // a warp without chunks still takes part in the barrier protocol
-        if (elected) {
+        if (warp == 2) {
           if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
@@ -675,17 +883,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (g.tma_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
         named_bar_sync(2, kEpiThreads);
-        if (elected) {
-          for (int bx = 0; bx < g.n_oboxes; ++bx)
-            if (n0 + bx * g.oc < g.cout)
-              tma_store_4d(&tmO, o_stage + (uint32_t)(bx * g.obox_bytes), n0 + bx * g.oc, tc.tw_i * g.TW,
-                           tc.th_i * rows_tile, tc.b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (warp == 2) {
+          if (elect_one()) {
+            for (int bx = 0; bx < g.n_oboxes; ++bx)
+              if (n0 + bx * g.oc < g.cout)
+                tma_store_4d(&tmO, o_stage + (uint32_t)(bx * g.obox_bytes), n0 + bx * g.oc, tc.tw_i * g.TW,
+                             tc.th_i * rows_tile, tc.b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
         }
         if (++os == g.o_stages) os = 0;
       }
     }
-    if (g.tma_out && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (g.tma_out && warp == 2) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (elected) trace_evt(g, 2, eslot);  // last: all stores complete
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -727,15 +942,22 @@ void find_div(unsigned d, unsigned &mul, unsigned &shr) {  // n / d == umulhi(n,
 
 typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcGeom);
 
-template <int TAPS, bool S2>
+template <int TAPS, bool S2, int EPI>
 KernelFn pick_ksteps(int ksteps) {
-  return ksteps == 4 ? conv_tc_kernel<TAPS, 4, S2> : ksteps == 2 ? conv_tc_kernel<TAPS, 2, S2> : conv_tc_kernel<TAPS, 1, S2>;
+  return ksteps == 4 ? conv_tc_kernel<TAPS, 4, S2, EPI> : ksteps == 2 ? conv_tc_kernel<TAPS, 2, S2, EPI>
+                                                                        : conv_tc_kernel<TAPS, 1, S2, EPI>;
 }
 
-KernelFn pick_kernel(int taps, int ksteps, bool stride2) {
-  if (taps == 1) return pick_ksteps<1, false>(ksteps);
-  if (taps == 4) return pick_ksteps<4, false>(ksteps);
-  return stride2 ? pick_ksteps<9, true>(ksteps) : pick_ksteps<9, false>(ksteps);
+template <int EPI>
+KernelFn pick_taps(int taps, int ksteps, bool stride2) {
+  if (taps == 1) return pick_ksteps<1, false, EPI>(ksteps);
+  if (taps == 4) return pick_ksteps<4, false, EPI>(ksteps);
+  return stride2 ? pick_ksteps<9, true, EPI>(ksteps) : pick_ksteps<9, false, EPI>(ksteps);
+}
+
+KernelFn pick_kernel(int taps, int ksteps, bool stride2, int epi) {
+  if (epi == 2) return pick_ksteps<1, false, 2>(ksteps);  // the Detect output convs are 1x1
+  return epi == 1 ? pick_taps<1>(taps, ksteps, stride2) : pick_taps<0>(taps, ksteps, stride2);
 }
 
 }  // namespace
@@ -743,6 +965,7 @@ KernelFn pick_kernel(int taps, int ksteps, bool stride2) {
 struct ConvTcPlan {
   CUtensorMap tmA, tmB, tmO;
   TcGeom g;
+  unsigned long long *trace = nullptr;  // device buffer when tracing (B2Y_TRACE_OP)
   int grid;
   size_t smem;
   KernelFn fn;
@@ -761,6 +984,8 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
   if (!(k1 || k3s1 || k3s2 || k2)) return no("kernel/stride/padding combination");
   if (p.epi_mode && !(k1 && p.out_f32 && p.res_mode == 0 && !p.act)) return no("fused decode needs a plain fp32 1x1 conv");
   if (p.epi_mode == 1 && p.cout != 64) return no("fused DFL decode needs 64 box channels");
+  if (p.grouped && !(p.cin == p.cout && p.cout == p.cout_pad && p.cout <= 256 && !p.epi_mode && p.kh == 3 && p.sh == 1))
+    return no("grouped (depthwise) mode needs a 3x3 s1 conv with cin == cout <= 256, multiple of 16");
   if (p.cin % 16) return no("cin not a multiple of 16");
   if (p.cout_pad % 16) return no("cout_pad not a multiple of 16");
   if (p.in_cs % 8 || (reinterpret_cast<uintptr_t>(p.in) & 15)) return no("input view not 16-byte aligned");
@@ -769,9 +994,9 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
   return true;
 }
 
-int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, ConvTcPlan **out) {
+int conv_tc_plan_create(const ConvParams &p_in, int device, const TcConfig &cfg, ConvTcPlan **out) {
   char why[128];
-  B2Y_REQUIRE(conv_tc_supported(p, why, sizeof(why)), B2Y_ERR_UNSUPPORTED, "tcgen05 conv: %s", why);
+  B2Y_REQUIRE(conv_tc_supported(p_in, why, sizeof(why)), B2Y_ERR_UNSUPPORTED, "tcgen05 conv: %s", why);
   EncodeTiledFn encode = get_encode_fn();
   B2Y_REQUIRE(encode != nullptr, B2Y_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cudaDeviceProp prop;
@@ -780,10 +1005,29 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   ConvTcPlan *pl = new ConvTcPlan();
   TcGeom &g = pl->g;
   memset(&g, 0, sizeof(g));
+  // 1x1 convs see the activations as one flat pixel axis (NHWC pixels are equidistant in memory across rows and
+  // images): a tile is Wf consecutive pixels x MB rows of a (npix/Wf, Wf) grid, Wf the largest divisor of npix <= 128,
+  // so accumulator blocks are full and every TMA box row is one contiguous run, whatever the map size.
+  ConvParams pf = p_in;
+  if (p_in.kh == 1) {
+    const long long npix = (long long)p_in.B * p_in.Ho * p_in.Wo;
+    int wf = 128;
+    while (wf > 1 && npix % wf) --wf;
+    if (wf >= 64 && npix / wf <= 65535) {
+      g.flat = 1;
+      g.real_hw = p_in.Ho * p_in.Wo;
+      g.real_w = p_in.Wo;
+      pf.B = 1;
+      pf.H = pf.Ho = (int)(npix / wf);
+      pf.W = pf.Wo = wf;
+    }
+  }
+  const ConvParams &p = pf;
   g.B = p.B; g.Ho = p.Ho; g.Wo = p.Wo; g.cin = p.cin; g.cout = p.cout; g.cout_pad = p.cout_pad;
   g.taps = p.kh * p.kw; g.stride2 = (p.sh == 2); g.in_cs = p.in_cs;
   g.nplanes = g.stride2 ? 4 : 1;
-  g.BK = (p.cin % 64 == 0) ? 64 : (p.cin % 32 == 0) ? 32 : 16;
+  g.grouped = p.grouped ? 1 : 0;
+  g.BK = g.grouped ? 16 : (p.cin % 64 == 0) ? 64 : (p.cin % 32 == 0) ? 32 : 16;
   g.nkc = p.cin / g.BK;
   g.row_bytes = g.BK * 2;
   const int halo = (p.kh == 3) ? (g.stride2 ? 1 : 2) : (p.kh == 2 ? 1 : 0);  // extra halo columns/rows per tile
@@ -799,9 +1043,10 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   g.o_sw_mask = g.oc == 64 ? 7 : (g.oc == 32 ? 3 : 1);
   const int bias_bytes = round_up(p.cout_pad * 4, 1024);
   const int w_tiles = g.taps * g.nkc;
-  g.b_tile_bytes = round_up(g.BN * g.row_bytes, 1024);
-  g.b_tx_bytes = g.BN * g.row_bytes;
-  const long long w_res_bytes = (long long)w_tiles * g.b_tile_bytes;
+  const int b_rows = g.grouped ? 16 : g.BN;  // weight rows per (tap, chunk) tile
+  g.b_tile_bytes = round_up(b_rows * g.row_bytes, g.grouped ? 512 : 1024);
+  g.b_tx_bytes = b_rows * g.row_bytes;
+  const long long w_res_bytes = round_up(w_tiles * g.b_tile_bytes, 1024);
   g.w_bytes_tx = w_tiles * g.b_tx_bytes;
 
   // spatial block: accumulator rows m = th*P + tw, P = TW + halo; maximise useful rows per 128-row MMA block
@@ -815,7 +1060,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
       if (th < 1 || P > 256) continue;
       const double eff = (double)p.Ho * p.Wo / ((double)ceil_div(p.Ho, th) * ceil_div(p.Wo, tw) * 128.0);
       const double amp = (double)(th + halo) * P / ((double)th * tw);  // halo read amplification
-      const double score = eff - 0.02 * amp;
+      const double score = eff - 0.02 * amp + 1e-4 * tw;  // ties: the widest tile (longest contiguous TMA rows)
       if (score > best) { best = score; bth = th; btw = tw; }
     }
     g.TH = bth; g.TW = btw; g.P = btw + halo;
@@ -842,6 +1087,8 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     const int o_stage = g.tma_out ? g.n_oboxes * mb * 128 * g.o_row_bytes : 0;
     int o_stages = g.tma_out ? 2 : 0;
     const long long fixed = bias_bytes + 1024;
+    if (g.grouped && !((g.n_ntiles == 1) && (w_res_bytes + (long long)(nsub + 1) * a_stage + o_stage + fixed <= smem_budget)))
+      continue;  // grouped weights are tiny and must be resident
     const bool res_ok = (g.n_ntiles == 1) && (w_res_bytes + (long long)(nsub + 1) * a_stage + o_stage + fixed <= smem_budget);
     const long long b_bytes = res_ok ? w_res_bytes : 2LL * g.b_tile_bytes;
     if (b_bytes + (long long)nsub * a_stage + o_stage + fixed > smem_budget) continue;  // does not fit even single-buffered
@@ -896,7 +1143,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   int b_bytes_total;
   if (g.resident) {
     g.sb = 0;
-    b_bytes_total = (int)w_res_bytes;
+    b_bytes_total = round_up((int)w_res_bytes, 1024);  // keeps the output staging area 1024-byte aligned
   } else {
     g.sb = 4;
     while (g.sb > 2 && (long long)g.sb * g.b_tile_bytes + (long long)(nsub + 1) * g.a_stage_bytes + out_bytes + bias_bytes + 1024 > smem_budget) --g.sb;
@@ -904,6 +1151,14 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   }
   int sa = (smem_budget - b_bytes_total - out_bytes - bias_bytes - 1024) / g.a_stage_bytes;
   if (sa > kMaxStages) sa = kMaxStages;
+  {
+    // a CTA never has more than its own tiles' stages in flight: thin layers (1-2 tiles per CTA) keep their shared-memory
+    // request small, so the next kernel's CTAs can become resident beside them (PDL) instead of queueing for the SM
+    const long long max_ctas_ = (long long)num_sms * want_per_sm;
+    const long long tiles_per_cta = (g.ntiles + max_ctas_ - 1) / max_ctas_;
+    const long long useful = tiles_per_cta * g.nkc * nsub;
+    if (sa > useful) sa = (int)(useful < nsub ? nsub : useful);
+  }
   if (sa < 1) sa = 1;
   g.sa = sa;
   g.o_off = g.sa * g.a_stage_bytes + b_bytes_total;
@@ -918,7 +1173,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   const unsigned layout = (g.row_bytes == 128) ? 2u : (g.row_bytes == 64) ? 4u : 6u;  // UMMA LayoutType SW128/SW64/SW32
   const unsigned sbo = (unsigned)(8 * g.row_bytes) >> 4;
   g.desc_hi = sbo | (1u << 14) | (layout << 29);  // bits [32,46) SBO, [46,48) version=1, [61,64) layout
-  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(g.BN >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((g.grouped ? 16 : g.BN) >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
   g.out = p.out; g.out_cs = p.out_cs; g.out_f32 = p.out_f32;
   g.res = p.res; g.res_cs = p.res_cs; g.res_mode = p.res_mode;
   g.bias = p.bias; g.act = p.act;
@@ -930,6 +1185,12 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
     g.vec_ok = ok ? 1 : 0;
   }
   g.fast_epi = (g.tma_out && !g.epi_mode && p.cout % 16 == 0 && (!p.res_mode || g.vec_ok)) ? 1 : 0;
+  {  // timing experiments only (results are wrong with either): which pipe bounds a layer?
+    static const char *na = getenv("B2Y_DEBUG_NOACT"), *ns = getenv("B2Y_DEBUG_NOSHIFT");
+    if (na && na[0] == '1') g.act = 0;
+    if (ns && ns[0] == '1')
+      for (int t = 0; t < 9; ++t) g.tap_off16[t] = 0;
+  }
 
   const CUtensorMapSwizzle sw = (g.row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : (g.row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -961,7 +1222,7 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   {
     const cuuint64_t dims[2] = {(cuuint64_t)g.taps * p.cin, (cuuint64_t)p.cout_pad};
     const cuuint64_t strides[1] = {(cuuint64_t)g.taps * p.cin * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)g.BK, (cuuint32_t)g.BN};
+    const cuuint32_t box[2] = {(cuuint32_t)g.BK, (cuuint32_t)(g.grouped ? 16 : g.BN)};
     r = encode(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(p.w), dims, strides, box, ones,
                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -998,13 +1259,42 @@ int conv_tc_plan_create(const ConvParams &p, int device, const TcConfig &cfg, Co
   }
   const long long max_ctas = (long long)num_sms * want_per_sm;
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
-  pl->fn = pick_kernel(g.taps, g.BK / 16, g.stride2 != 0);
+  pl->fn = pick_kernel(g.taps, g.BK / 16, g.stride2 != 0, g.epi_mode ? 2 : (g.fast_epi ? 1 : 0));
   B2Y_CUDA_CHECK(cudaFuncSetAttribute(pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   *out = pl;
   return B2Y_OK;
 }
 
-void conv_tc_plan_destroy(ConvTcPlan *p) { delete p; }
+void conv_tc_plan_destroy(ConvTcPlan *p) {
+  if (p && p->trace) cudaFree(p->trace);
+  delete p;
+}
+
+// Debug aid: log the pipeline timeline of CTA 0 (producer / MMA / epilogue events, ns relative to the first) to stderr.
+int conv_tc_plan_trace(ConvTcPlan *pl, cudaStream_t st) {
+  if (!pl->trace) B2Y_CUDA_CHECK(cudaMalloc(&pl->trace, 3 * 64 * sizeof(unsigned long long)));
+  pl->g.trace = pl->trace;
+  B2Y_CUDA_CHECK(cudaMemsetAsync(pl->trace, 0, 3 * 64 * sizeof(unsigned long long), st));
+  int rc = launch_conv_tc(pl, st);
+  if (rc != B2Y_OK) return rc;
+  unsigned long long h[192];
+  B2Y_CUDA_CHECK(cudaMemcpyAsync(h, pl->trace, sizeof(h), cudaMemcpyDeviceToHost, st));
+  B2Y_CUDA_CHECK(cudaStreamSynchronize(st));
+  unsigned long long t0 = ~0ull;
+  for (int i = 0; i < 192; ++i)
+    if (h[i] && h[i] < t0) t0 = h[i];
+  const TcGeom &g = pl->g;
+  fprintf(stderr, "[b2y trace] grid %d ntiles %lld MB %d TH %d TW %d BN %d BK %d nkc %d sa %d resident %d o_stages %d fast %d smem %zu\n",
+          pl->grid, g.ntiles, g.MB, g.TH, g.TW, g.BN, g.BK, g.nkc, g.sa, g.resident, g.o_stages, g.fast_epi, pl->smem);
+  const char *names[3] = {"producer", "mma", "epilogue"};
+  for (int r = 0; r < 3; ++r) {
+    fprintf(stderr, "[b2y trace] %-8s", names[r]);
+    for (int i = 0; i < 64 && h[r * 64 + i]; ++i) fprintf(stderr, " %llu", h[r * 64 + i] - t0);
+    fprintf(stderr, "\n");
+  }
+  pl->g.trace = nullptr;
+  return B2Y_OK;
+}
 
 int launch_conv_tc(const ConvTcPlan *pl, cudaStream_t st) {
   b2y_launch(pl->fn, dim3(pl->grid), dim3(kNumThreads), pl->smem, st, pl->tmA, pl->tmB, pl->tmO, pl->g);

@@ -99,9 +99,10 @@ int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
   c.B = pl->B; c.H = bi->H; c.W = bi->W; c.Ho = bo->H; c.Wo = bo->W;
   c.cin = o.cin; c.cout = o.cout; c.cout_pad = o.cout_pad;
   c.kh = o.kh; c.kw = o.kw; c.sh = o.sh; c.sw = o.sw; c.ph = o.ph; c.pw = o.pw; c.act = o.act;
-  c.asym = 0; c.epi_mode = 0; c.a_off = 0; c.A = 0; c.nc = 0; c.det_stride = 0.f;
+  c.asym = 0; c.grouped = 0; c.epi_mode = 0; c.a_off = 0; c.A = 0; c.nc = 0; c.det_stride = 0.f;
   if (o.kind == B2Y_OP_CONV) {
     c.asym = o.ip[0];
+    c.grouped = o.ip[5];
     c.epi_mode = o.ip[1];
     c.a_off = o.ip[2];
     c.A = o.ip[3];
@@ -134,8 +135,18 @@ int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
   Resolver R{pl};
   const b2y_op &o = r.op;
   switch (o.kind) {
-    case B2Y_OP_CONV:
-      return r.impl == B2Y_IMPL_TCGEN05 ? launch_conv_tc(r.tc, st) : launch_conv_simt(r.cp, st);
+    case B2Y_OP_CONV: {
+      if (r.impl == B2Y_IMPL_TCGEN05) {
+        static const char *tr = getenv("B2Y_TRACE_OP");  // debug: comma-free single op index, eager launches only
+        if (tr && atoi(tr) == idx) {
+          cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+          cudaStreamIsCapturing(st, &cs);
+          if (cs == cudaStreamCaptureStatusNone) return conv_tc_plan_trace(r.tc, st);
+        }
+        return launch_conv_tc(r.tc, st);
+      }
+      return launch_conv_simt(r.cp, st);
+    }
     case B2Y_OP_DWCONV:
       return launch_dwconv(r.cp, st);
     case B2Y_OP_SPPF_POOL: {

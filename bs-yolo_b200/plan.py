@@ -193,16 +193,20 @@ class Plan:
                 op.ip, op.fp = (0, mode, a_off, self.A, self.nc), (float(stride),)
                 rows = 4 if mode == 1 else c2
                 op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + c2 * c1 * 2
-        elif (self.dw_dense and g == c1 == c2 and (kh, kw, sh, sw) == (3, 3, 1, 1) and c1 % 16 == 0 and c1 <= 128
+        elif (self.dw_dense and g == c1 == c2 and (kh, kw, sh, sw) == (3, 3, 1, 1) and c1 % 16 == 0 and c1 <= 256
               and x.c == c1 and self.conv_impl != A.IMPL_SIMT):
-            # Depthwise 3x3 on the tensor cores: the same implicit-GEMM kernel with a block-diagonal weight matrix
-            # (W[co][tap][ci] = w[co][tap] iff ci == co).  It wastes C x the MACs of a pipe that idles anyway on these
-            # memory-bound layers and inherits the TMA halo loads / TMA stores (measured: 2x the CUDA-core kernel).
+            # Depthwise 3x3 on the tensor cores: the same implicit-GEMM kernel with a diagonal weight matrix
+            # (W[co][tap][ci] = w[co][tap] iff ci == co) run in groups of 16 channels (ip[5] = 1): K-chunk kc only feeds
+            # accumulator columns [16kc, 16kc+16) with its 16x16 diagonal block, so the weights in shared memory stay
+            # tiny.  It wastes 16x the MACs of a pipe that idles anyway on these memory-bound layers and inherits the
+            # TMA halo loads / TMA stores (measured: 2-3x the CUDA-core kernel).  The SIMT twin and the emulator execute
+            # the same op with the full diagonal matrix.
             dense = torch.zeros(c2, c1, kh, kw)
             dense[torch.arange(c2), torch.arange(c1)] = w[:, 0]
             node = dict(n, g=1, weight=dense, bias=b)
             out = self.conv(node, x, dest, res, res_mode, out_dtype)
             op = self.ops[-1]
+            op.ip = (0, 0, 0, 0, 0, 1)
             op.flops = 2 * c2 * kh * kw * Ho * Wo
             op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + c2 * kh * kw * 2
             return out

@@ -41,7 +41,8 @@ enum b2y_op_kind {
   B2Y_OP_CONV = 1,      /* dense conv k{1,3} s{1,2} + bias (+SiLU) (+residual add|mul); conv.py:145-151.  ip[0]=1: 2x2
                            conv padded before only (the 3x3 s2 stem on the space-to-depth input); ip[1]: fused Detect
                            decode epilogue 1 = DFL+dist2bbox, 2 = class sigmoid (head.py:100-131) writing y (B,4+nc,A):
-                           ip[2] anchor offset, ip[3] A, ip[4] nc, fp[0] stride                                      */
+                           ip[2] anchor offset, ip[3] A, ip[4] nc, fp[0] stride; ip[5]=1: the weight matrix is diagonal
+                           (a depthwise 3x3 lowered to the tensor cores) and may be evaluated in groups of 16 channels   */
   B2Y_OP_DWCONV = 2,    /* depthwise kh x kw conv + bias (+SiLU) (+residual add); conv.py:224-229, MSCA.py:24-39  */
   B2Y_OP_SPPF_POOL = 4, /* three chained MaxPool2d(5,1,2) written to three channel slices; block.py:3145-3149   */
   B2Y_OP_RESAMPLE = 5,  /* channel-slice copy, optionally nearest 2x upsample (nn.Upsample, Concat conv.py:455)  */
