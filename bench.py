@@ -10,7 +10,8 @@ Workload at N=1: BASELINE.json configs[1] (stock yolo11n, batch 64, bf16, one B2
 (weak scaling: every rank runs its own batch, only the final detections are gathered -- no collective on the layer path).
 
 `value`  : whole-job images/s, frames already resident in HBM (device-timed, max over ranks).
-`e2e`    : same metric through DetectPipeline.predict_host: pinned host frames -> H2D -> pipeline -> D2H of detections.
+`e2e`    : same metric through DetectPipeline.predict_stream: pinned host frames -> H2D -> pipeline -> D2H of detections,
+            every step's copies inside the timed region (wall clock around K steps), copies overlapped with compute.
 `roofline`: the dominant kernel (the tcgen05 implicit-GEMM conv, summed over its launches of one step): algorithmic
             bytes / CUDA-event time against the measured HBM peak (MEASURED_PEAKS.json).
 `cpu_baseline`: the oracle port (torch fp32 CPU restatement of the reference path) timed on the host cores, rank 0 only.
@@ -36,7 +37,7 @@ MODEL_CFG = {  # workload name -> (arch model, per-GPU batch, imgsz)
     "bsyolo_n": ("bsyolo_n", 256, 640),
     "yolo11x": ("yolo11x", 32, 1280),
 }
-METRIC, UNIT = "images/sec @640x640 (yolo11n, synthetic seeded checkpoint)", "images/s"
+METRIC, UNIT = "images/sec @640x640", "images/s"  # BASELINE.json metric; the workload (model, batch) is named in config
 
 
 def make_ir(model):
@@ -270,14 +271,26 @@ def main():
     ms, wall = timed(step_resident, K)
     value = world * batch * K / (ms * 1e-3)
 
-    # ---- end to end through the public API with host buffers
-    def step_e2e(j):
-        out = pipe.predict_host(host[j % n_rot], gather=world > 1)
-        return out
+    # ---- end to end through the public streaming API with host buffers: every step copies its frames host->device
+    #      (pinned memory) and its detections device->host inside the timed region; copies overlap the previous compute
+    def run_e2e(steps):
+        n = 0
+        for dets_h, counts_h in pipe.predict_stream((host[j % n_rot] for j in range(steps)), gather=world > 1):
+            n += int(counts_h.shape[0])
+        return n
 
-    for j in range(3):
-        step_e2e(j)
-    ms_e2e, wall_e2e = timed(step_e2e, K)
+    run_e2e(3)
+    barrier()
+    t0 = time.perf_counter()
+    n_out = run_e2e(K)
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    assert n_out == K * world * batch
+    if world > 1:
+        t = torch.tensor([wall_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_e2e = float(t[0])
+    ms_e2e = wall_e2e
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * batch * K / (max(ms_e2e, wall_e2e) * 1e-3)
 
@@ -316,15 +329,29 @@ def main():
                            "bytes": o.bytes_alg * batch, "flops": o.flops * batch})
         dom_kind = "conv"
         dom = [L for L in layers if L["kind"] == dom_kind and L["impl"] == A.IMPL_TCGEN05] or [L for L in layers if L["kind"] == dom_kind]
-        t_dom = sum(L["ms"] for L in dom) * 1e-3
         b_dom = sum(L["bytes"] for L in dom)
         f_dom = sum(L["flops"] for L in dom)
+        # duration of the kernel's launches inside one step: the CUDA-graphed network time (events, median over K steps)
+        # times the kernel's share of the eager per-op times (an eager event pair adds launch overhead to every op, the
+        # share is insensitive to it)
+        share = sum(L["ms"] for L in dom) / max(sum(times), 1e-9)
+        t_dom = stages["network_graph_ms"] * 1e-3 * share
         ach = b_dom / t_dom / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
-                "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv), summed over its launches of one step" if dom and dom[0]["impl"] == 2 else "conv_simt_kernel",
-                "launches_per_step": len(dom), "avg_launch_ms": t_dom * 1e3 / max(len(dom), 1), "tflops": f_dom / t_dom / 1e12,
-                "share_of_step": (t_dom * 1e3) / max(sum(times), 1e-9), "peak_source": which,
-                "net_bytes_per_image": eng.plan.work_per_image()[1], "net_flops_per_image": eng.plan.work_per_image()[0]}
+        traffic = None
+        try:  # DRAM bytes of the same kernel's launches of one step, from the committed ncu launch list (profiles/)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("workload") == args.workload and tr.get("batch") == batch:
+                traffic = tr["conv_tc_dram_bytes_per_step"] / max(tr["conv_tc_launches_per_step"], 1)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+                "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv), all its launches of one step" if dom and dom[0]["impl"] == 2 else "conv_simt_kernel",
+                "launches_per_step": len(dom), "avg_launch_ms": t_dom * 1e3 / max(len(dom), 1),
+                "algorithmic_bytes_per_launch": b_dom / max(len(dom), 1), "tflops": f_dom / t_dom / 1e12,
+                "share_of_step": share * stages["network_graph_ms"] / (ms / K), "peak_source": which,
+                "net_bytes_per_image": eng.plan.work_per_image()[1], "net_flops_per_image": eng.plan.work_per_image()[0],
+                "network_roofline_frac": (sum(max(L["bytes"] / (hbm * 1e9), L["flops"] / (float(peaks.get("bf16_tflops", 1590.0)) * 1e12))
+                                              for L in layers) * 1e3) / stages["network_graph_ms"]}
         if args.layers_out:
             with open(args.layers_out, "w") as f:
                 json.dump({"batch": batch, "sum_ms": sum(times), "layers": layers}, f, indent=1)

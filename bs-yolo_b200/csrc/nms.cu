@@ -12,6 +12,8 @@
 //                                64x64 IoU bitmask built with warp ballots; stops at max_det (ops.py:297).
 // Every fp32 operation mirrors the reference's op order (xywh2xyxy ops.py:416-433, class offset boxes + cls*max_wh
 // ops.py:289-295); this file is compiled with -fmad=false so nothing is contracted into FMAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -19,6 +21,7 @@ constexpr int NT = 1024;
 constexpr int CH = 64;            // candidates per greedy step
 constexpr int MAX_KEPT = 1024;    // upper bound on max_det
 constexpr int SMEM_SORT = 8192;   // keys sorted in shared memory (64 KB); larger sets sort in global memory
+constexpr size_t SMEM_DYN = (size_t)SMEM_SORT * 8;
 
 struct ClassMask {
   uint32_t bits[32];  // nc <= 1024
@@ -73,9 +76,10 @@ struct Box { float x1, y1, x2, y2; };
 __device__ __forceinline__ bool iou_gt(const Box &k, float ka, const Box &c, float ca, float thr) {
   const float xx1 = fmaxf(k.x1, c.x1), yy1 = fmaxf(k.y1, c.y1);
   const float xx2 = fminf(k.x2, c.x2), yy2 = fminf(k.y2, c.y2);
-  float w = __fsub_rn(xx2, xx1), h = __fsub_rn(yy2, yy1);
-  w = w > 0.f ? w : 0.f;
-  h = h > 0.f ? h : 0.f;
+  const float w = __fsub_rn(xx2, xx1), h = __fsub_rn(yy2, yy1);
+  // disjoint boxes (the vast majority of pairs): torchvision clamps w, h to 0, so inter = 0 and IoU is 0 or NaN (0/0),
+  // neither of which exceeds a threshold >= 0 -- same decision without the division
+  if (!(w > 0.f && h > 0.f)) return false;
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ka, ca), inter));
   return ovr > thr;  // NaN (0/0 for zero-area duplicates) compares false: not suppressed, like the reference
@@ -163,10 +167,10 @@ __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
   bitonic_sort(keys, P);
   const int m = min(n, p.max_nms);
 
-  // ---- 3. blocked greedy suppression
   if (tid == 0) s_nk = 0;
   __syncthreads();
   const float *pb = p.pred + (size_t)b * (4 + p.nc) * p.A;
+  // ---- 3. blocked greedy suppression
   for (int c0 = 0; c0 < m; c0 += CH) {
     const int nc_chunk = min(CH, m - c0);
     const int nk = s_nk;
@@ -322,7 +326,7 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
   cudaStream_t st = (cudaStream_t)stream;
   b2y_launch(nms_score_kernel, dim3(dim3(ceil_div(A, 256), B)), dim3(256), 0, st, p);
   B2Y_LAUNCH_CHECK();
-  const size_t smem = SMEM_SORT * sizeof(unsigned long long);
+  const size_t smem = SMEM_DYN;
   static bool attr_set = false;
   if (!attr_set) {
     B2Y_CUDA_CHECK(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

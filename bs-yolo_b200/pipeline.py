@@ -31,9 +31,12 @@ class DetectPipeline:
     def launches_per_batch(self) -> int:
         return self.engine.n_launches + 1 + 2  # network ops + preprocess + NMS (score, select)
 
-    def __call__(self, src_u8: torch.Tensor, rescale: bool = False):
-        """src_u8: (B,h,w,3) uint8 BGR on this pipeline's device. Returns (dets (B,max_det,6), counts (B,)) on device."""
+    def __call__(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None):
+        """src_u8: (B,h,w,3) uint8 BGR on this pipeline's device. Returns (dets (B,max_det,6), counts (B,)) on device.
+        ``consumed`` (optional) is recorded as soon as the frames have been read (after the preprocess kernel)."""
         self.engine.preprocess(src_u8, auto=self.auto)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream(self.device))
         self.engine.forward()
         dets, counts = nms_raw(self.engine.y, self.conf, self.iou, self.max_det, self.classes, self.agnostic)
         if rescale:
@@ -57,3 +60,58 @@ class DetectPipeline:
         self._out[1].copy_(counts, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._out
+
+    def predict_stream(self, batches, rescale: bool = False, gather: bool = False):
+        """Streaming end-to-end API (the analogue of ``predict(..., stream=True)``, engine/predictor.py:217-296): an
+        iterable of pinned host uint8 batches (B,h,w,3) in, one host ``(dets, counts)`` pair per batch out, in order.
+        The host->device copy of batch i+1 runs on a second stream while batch i is computed, and the result of batch i
+        is handed out after batch i+1 has been enqueued, so neither the PCIe copy nor the host-side wait idles the GPU.
+        The yielded tensors are pinned buffers that stay valid until two more batches have been requested."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        stage, copied, consumed, done, outs = [None, None], [None, None], [None, None], [None, None], [None, None]
+        for k in range(2):
+            copied[k], consumed[k], done[k] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+
+        def upload(frames, k):
+            if stage[k] is None or stage[k].shape != frames.shape:
+                stage[k] = torch.empty(frames.shape, dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(cs):
+                cs.wait_event(consumed[k])  # the preprocess kernel that last read this slot has finished
+                stage[k].copy_(frames, non_blocking=True)
+                copied[k].record(cs)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        consumed[0].record(main)
+        consumed[1].record(main)
+        upload(nxt, 0)
+        i, pending = 0, None
+        while nxt is not None:
+            k = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(nxt, k ^ 1)  # overlaps the compute of batch i
+            main.wait_event(copied[k])
+            dets, counts = self(stage[k], rescale, consumed=consumed[k])
+            if gather:
+                from .shard import gather_detections
+                dets, counts = gather_detections(dets, counts)
+            if outs[k] is None or outs[k][0].shape != dets.shape:
+                outs[k] = (torch.empty(dets.shape, dtype=torch.float32).pin_memory(),
+                           torch.empty(counts.shape, dtype=torch.int32).pin_memory())
+            outs[k][0].copy_(dets, non_blocking=True)
+            outs[k][1].copy_(counts, non_blocking=True)
+            done[k].record(main)
+            if pending is not None:
+                done[pending].synchronize()
+                yield outs[pending]
+            pending = k
+            i += 1
+        done[pending].synchronize()
+        yield outs[pending]

@@ -319,6 +319,26 @@ def test_fused_decode_equals_decode_kernel(model):
     assert float((e.y.cpu()[:, 4:] - y_ref[:, 4:]).abs().max()) < 5e-2  # bf16 network vs fp32 oracle, scores
 
 
+def test_predict_stream_matches_synchronous_calls():
+    """The streaming end-to-end API (overlapped H2D copies, results one step behind) returns, per batch and in order,
+    exactly what the synchronous pipeline call returns."""
+    from bs_yolo_b200.pipeline import DetectPipeline
+    g = _graph("yolo11n")
+    pipe = DetectPipeline(g, 2, 160, (160, 160))
+    rng = np.random.default_rng(12)
+    host = [torch.from_numpy(rng.integers(0, 256, (2, 160, 160, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+    ref = []
+    for h in host:
+        d, c = pipe(h.cuda())
+        ref.append((d.cpu().clone(), c.cpu().clone()))
+    got = [(d.clone(), c.clone()) for d, c in pipe.predict_stream(iter(host))]
+    assert len(got) == len(ref) == 5
+    for (d, c), (dr, cr) in zip(got, ref):
+        assert torch.equal(c, cr) and torch.equal(d, dr)
+    assert int(sum(int(c.sum()) for _, c in ref)) > 0
+    assert list(pipe.predict_stream(iter([]))) == []
+
+
 def test_graph_replay_equals_eager():
     g = _graph("yolo11n")
     x = torch.from_numpy(np.random.default_rng(2).random((2, 3, 96, 96), dtype=np.float32))

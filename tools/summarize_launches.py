@@ -47,6 +47,13 @@ for i, o in enumerate(ops):
 lines += ["", "| kernel | launches | us | share | alg MB | dram MB | alg GB/s |", "|---|---|---|---|---|---|---|"]
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     lines.append(f"| {k} | {a[3]} | {a[0]:.0f} | {100*a[0]/tot:.1f}% | {a[1]/1e6:.0f} | {a[2]/1e6:.0f} | {(a[1]/a[0]/1e3 if a[0] else 0):.0f} |")
+conv = [(k, a) for k, a in agg.items() if "conv_tc_kernel" in k]
+traffic = {"workload": tab["workload"], "batch": tab["batch"], "source": f"ncu launch list {tag} (tools/ncu_capture.sh)",
+           "conv_tc_launches_per_step": sum(a[3] for _, a in conv), "conv_tc_dram_bytes_per_step": sum(a[2] for _, a in conv),
+           "conv_tc_alg_bytes_per_step": sum(a[1] for _, a in conv), "conv_tc_us_per_step_serialised": sum(a[0] for _, a in conv),
+           "all_kernels_us_per_step_serialised": tot}
+if len(sys.argv) > 3:
+    json.dump(traffic, open(sys.argv[3], "w"), indent=1)
 out = "\n".join(lines) + "\n"
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write(out)
