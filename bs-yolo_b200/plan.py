@@ -120,6 +120,8 @@ class Plan:
         # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
         self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
         self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
+        import os
+        self.head_per_sm = int(os.environ.get("B2Y_HEAD_PER_SM", "0"))
         self.bufs: list[BufSpec] = []
         self.ops: list[OpSpec] = []
         self.blob = WeightBlob()
@@ -388,6 +390,15 @@ class Plan:
         return dest
 
     def detect(self, n, xs):
+        first_op = len(self.ops)
+        self._detect(n, xs)
+        if self.head_per_sm:  # the 6 branches of the head are independent: cap their CTAs/SM so they can share the SMs
+            for op in self.ops[first_op:]:
+                if op.kind == A.OP_CONV:
+                    ip = tuple(op.ip) + (0,) * (8 - len(op.ip))
+                    op.ip = ip[:7] + (self.head_per_sm,)
+
+    def _detect(self, n, xs):
         nc = n["nc"]
         no = 64 + nc
         self.A = sum(x.H * x.W for x in xs)
