@@ -14,7 +14,7 @@ BF16, F32 = 0, 1
 (OP_CONV, OP_DWCONV, _OP_RESERVED3, OP_SPPF_POOL, OP_RESAMPLE, OP_ATTN, OP_ROWCOL_MEAN, OP_ELA_GATE, OP_ELA_APPLY, OP_GAP4,
  OP_MSCA_GATE, OP_WSUM4, OP_DECODE) = range(1, 14)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
-RES_NONE, RES_ADD, RES_MUL = 0, 1, 2
+RES_NONE, RES_ADD, RES_MUL, RES_PREADD_UP2 = 0, 1, 2, 3
 OP_NAMES = {1: "conv", 2: "dwconv", 4: "sppf_pool", 5: "resample", 6: "attn", 7: "rowcol_mean", 8: "ela_gate",
             9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode"}
 

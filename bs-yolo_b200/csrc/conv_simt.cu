@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvParams p) {
     const int co = co0 + j;
     if (co >= p.cout) break;
     float v = acc[j] + p.bias[co];
+    if (p.res_mode == B2Y_RES_PREADD_UP2)  // pre-activation add of the nearest-2x-upsampled half-resolution map
+      v += __bfloat162float(p.res[((size_t)(b * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * p.res_cs + co]);
     if (p.act) v = silu_f(v);
-    if (p.res_mode) {
+    if (p.res_mode == B2Y_RES_ADD || p.res_mode == B2Y_RES_MUL) {
       const float r = __bfloat162float(p.res[opix * p.res_cs + co]);
       v = (p.res_mode == B2Y_RES_ADD) ? v + r : v * r;
     }
@@ -327,6 +329,7 @@ static int launch_dw_strip(const ConvParams &p, cudaStream_t st) {
 
 int launch_dwconv(const ConvParams &p, cudaStream_t st) {
   B2Y_REQUIRE(p.cin == p.cout && !p.out_f32, B2Y_ERR_UNSUPPORTED, "depthwise conv needs cin == cout and bf16 output");
+  B2Y_REQUIRE(p.res_mode != B2Y_RES_PREADD_UP2, B2Y_ERR_UNSUPPORTED, "depthwise conv: upsampled pre-activation residual");
   auto aligned = [&](int v) {
     const uintptr_t m = (uintptr_t)v * 2 - 1;
     bool ok = (p.cout % v == 0) && (p.in_cs % v == 0) && (p.out_cs % v == 0) &&

@@ -467,7 +467,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         auto res_ptr = [&](int j, int c) -> const uint4 * {
           const int ho = ho0 + j * THq;
           if (!(col_ok && ho < g.Ho)) return nullptr;
-          return reinterpret_cast<const uint4 *>(g.res + (((size_t)tc.b * g.Ho + ho) * g.Wo + wo) * g.res_cs + n0 + c * 16);
+          size_t pix = ((size_t)tc.b * g.Ho + ho) * g.Wo + wo;
+          if (res_mode == B2Y_RES_PREADD_UP2) {  // half-resolution map: pixel (b, y/2, x/2) of the real (unflattened) image
+            const int rb = (int)(pix / (size_t)g.real_hw);
+            const int a = (int)(pix - (size_t)rb * g.real_hw);
+            const int y = a / g.real_w, x = a - y * g.real_w;
+            pix = ((size_t)rb * (g.real_hw >> 2)) + (size_t)(y >> 1) * (g.real_w >> 1) + (x >> 1);
+          }
+          return reinterpret_cast<const uint4 *>(g.res + pix * g.res_cs + n0 + c * 16);
         };
         uint4 rc[4];  // residual of the current item
         bool rc_ok = false;
@@ -500,6 +507,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         auto epi16 = [&](float(&v)[16], const int c, const uint32_t rowaddr, const uint32_t xr, const uint4 *r, const bool r_ok) {
           const int col = c * 16;
           const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0 + col);
+          if (res_mode == B2Y_RES_PREADD_UP2 && r_ok) {  // pre-activation: conv + upsampled half-resolution partial sum
+            float rf[16];
+            unpack8(r[0], rf);
+            unpack8(r[1], rf + 8);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] += rf[q];
+          }
           if (act) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -516,7 +530,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
             }
           }
-          if (r_ok) {
+          if (r_ok && res_mode != B2Y_RES_PREADD_UP2) {
             float rf[16];
             unpack8(r[0], rf);
             unpack8(r[1], rf + 8);
@@ -986,6 +1000,10 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
   if (p.epi_mode == 1 && p.cout != 64) return no("fused DFL decode needs 64 box channels");
   if (p.grouped && !(p.cin == p.cout && p.cout == p.cout_pad && p.cout <= 256 && !p.epi_mode && p.kh == 3 && p.sh == 1))
     return no("grouped (depthwise) mode needs a 3x3 s1 conv with cin == cout <= 256, multiple of 16");
+  if (p.res_mode == B2Y_RES_PREADD_UP2 &&
+      !(k1 && !p.out_f32 && !p.epi_mode && p.cout % 16 == 0 && p.res_cs % 8 == 0 && p.out_cs % 8 == 0 && p.Ho % 2 == 0 &&
+        p.Wo % 2 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0))
+    return no("upsampled pre-activation residual needs an aligned bf16 1x1 conv");
   if (p.cin % 16) return no("cin not a multiple of 16");
   if (p.cout_pad % 16) return no("cout_pad not a multiple of 16");
   if (p.in_cs % 8 || (reinterpret_cast<uintptr_t>(p.in) & 15)) return no("input view not 16-byte aligned");
@@ -1013,10 +1031,10 @@ int conv_tc_plan_create(const ConvParams &p_in, int device, const TcConfig &cfg,
     const long long npix = (long long)p_in.B * p_in.Ho * p_in.Wo;
     int wf = 128;
     while (wf > 1 && npix % wf) --wf;
+    g.real_hw = p_in.Ho * p_in.Wo;  // (also valid unflattened: pixel index = (b*Ho + ho)*Wo + wo either way)
+    g.real_w = p_in.Wo;
     if (wf >= 64 && npix / wf <= 65535) {
       g.flat = 1;
-      g.real_hw = p_in.Ho * p_in.Wo;
-      g.real_w = p_in.Wo;
       pf.B = 1;
       pf.H = pf.Ho = (int)(npix / wf);
       pf.W = pf.Wo = wf;

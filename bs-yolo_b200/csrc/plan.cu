@@ -91,7 +91,8 @@ int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
   if (o.res_mode) {
     const b2y_buf *br = R.buf(o.res);
     if (!R.ok) return B2Y_ERR_INVALID;
-    B2Y_REQUIRE(br->dtype == B2Y_BF16 && br->H == bo->H && br->W == bo->W && o.res_coff + o.cout <= br->C,
+    const int rs = (o.res_mode == B2Y_RES_PREADD_UP2) ? 2 : 1;  // half-resolution residual, upsampled on the fly
+    B2Y_REQUIRE(br->dtype == B2Y_BF16 && br->H * rs == bo->H && br->W * rs == bo->W && o.res_coff + o.cout <= br->C,
                 B2Y_ERR_INVALID, "op %d: residual view does not match the output", idx);
     c.res = reinterpret_cast<const bf16 *>(R.ptr(o.res, o.res_coff));
     c.res_cs = br->C;

@@ -111,7 +111,7 @@ class Plan:
     """Flat op list + buffers + packed weights for one (H, W) input size (batch is bound later)."""
 
     def __init__(self, ir: Node, H: int, W: int, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
-                 fuse_decode: bool = True, dw_dense: bool = True):
+                 fuse_decode: bool = True, dw_dense: bool = True, fold_upsample: bool = True):
         if H % 32 or W % 32:
             raise ValueError(f"input {H}x{W} must be a multiple of the max stride 32 (utils/checks.py:120-171)")
         self.ir, self.H, self.W = ir, H, W
@@ -119,8 +119,10 @@ class Plan:
         self.keep_fp32 = keep_fp32  # tests only: keep unrounded packed conv weights next to the bf16 blob
         # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
         self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
-        self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
         import os
+        self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
+        # Upsample + Concat + C3k2.cv1 -> half-resolution partial sum + pre-activation add (B2Y_FOLD_UPSAMPLE=0: A/B knob)
+        self.fold_upsample = fold_upsample and os.environ.get("B2Y_FOLD_UPSAMPLE", "1") != "0"
         self.head_per_sm = int(os.environ.get("B2Y_HEAD_PER_SM", "0"))
         self.bufs: list[BufSpec] = []
         self.ops: list[OpSpec] = []
@@ -138,9 +140,9 @@ class Plan:
 
     @classmethod
     def empty(cls, H: int, W: int, nc: int = 1, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
-              fuse_decode: bool = True, dw_dense: bool = True) -> "Plan":
+              fuse_decode: bool = True, dw_dense: bool = True, fold_upsample: bool = True) -> "Plan":
         """A plan with no ops (unit tests append single ops through the same lowering helpers)."""
-        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode, dw_dense)
+        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode, dw_dense, fold_upsample)
 
     # ------------------------------------------------------------------ buffers / views
     def new_buf(self, C, H, W, dtype=A.BF16, name="", exact=False) -> int:
@@ -288,10 +290,28 @@ class Plan:
         self.conv(n["cv2"], x, self.sub(z, c_, c_))
         return self.conv(n["cv3"], z, dest)
 
-    def c3k2(self, n, x, dest):
+    def c3k2(self, n, x, dest, up=None):
+        """``up`` = (low, skip, low_first): the block's input is Concat(Upsample2x(low), skip) (yaml head).  cv1 is a 1x1
+        conv, so cv1(cat(up(a), b)) = act(up(W_a a) + W_b b + bias): W_a a is computed at half resolution and added,
+        upsampled on the fly, before the activation of the conv over ``skip`` (RES_PREADD_UP2) -- the upsampled and the
+        concatenated tensors are never written."""
         c, nm = n["c"], len(n["m"])
-        y = self.full(self.new_buf((2 + nm) * c, x.H, x.W, name=n["name"] + ".cat"), (2 + nm) * c)
-        self.conv(n["cv1"], x, self.sub(y, 0, 2 * c))
+        if up is not None:
+            low, skip, low_first = up
+            Hy, Wy = skip.H, skip.W
+        else:
+            Hy, Wy = x.H, x.W
+        y = self.full(self.new_buf((2 + nm) * c, Hy, Wy, name=n["name"] + ".cat"), (2 + nm) * c)
+        if up is not None:
+            cv1 = n["cv1"]
+            w, b = cv1["weight"], cv1["bias"]
+            ca, cb = low.real, skip.real
+            assert cv1["k"] == (1, 1) and cv1["c1"] == ca + cb and cv1["c2"] == 2 * c
+            w_low, w_skip = (w[:, :ca], w[:, ca:]) if low_first else (w[:, cb:], w[:, :cb])
+            t = self.conv(dict(cv1, c1=ca, act="none", name=cv1["name"] + ".low"), low, wb=(w_low.contiguous(), torch.zeros_like(b)))
+            self.conv(dict(cv1, c1=cb), skip, self.sub(y, 0, 2 * c), res=t, res_mode=A.RES_PREADD_UP2, wb=(w_skip.contiguous(), b))
+        else:
+            self.conv(n["cv1"], x, self.sub(y, 0, 2 * c))
         for i, m in enumerate(n["m"]):
             self.inner(m, self.sub(y, (1 + i) * c, c), self.sub(y, (2 + i) * c, c))
         return self.conv(n["cv2"], y, dest)
@@ -459,11 +479,39 @@ class Plan:
             else:
                 raise NotImplementedError(ty)
             shape[i] = o
+        # Upsample -> Concat([up, skip]) -> C3k2 whose cv1 is 1x1, with no other consumers: folded into C3k2.cv1
+        consumers: dict[int, list[int]] = {}
+        for L in layers:
+            for ff in ([L["f"]] if isinstance(L["f"], int) else L["f"]):
+                if not (L["i"] == 0 and ff == -1):
+                    consumers.setdefault(src_of(L["i"], ff), []).append(L["i"])
+        upcat: dict[int, tuple[int, int, bool]] = {}  # C3k2 layer -> (low source layer, skip layer, low first in the cat)
+        folded: set[int] = set()
+        if self.fold_upsample and self.conv_impl != A.IMPL_SIMT:
+            for L in layers:
+                i, m = L["i"], L["module"]
+                if m["type"] != "C3k2" or not isinstance(L["f"], int) or m["cv1"]["k"] != (1, 1):
+                    continue
+                jc = src_of(i, L["f"])
+                Lc = layers[jc]
+                if Lc["module"]["type"] != "Concat" or consumers.get(jc) != [i] or len(Lc["f"]) != 2:
+                    continue
+                srcs = [src_of(jc, ff) for ff in Lc["f"]]
+                ups = [k for k in srcs if layers[k]["module"]["type"] == "Upsample" and consumers.get(k) == [jc]]
+                if len(ups) != 1:
+                    continue
+                ju = ups[0]
+                skip = srcs[1] if srcs[0] == ju else srcs[0]
+                cl, cs = shape[src_of(ju, layers[ju]["f"])][0], shape[skip][0]
+                if layers[skip]["module"]["type"] in ("Concat", "Upsample") or cl % 16 or cs % 16 or m["cv1"]["c2"] % 16:
+                    continue
+                upcat[i] = (src_of(ju, layers[ju]["f"]), skip, srcs[0] == ju)
+                folded.update((ju, jc))
         # concat destinations: the first Concat consumer of a layer gets a direct write
         dest: dict[int, View] = {}
         cat_view: dict[int, View] = {}
         for L in layers:
-            if L["module"]["type"] != "Concat":
+            if L["module"]["type"] != "Concat" or L["i"] in folded:
                 continue
             i = L["i"]
             C, Hc, Wc = shape[i]
@@ -484,6 +532,14 @@ class Plan:
             ty = m["type"]
             first = len(self.ops)
             d = dest.get(i)
+            if i in folded:  # Upsample / Concat folded into the consuming C3k2.cv1: nothing to launch, nothing to store
+                self.layer_op_range[i] = (first, first)
+                continue
+            if i in upcat:
+                lo, sk, low_first = upcat[i]
+                self.layer_out[i] = self.c3k2(m, None, d, up=(self.layer_out[lo], self.layer_out[sk], low_first))
+                self.layer_op_range[i] = (first, len(self.ops))
+                continue
             if ty == "Detect":
                 self.detect(m, [self.layer_out[src_of(i, ff)] for ff in f])
             elif ty == "Concat":

@@ -38,7 +38,7 @@ enum {
 enum b2y_dtype { B2Y_BF16 = 0, B2Y_F32 = 1 };
 
 enum b2y_op_kind {
-  B2Y_OP_CONV = 1,      /* dense conv k{1,3} s{1,2} + bias (+SiLU) (+residual add|mul); conv.py:145-151.  ip[0]=1: 2x2
+  B2Y_OP_CONV = 1,      /* dense conv k{1,3} s{1,2} + bias (+SiLU) (+residual, b2y_res_mode); conv.py:145-151.  ip[0]=1: 2x2
                            conv padded before only (the 3x3 s2 stem on the space-to-depth input); ip[1]: fused Detect
                            decode epilogue 1 = DFL+dist2bbox, 2 = class sigmoid (head.py:100-131) writing y (B,4+nc,A):
                            ip[2] anchor offset, ip[3] A, ip[4] nc, fp[0] stride; ip[5]=1: the weight matrix is diagonal
@@ -57,7 +57,14 @@ enum b2y_op_kind {
 };
 
 enum b2y_conv_impl { B2Y_IMPL_AUTO = 0, B2Y_IMPL_SIMT = 1, B2Y_IMPL_TCGEN05 = 2 };
-enum b2y_res_mode { B2Y_RES_NONE = 0, B2Y_RES_ADD = 1, B2Y_RES_MUL = 2 };
+enum b2y_res_mode {
+  B2Y_RES_NONE = 0,
+  B2Y_RES_ADD = 1,        /* out = act(conv) + res                                                            */
+  B2Y_RES_MUL = 2,        /* out = act(conv) * res                                                            */
+  B2Y_RES_PREADD_UP2 = 3  /* out = act(conv + nearest-2x-upsampled res): res is a half-resolution map.  A 1x1 conv over
+                             Concat(Upsample(a), b) (yaml head: nn.Upsample + Concat + C3k2.cv1) equals
+                             act(up(W_a a) + W_b b + bias), so neither the upsampled nor the concatenated tensor exists */
+};
 
 /* A buffer is one NHWC activation tensor (batch B is a plan property): B x H x W x C elements. */
 typedef struct {

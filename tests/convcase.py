@@ -23,6 +23,9 @@ CASES = {
     "k1_64_12_f32": dict(c1=64, c2=12, k=1, s=1, H=20, W=20, f32=True, act=False, out_total=76, out_off=64),
     "k1_mul_res": dict(c1=256, c2=256, k=1, s=1, H=20, W=20, res="mul", act=False),
     "k3_96_96_n": dict(c1=96, c2=96, k=3, s=1, H=24, W=40),
+    # Upsample + Concat folded into a 1x1 conv: pre-activation add of a half-resolution map (RES_PREADD_UP2)
+    "k1_up2_preadd": dict(c1=128, c2=64, k=1, s=1, H=40, W=40, res="up2", out_total=192, out_off=0),
+    "k1_up2_preadd_b": dict(c1=64, c2=128, k=1, s=1, H=20, W=28, res="up2", B=5),
     "k1_1536_768": dict(c1=1536, c2=768, k=1, s=1, H=16, W=16),
     "k3_768_768_s2": dict(c1=768, c2=768, k=3, s=2, H=16, W=16),
     # large enough tile counts for multi-block (MB > 1) tiles
@@ -54,7 +57,10 @@ def build_case(name: str, impl: int, seed: int = 0):
         ob = plan.new_buf(c["out_total"], Ho, Wo, odt, name="out")
         dest = View(ob, c["out_off"], c2, Ho, Wo)
     res, mode = None, A.RES_NONE
-    if c["res"]:
+    if c["res"] == "up2":
+        rb = plan.new_buf(c2, Ho // 2, Wo // 2, name="res_half")
+        res, mode = View(rb, 0, c2, Ho // 2, Wo // 2), A.RES_PREADD_UP2
+    elif c["res"]:
         rb = plan.new_buf(c2, Ho, Wo, name="res")
         res, mode = View(rb, 0, c2, Ho, Wo), (A.RES_ADD if c["res"] == "add" else A.RES_MUL)
     out = plan.conv(node, x, dest, res=res, res_mode=mode, out_dtype=odt, pad16=c["pad16"])

@@ -49,6 +49,13 @@ class PlanEmulator:
             getattr(self, "op_" + A.OP_NAMES[op.kind])(op)
 
     def _epilogue(self, op, y):
+        if op.res_mode == A.RES_PREADD_UP2:  # pre-activation add of the nearest-2x-upsampled half-resolution map
+            r = self.get(op.res).repeat_interleave(2, 1).repeat_interleave(2, 2)
+            y = y.clone()
+            y[..., :op.cout] = y[..., :op.cout] + r
+            y = F.silu(y) if op.act else y
+            self.put(op.out, y, op.cout)
+            return
         if op.act:
             y = F.silu(y)
         if op.res_mode:

@@ -79,8 +79,13 @@ def test_structure_and_alignment():
     assert (plan.bufs[plan.input_buf].C, plan.bufs[plan.input_buf].H) == (16, 320)
     assert plan.A == 8400 and plan.bufs[plan.y_buf].H == 84
     n_conv = sum(k in (A.OP_CONV, A.OP_DWCONV) for k in kinds)
-    assert n_conv == 88  # SURVEY C.1 lists 88 convs incl. DFL's (fused into decode here); pe is split per head (+1)
-    assert sum(k == A.OP_RESAMPLE for k in kinds) == 2  # only the two nearest-2x upsamples; every concat is fused away
+    # SURVEY C.1 lists 88 convs incl. DFL's (fused into decode here); pe is split per head (+1); the two Upsample+Concat
+    # pairs of the neck are folded into the consuming C3k2.cv1 as a half-resolution partial conv each (+2)
+    assert n_conv == 90
+    assert sum(k == A.OP_RESAMPLE for k in kinds) == 0  # every concat AND both nearest-2x upsamples are fused away
+    assert sum(o.res_mode == A.RES_PREADD_UP2 for o in plan.ops) == 2
+    plain = Plan(_graph("yolo11n"), 640, 640, fold_upsample=False)
+    assert sum(o.kind == A.OP_RESAMPLE for o in plain.ops) == 2 and len(plain.ops) == len(plan.ops)
     for o in plan.ops:
         if o.kind == A.OP_CONV:  # tensor-core path preconditions hold for every dense conv of yolo11n
             assert o.cin % 16 == 0 and o.cout_pad % 16 == 0 and o.ins[0].coff % 8 == 0, o.name
