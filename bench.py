@@ -233,13 +233,10 @@ def main():
     n_rot = 4  # rotate over 4 distinct input batches (4 x 78.6 MB > 126 MB L2); activations add ~GBs of traffic per step
     host = [torch.from_numpy(synth_frames(batch, imgsz, 100 + rank * 16 + j)).pin_memory() for j in range(n_rot)]
     devf = [h.to(dev) for h in host]
-    from bs_yolo_b200 import shard
-
     def step_resident(j):
-        dets, counts = pipe(devf[j % n_rot])
-        if world > 1:  # only the final detections cross GPUs (one all-gather of padded rows + counts)
-            dets, counts = shard.gather_detections(dets, counts)
-        return dets, counts
+        # pipelined submit: the NMS (and, multi-GPU, the all-gather of the padded detections -- the only data that crosses
+        # GPUs) of this batch runs on the post-process stream underneath the next batch's network
+        return pipe.submit(devf[j % n_rot], gather=world > 1)
 
     def barrier():
         if world > 1:

@@ -1,9 +1,15 @@
 """DetectPipeline: the public batch API of the B200 path -- uint8 BGR frames in, final detections out.
 
-One pipeline = one GPU = one CUDA-graphed network (Engine) + preprocess + NMS (+ optional scale_boxes), i.e. the
-device-side body of BasePredictor.stream_inference's hot loop (ultralytics/engine/predictor.py:241-266):
-preprocess -> inference -> postprocess.  `predict_host` is the end-to-end entry: pinned host frames are copied in,
-detections are copied back, with the copies double-buffered against compute on a second stream."""
+One pipeline = one GPU: preprocess + CUDA-graphed network + NMS (+ optional scale_boxes), i.e. the device-side body of
+BasePredictor.stream_inference's hot loop (ultralytics/engine/predictor.py:241-266): preprocess -> inference ->
+postprocess.  Batches are independent, so the pipeline is software-pipelined over two slots (two Engines = two activation
+workspaces and graphs): the post-process of batch i (NMS: one CTA per image, latency-bound, most SMs idle) runs on a second
+stream underneath the network of batch i+1, and -- in `predict_stream` -- so do the host<->device copies.
+
+    __call__(frames)        one batch, stream-synchronous semantics: the results are ready for the caller's stream
+    submit(frames)          one batch, pipelined: returns (dets, counts, event); the results are ready when `event` is
+    predict_stream(batches) end to end with host buffers: pinned frames in, pinned detections out, everything overlapped
+"""
 from __future__ import annotations
 
 import torch
@@ -15,58 +21,80 @@ from .ops import nms_raw, scale_boxes_batched
 
 class DetectPipeline:
     def __init__(self, ir, batch: int, imgsz=(640, 640), src_shape=(640, 640), device: int = 0, conf=0.25, iou=0.7,
-                 max_det=300, classes=None, agnostic=False, auto=True, use_graph=True, conv_impl=A.IMPL_AUTO):
+                 max_det=300, classes=None, agnostic=False, auto=True, use_graph=True, conv_impl=A.IMPL_AUTO, slots: int = 2):
         imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
         self.src_shape = tuple(src_shape)
         H, W, *_ = letterbox_geometry(self.src_shape, imgsz, auto)
         self.auto = auto
-        self.engine = Engine(ir, batch, H, W, device=device, use_graph=use_graph, conv_impl=conv_impl)
+        self.engines = [Engine(ir, batch, H, W, device=device, use_graph=use_graph, conv_impl=conv_impl)
+                        for _ in range(max(1, slots))]
+        self.engine = self.engines[0]
         self.device = self.engine.device
         self.B, self.H, self.W = batch, H, W
         self.conf, self.iou, self.max_det, self.classes, self.agnostic = conf, iou, max_det, classes, agnostic
+        self._slot = 0
+        self._post_stream = torch.cuda.Stream(self.device)
         self._copy_stream = None
-        self._staging = None
+        self._fwd_done = [torch.cuda.Event() for _ in self.engines]
+        self._post_done = [torch.cuda.Event() for _ in self.engines]
+        for e in self._post_done:
+            e.record(torch.cuda.current_stream(self.device))
 
     @property
     def launches_per_batch(self) -> int:
         return self.engine.n_launches + 1 + 2  # network ops + preprocess + NMS (score, select)
 
-    def __call__(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None):
-        """src_u8: (B,h,w,3) uint8 BGR on this pipeline's device. Returns (dets (B,max_det,6), counts (B,)) on device.
-        ``consumed`` (optional) is recorded as soon as the frames have been read (after the preprocess kernel)."""
-        self.engine.preprocess(src_u8, auto=self.auto)
+    def submit(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None,
+               gather: bool = False, host_out=None):
+        """Enqueue one batch: src_u8 (B,h,w,3) uint8 BGR on this device.  Preprocess + network go to the current stream,
+        NMS (+ scale_boxes, + the multi-GPU gather, + the device->host copy into `host_out`) to the post-process stream.
+        Returns (dets (B,max_det,6), counts (B,), event): the tensors are valid once `event` has completed; they must not
+        be consumed on another stream before that.  ``consumed`` is recorded when the frames have been read."""
+        k = self._slot
+        self._slot = (k + 1) % len(self.engines)
+        eng = self.engines[k]
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._post_done[k])  # the NMS that last read this slot's y has finished
+        eng.preprocess(src_u8, auto=self.auto)
         if consumed is not None:
-            consumed.record(torch.cuda.current_stream(self.device))
-        self.engine.forward()
-        dets, counts = nms_raw(self.engine.y, self.conf, self.iou, self.max_det, self.classes, self.agnostic)
-        if rescale:
-            scale_boxes_batched(dets, counts, (self.H, self.W), [self.src_shape] * self.B)
+            consumed.record(main)
+        eng.forward()
+        self._fwd_done[k].record(main)
+        post = self._post_stream
+        with torch.cuda.stream(post):
+            post.wait_event(self._fwd_done[k])
+            dets, counts = nms_raw(eng.y, self.conf, self.iou, self.max_det, self.classes, self.agnostic)
+            if rescale:
+                scale_boxes_batched(dets, counts, (self.H, self.W), [self.src_shape] * self.B)
+            if gather:
+                from .shard import gather_detections
+                dets, counts = gather_detections(dets, counts)
+            if host_out is not None:
+                host_out[0].copy_(dets, non_blocking=True)
+                host_out[1].copy_(counts, non_blocking=True)
+            self._post_done[k].record(post)
+        return dets, counts, self._post_done[k]
+
+    def __call__(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None):
+        """One batch with plain stream semantics: returns (dets (B,max_det,6), counts (B,)) usable on the current stream."""
+        dets, counts, ev = self.submit(src_u8, rescale, consumed)
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(ev)
+        dets.record_stream(main)
+        counts.record_stream(main)
         return dets, counts
 
     def predict_host(self, frames: torch.Tensor, rescale: bool = False, gather: bool = False):
-        """frames: pinned host uint8 (B,h,w,3). Returns host (dets, counts); blocks until they are valid.
-        gather=True (multi-GPU): every rank receives the detections of all ranks' shards (shard.gather_detections)."""
-        if self._staging is None:
-            self._staging = torch.empty(frames.shape, dtype=torch.uint8, device=self.device)
-        self._staging.copy_(frames, non_blocking=True)
-        dets, counts = self(self._staging, rescale)
-        if gather:
-            from .shard import gather_detections
-            dets, counts = gather_detections(dets, counts)
-        if getattr(self, "_out", None) is None or self._out[0].shape != dets.shape:
-            self._out = (torch.empty(dets.shape, dtype=torch.float32).pin_memory(),
-                         torch.empty(counts.shape, dtype=torch.int32).pin_memory())
-        self._out[0].copy_(dets, non_blocking=True)
-        self._out[1].copy_(counts, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._out
+        """frames: pinned host uint8 (B,h,w,3). Returns host (dets, counts); blocks until they are valid."""
+        return next(self.predict_stream(iter([frames]), rescale, gather))
 
     def predict_stream(self, batches, rescale: bool = False, gather: bool = False):
         """Streaming end-to-end API (the analogue of ``predict(..., stream=True)``, engine/predictor.py:217-296): an
         iterable of pinned host uint8 batches (B,h,w,3) in, one host ``(dets, counts)`` pair per batch out, in order.
-        The host->device copy of batch i+1 runs on a second stream while batch i is computed, and the result of batch i
-        is handed out after batch i+1 has been enqueued, so neither the PCIe copy nor the host-side wait idles the GPU.
-        The yielded tensors are pinned buffers that stay valid until two more batches have been requested."""
+        The host->device copy of batch i+1 and the NMS + device->host copy of batch i-1 run on their own streams beside
+        the network of batch i, and the result of batch i is handed out after batch i+1 has been enqueued, so neither
+        PCIe nor the host-side wait idles the GPU.  The yielded tensors are pinned buffers that stay valid until two more
+        batches have been requested.  gather=True (multi-GPU): every rank receives all ranks' detections."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
@@ -74,7 +102,7 @@ class DetectPipeline:
         cs = self._copy_stream
         stage, copied, consumed, done, outs = [None, None], [None, None], [None, None], [None, None], [None, None]
         for k in range(2):
-            copied[k], consumed[k], done[k] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            copied[k], consumed[k] = torch.cuda.Event(), torch.cuda.Event()
 
         def upload(frames, k):
             if stage[k] is None or stage[k].shape != frames.shape:
@@ -91,6 +119,10 @@ class DetectPipeline:
         consumed[0].record(main)
         consumed[1].record(main)
         upload(nxt, 0)
+        world = 1
+        if gather:
+            import torch.distributed as dist
+            world = dist.get_world_size()
         i, pending = 0, None
         while nxt is not None:
             k = i & 1
@@ -98,16 +130,10 @@ class DetectPipeline:
             if nxt is not None:
                 upload(nxt, k ^ 1)  # overlaps the compute of batch i
             main.wait_event(copied[k])
-            dets, counts = self(stage[k], rescale, consumed=consumed[k])
-            if gather:
-                from .shard import gather_detections
-                dets, counts = gather_detections(dets, counts)
-            if outs[k] is None or outs[k][0].shape != dets.shape:
-                outs[k] = (torch.empty(dets.shape, dtype=torch.float32).pin_memory(),
-                           torch.empty(counts.shape, dtype=torch.int32).pin_memory())
-            outs[k][0].copy_(dets, non_blocking=True)
-            outs[k][1].copy_(counts, non_blocking=True)
-            done[k].record(main)
+            if outs[k] is None:
+                outs[k] = (torch.empty(world * self.B, self.max_det, 6, dtype=torch.float32).pin_memory(),
+                           torch.empty(world * self.B, dtype=torch.int32).pin_memory())
+            _, _, done[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k])
             if pending is not None:
                 done[pending].synchronize()
                 yield outs[pending]
