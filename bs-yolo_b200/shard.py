@@ -78,3 +78,23 @@ def merge_prediction(dets: torch.Tensor, counts: torch.Tensor, origins: torch.Te
     cls = d[:, 5].to(torch.int64).clamp_(0, nc - 1)
     pred[0, 4:].scatter_(0, cls.unsqueeze(0), torch.where(valid, d[:, 4], torch.zeros_like(d[:, 4])).unsqueeze(0))
     return pred
+
+
+def sahi_predict(pipe, frame_u8: torch.Tensor, tile: int = 640, overlap: float = 0.0, iou: float | None = None):
+    """SAHI-style tiled inference of ONE frame on ONE GPU (BASELINE.json config 5; multi-GPU = tiles sharded by
+    `tile_owner`, detections gathered with `gather_detections`, then the same merge): slice the (H,W,3) uint8 BGR device
+    frame into `sahi_tiles`, run the tile batch through `pipe` (a DetectPipeline built for batch = number of tiles and
+    tile-sized sources), shift the boxes to frame coordinates and merge them with one global class-aware NMS (the same
+    kernel as the per-image NMS).  Returns (dets (max_det,6), count) on the device plus the per-tile results."""
+    from .ops import nms_raw
+
+    H, W = int(frame_u8.shape[0]), int(frame_u8.shape[1])
+    origins = sahi_tiles(H, W, tile, overlap)
+    if len(origins) != pipe.B:
+        raise ValueError(f"pipeline batch {pipe.B} != {len(origins)} tiles of a {H}x{W} frame")
+    tiles = torch.stack([frame_u8[y:y + tile, x:x + tile] for x, y in origins]).contiguous()
+    dets, counts = pipe(tiles)
+    org = torch.tensor(origins, dtype=torch.float32, device=dets.device)
+    pred = merge_prediction(dets, counts, org, pipe.engine.nc)
+    md, mc = nms_raw(pred, pipe.conf, pipe.iou if iou is None else iou, pipe.max_det)
+    return md[0], mc[0], (dets, counts, org)
