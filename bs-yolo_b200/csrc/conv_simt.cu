@@ -249,9 +249,16 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
-template <int KH, int KW>
+// WS: the KH*KW*4 weights of a thread do not fit the register file (7x7): they are staged in shared memory
+// ([tap][C] fp32) and read back as 16-byte broadcasts.
+template <int KH, int KW, bool WS>
 __global__ void __launch_bounds__(256, (KH * KW <= 9) ? 3 : 1) dwconv_strip_kernel(ConvParams p, int R, int nstrips) {
+  extern __shared__ float wsm_strip[];
   pdl_launch_dependents();
+  if (WS) {
+    for (int i = threadIdx.x; i < KH * KW * p.cout; i += blockDim.x) wsm_strip[i] = reinterpret_cast<const float *>(p.w)[i];
+    __syncthreads();
+  }
   const int cg = p.cout >> 2;
   const long long total = (long long)p.B * nstrips * p.Wo * cg;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,10 +269,12 @@ __global__ void __launch_bounds__(256, (KH * KW <= 9) ? 3 : 1) dwconv_strip_kern
   t /= p.Wo;
   const int strip = (int)(t % nstrips);
   const int b = (int)(t / nstrips);
-  float4 w[KH * KW];
+  float4 w[WS ? 1 : KH * KW];
   const float *wp = reinterpret_cast<const float *>(p.w) + c0;
+  if (!WS) {
 #pragma unroll
-  for (int i = 0; i < KH * KW; ++i) w[i] = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)i * p.cout));
+    for (int i = 0; i < KH * KW; ++i) w[i] = __ldg(reinterpret_cast<const float4 *>(wp + (size_t)i * p.cout));
+  }
   const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + c0));
   pdl_wait();  // weights are constants: only the activations depend on the preceding kernel
   const int ho0 = strip * R, ho1 = min(ho0 + R, p.Ho);
@@ -273,23 +282,37 @@ __global__ void __launch_bounds__(256, (KH * KW <= 9) ? 3 : 1) dwconv_strip_kern
 #pragma unroll
   for (int r = 0; r < KH; ++r) acc[r] = bias;
   const bf16 *img = p.in + (size_t)b * p.H * p.W * p.in_cs + c0;
-  for (int i = ho0 - p.ph; i < ho1 - p.ph + KH - 1; ++i) {
-    if (i >= 0 && i < p.H) {
-      const bf16 *row = img + (size_t)i * p.W * p.in_cs;
+  // input rows are fetched one iteration ahead (raw 8-byte pixels, zeros outside the map) so that the loads of row i+1
+  // are in flight while row i is being accumulated; the loop body itself is branch-free
+  auto load_row = [&](int i, uint2(&buf)[KW]) {
+    const bool row_in = (i >= 0 && i < p.H);
+    const bf16 *row = img + (size_t)(row_in ? i : 0) * p.W * p.in_cs;
 #pragma unroll
-      for (int s_ = 0; s_ < KW; ++s_) {
-        const int wi = wo - p.pw + s_;
-        if (wi < 0 || wi >= p.W) continue;
-        float x[4];
-        unpack4(__ldg(reinterpret_cast<const uint2 *>(row + (size_t)wi * p.in_cs)), x);
+    for (int s_ = 0; s_ < KW; ++s_) {
+      const int wi = wo - p.pw + s_;
+      buf[s_] = (row_in && wi >= 0 && wi < p.W) ? __ldg(reinterpret_cast<const uint2 *>(row + (size_t)wi * p.in_cs))
+                                                  : make_uint2(0u, 0u);
+    }
+  };
+  const int i_end = ho1 - p.ph + KH - 1;
+  uint2 nxt[KW];
+  load_row(ho0 - p.ph, nxt);
+  for (int i = ho0 - p.ph; i < i_end; ++i) {
+    uint2 cur[KW];
 #pragma unroll
-        for (int r = 0; r < KH; ++r) {
-          const float4 ww = w[r * KW + s_];
-          acc[r].x = fmaf(x[0], ww.x, acc[r].x);
-          acc[r].y = fmaf(x[1], ww.y, acc[r].y);
-          acc[r].z = fmaf(x[2], ww.z, acc[r].z);
-          acc[r].w = fmaf(x[3], ww.w, acc[r].w);
-        }
+    for (int s_ = 0; s_ < KW; ++s_) cur[s_] = nxt[s_];
+    if (i + 1 < i_end) load_row(i + 1, nxt);
+#pragma unroll
+    for (int s_ = 0; s_ < KW; ++s_) {
+      float x[4];
+      unpack4(cur[s_], x);
+#pragma unroll
+      for (int r = 0; r < KH; ++r) {
+        const float4 ww = WS ? *reinterpret_cast<const float4 *>(wsm_strip + (size_t)(r * KW + s_) * p.cout + c0) : w[r * KW + s_];
+        acc[r].x = fmaf(x[0], ww.x, acc[r].x);
+        acc[r].y = fmaf(x[1], ww.y, acc[r].y);
+        acc[r].z = fmaf(x[2], ww.z, acc[r].z);
+        acc[r].w = fmaf(x[3], ww.w, acc[r].w);
       }
     }
     const int ho = i + p.ph - (KH - 1);  // slot KH-1 is complete after input row i
@@ -314,7 +337,7 @@ __global__ void __launch_bounds__(256, (KH * KW <= 9) ? 3 : 1) dwconv_strip_kern
   }
 }
 
-template <int KH, int KW>
+template <int KH, int KW, bool WS = false>
 static int launch_dw_strip(const ConvParams &p, cudaStream_t st) {
   // strips of R output rows: long enough to amortise the weight loads and the KH-1 halo rows, short enough to fill the GPU
   const long long cols = (long long)p.B * p.Wo * (p.cout >> 2);
@@ -322,7 +345,10 @@ static int launch_dw_strip(const ConvParams &p, cudaStream_t st) {
   while (R > 2 && cols * ceil_div(p.Ho, R) < 148LL * 1536) R >>= 1;
   const int nstrips = ceil_div(p.Ho, R);
   const long long total = cols * nstrips;
-  b2y_launch(dwconv_strip_kernel<KH, KW>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p, R, nstrips);
+  const size_t smem = WS ? (size_t)KH * KW * p.cout * sizeof(float) : 0;
+  if (smem > 48 * 1024)
+    B2Y_CUDA_CHECK(cudaFuncSetAttribute(dwconv_strip_kernel<KH, KW, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  b2y_launch(dwconv_strip_kernel<KH, KW, WS>, dim3((unsigned)((total + 255) / 256)), dim3(256), smem, st, p, R, nstrips);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -346,6 +372,8 @@ int launch_dwconv(const ConvParams &p, cudaStream_t st) {
     if (p.kh == 7 && p.kw == 1) return launch_dw_strip<7, 1>(p, st);
     if (p.kh == 1 && p.kw == 11) return launch_dw_strip<1, 11>(p, st);
     if (p.kh == 11 && p.kw == 1) return launch_dw_strip<11, 1>(p, st);
+    const size_t wbytes = (size_t)p.kh * p.kw * p.cout * sizeof(float);
+    if (p.kh == 7 && p.kw == 7 && wbytes <= 64 * 1024) return launch_dw_strip<7, 7, true>(p, st);
   }
   const size_t wsmem = (size_t)(p.kh * p.kw + 1) * p.cout * sizeof(float);
   if (aligned(8) && wsmem <= 96 * 1024 && p.sh == p.sw) {

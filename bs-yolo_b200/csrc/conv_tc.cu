@@ -998,8 +998,8 @@ bool conv_tc_supported(const ConvParams &p, char *why, int why_len) {
   if (!(k1 || k3s1 || k3s2 || k2)) return no("kernel/stride/padding combination");
   if (p.epi_mode && !(k1 && p.out_f32 && p.res_mode == 0 && !p.act)) return no("fused decode needs a plain fp32 1x1 conv");
   if (p.epi_mode == 1 && p.cout != 64) return no("fused DFL decode needs 64 box channels");
-  if (p.grouped && !(p.cin == p.cout && p.cout == p.cout_pad && p.cout <= 256 && !p.epi_mode && p.kh == 3 && p.sh == 1))
-    return no("grouped (depthwise) mode needs a 3x3 s1 conv with cin == cout <= 256, multiple of 16");
+  if (p.grouped && !(p.cin == p.cout && p.cout == p.cout_pad && p.cout <= 256 && !p.epi_mode && p.kh == 3))
+    return no("grouped (depthwise) mode needs a 3x3 conv with cin == cout <= 256, multiple of 16");
   if (p.res_mode == B2Y_RES_PREADD_UP2 &&
       !(k1 && !p.out_f32 && !p.epi_mode && p.cout % 16 == 0 && p.res_cs % 8 == 0 && p.out_cs % 8 == 0 && p.Ho % 2 == 0 &&
         p.Wo % 2 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0))

@@ -197,8 +197,9 @@ class Plan:
                 op.ip, op.fp = (0, mode, a_off, self.A, self.nc), (float(stride),)
                 rows = 4 if mode == 1 else c2
                 op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + c2 * c1 * 2
-        elif (self.dw_dense and g == c1 == c2 and (kh, kw, sh, sw) == (3, 3, 1, 1) and c1 % 16 == 0 and c1 <= 256
-              and x.c == c1 and self.conv_impl != A.IMPL_SIMT):
+        elif (self.dw_dense and g == c1 == c2 and (kh, kw) == (3, 3) and (sh, sw) in ((1, 1), (2, 2)) and (ph, pw) == (1, 1)
+              and c1 % 16 == 0 and c1 <= 256 and x.c == c1 and self.conv_impl != A.IMPL_SIMT
+              and (sh == 1 or (x.H % 2 == 0 and x.W % 2 == 0))):
             # Depthwise 3x3 on the tensor cores: the same implicit-GEMM kernel with a diagonal weight matrix
             # (W[co][tap][ci] = w[co][tap] iff ci == co) run in groups of 16 channels (ip[5] = 1): K-chunk kc only feeds
             # accumulator columns [16kc, 16kc+16) with its 16x16 diagonal block, so the weights in shared memory stay
