@@ -476,28 +476,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           return reinterpret_cast<const uint4 *>(g.res + pix * g.res_cs + n0 + c * 16);
         };
-        uint4 rc[4];  // residual of the current item
-        bool rc_ok = false;
-        auto res_load = [&](int j, int c) {
-          const uint4 *rp = res_ptr(j, c);
-          rc_ok = rp != nullptr;
-          if (rc_ok) {
-            rc[0] = __ldg(rp);
-            rc[1] = __ldg(rp + 1);
-            if (c + 1 < c_hi) {
-              rc[2] = __ldg(rp + 2);
-              rc[3] = __ldg(rp + 3);
-            }
-          }
-        };
-        auto res_prefetch = [&](int j, int c) {  // next item: pull its rows into L1 without holding registers
+        uint4 rc[4];  // residual rows of the current item: rc[0..1] first chunk, rc[2..3] second chunk
+        bool rcA_ok = false, rcB_ok = false;
+        auto res_load1 = [&](int j, int c, uint4 *dst) -> bool {
           const uint4 *rp = res_ptr(j, c);
           if (rp) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
-            if (c + 1 < c_hi) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 2));
+            dst[0] = __ldg(rp);
+            dst[1] = __ldg(rp + 1);
           }
+          return rp != nullptr;
         };
-        if (res_mode && has_items) res_load(j_lo, c_lo);  // independent of the MMAs: in flight across the wait below
+        auto res_prefetch1 = [&](int j, int c) {  // next item: pull its rows into L1 without holding registers
+          const uint4 *rp = res_ptr(j, c);
+          if (rp) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+        };
+        // item = two 16-column chunks: (j, c) and (j, c+1) of one block, or -- 16-channel outputs -- block j and block
+        // j + j_step; B is absent at the ragged end
+        auto item_b = [&](int j, int c, int &jb, int &cb) -> bool {
+          if (by_block) { jb = j + j_step; cb = c; return jb < MBq; }
+          jb = j; cb = c + 1;
+          return cb < c_hi;
+        };
+        if (res_mode && has_items) {  // independent of the MMAs: in flight across the accumulator wait below
+          int jb, cb;
+          rcA_ok = res_load1(j_lo, c_lo, rc);
+          rcB_ok = item_b(j_lo, c_lo, jb, cb) && res_load1(jb, cb, rc + 2);
+        }
 
         mbar_wait(tfull0 + 8 * as, aphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -546,22 +550,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         };
 
-        for (int j = j_lo; j < MBq && has_items; j += j_step) {
-          const uint32_t rowoff = (rr0 + (uint32_t)j * blk_out_rows) * orb;
-          const uint32_t xr = ((rowoff >> 7) & sw_mask) << 4;
-          const uint32_t rowaddr = o_stage + rowoff;
+        const int j_inc = by_block ? 2 * j_step : j_step;
+        for (int j = j_lo; j < MBq && has_items; j += j_inc) {
           for (int c = c_lo; c < c_hi; c += 2) {
-            const bool two = c + 1 < c_hi;  // warp-uniform
-            const bool last = (j + j_step >= MBq) && (c + 2 >= c_hi);
+            int jb, cb;
+            const bool two = item_b(j, c, jb, cb);  // warp-uniform
+            const bool last = (j + j_inc >= MBq) && (c + 2 >= c_hi);
+            const bool first = (j == j_lo) && (c == c_lo);
+            const uint32_t rowoffA = (rr0 + (uint32_t)j * blk_out_rows) * orb;
+            const uint32_t rowoffB = (rr0 + (uint32_t)jb * blk_out_rows) * orb;
             float va[16], vb[16];
             const uint32_t ta = taddr + (uint32_t)(j * BNq + c * 16);
-            if (two) tmem_ld32_issue(ta, va, vb);
-            else tmem_ld16_issue(ta, va);
-            const bool first = (j == j_lo) && (c == c_lo);
-            const int jn = (c + 2 < c_hi) ? j : j + j_step, cn = (c + 2 < c_hi) ? c + 2 : c_lo;  // next item
+            if (two && !by_block) tmem_ld32_issue(ta, va, vb);
+            else {
+              tmem_ld16_issue(ta, va);
+              if (two) tmem_ld16_issue(taddr + (uint32_t)(jb * BNq + cb * 16), vb);
+            }
             if (res_mode) {
-              if (!first) res_load(j, c);           // (the first item's rows were requested before the accumulator wait)
-              if (!last) res_prefetch(jn, cn);
+              if (!first) {  // (the first item's rows were requested before the accumulator wait)
+                rcA_ok = res_load1(j, c, rc);
+                rcB_ok = two && res_load1(jb, cb, rc + 2);
+              }
+              if (!last) {
+                const int jn = (c + 2 < c_hi) ? j : j + j_inc, cn = (c + 2 < c_hi) ? c + 2 : c_lo;  // next item
+                int jnb, cnb;
+                res_prefetch1(jn, cn);
+                if (item_b(jn, cn, jnb, cnb)) res_prefetch1(jnb, cnb);
+              }
             }
             if (!reclaimed) {
               // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
@@ -580,8 +595,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_arrive(tempty0 + 8 * as);  // last load of this tile landed: the MMA warp may overwrite the stage
               released = true;
             }
-            epi16(va, c, rowaddr, xr, rc, res_mode && rc_ok);
-            if (two) epi16(vb, c + 1, rowaddr, xr, rc + 2, res_mode && rc_ok);
+            epi16(va, c, o_stage + rowoffA, ((rowoffA >> 7) & sw_mask) << 4, rc, res_mode && rcA_ok);
+            if (two) epi16(vb, cb, o_stage + rowoffB, ((rowoffB >> 7) & sw_mask) << 4, rc + 2, res_mode && rcB_ok);
           }
         }
         if (!reclaimed) {  // a warp without items still takes part in the barrier protocol
@@ -1203,12 +1218,6 @@ int conv_tc_plan_create(const ConvParams &p_in, int device, const TcConfig &cfg,
     g.vec_ok = ok ? 1 : 0;
   }
   g.fast_epi = (g.tma_out && !g.epi_mode && p.cout % 16 == 0 && (!p.res_mode || g.vec_ok)) ? 1 : 0;
-  {  // timing experiments only (results are wrong with either): which pipe bounds a layer?
-    static const char *na = getenv("B2Y_DEBUG_NOACT"), *ns = getenv("B2Y_DEBUG_NOSHIFT");
-    if (na && na[0] == '1') g.act = 0;
-    if (ns && ns[0] == '1')
-      for (int t = 0; t < 9; ++t) g.tap_off16[t] = 0;
-  }
 
   const CUtensorMapSwizzle sw = (g.row_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : (g.row_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B

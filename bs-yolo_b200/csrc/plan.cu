@@ -533,9 +533,7 @@ extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
     if (verbose)
       fprintf(stderr, "[b2y autotune] op %3d %dx%d s%d cin %4d cout %4d map %dx%d:", op_index, r.cp.kh, r.cp.kw, r.cp.sh,
               r.cp.cin, r.cp.cout, r.cp.Ho, r.cp.Wo);
-    // ip[7] > 0 caps the co-resident CTAs per SM: parallel branches (Detect levels) leave SM slots to each other
-    const int max_per_sm = (r.op.ip[7] > 0 && r.op.ip[7] < 3) ? r.op.ip[7] : 3;
-    for (int per_sm = 1; per_sm <= max_per_sm; ++per_sm)
+    for (int per_sm = 1; per_sm <= 3; ++per_sm)
       for (int mi = 0; mi < 3; ++mi) {
         ConvTcPlan *cand = nullptr;
         if (conv_tc_plan_create(r.cp, pl->device, TcConfig{mbs[mi], per_sm}, &cand) != B2Y_OK) continue;

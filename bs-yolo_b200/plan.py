@@ -123,7 +123,6 @@ class Plan:
         self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
         # Upsample + Concat + C3k2.cv1 -> half-resolution partial sum + pre-activation add (B2Y_FOLD_UPSAMPLE=0: A/B knob)
         self.fold_upsample = fold_upsample and os.environ.get("B2Y_FOLD_UPSAMPLE", "1") != "0"
-        self.head_per_sm = int(os.environ.get("B2Y_HEAD_PER_SM", "0"))
         self.bufs: list[BufSpec] = []
         self.ops: list[OpSpec] = []
         self.blob = WeightBlob()
@@ -411,15 +410,6 @@ class Plan:
         return dest
 
     def detect(self, n, xs):
-        first_op = len(self.ops)
-        self._detect(n, xs)
-        if self.head_per_sm:  # the 6 branches of the head are independent: cap their CTAs/SM so they can share the SMs
-            for op in self.ops[first_op:]:
-                if op.kind == A.OP_CONV:
-                    ip = tuple(op.ip) + (0,) * (8 - len(op.ip))
-                    op.ip = ip[:7] + (self.head_per_sm,)
-
-    def _detect(self, n, xs):
         nc = n["nc"]
         no = 64 + nc
         self.A = sum(x.H * x.W for x in xs)
