@@ -25,7 +25,9 @@ def _stream(dev) -> int:
 
 
 def _workspace(dev, nbytes: int) -> torch.Tensor:
-    key = (dev.index,)
+    # one scratch buffer per (device, stream): NMS calls on different streams (the pipeline's post-process stream beside a
+    # caller's own stream) must not share slot scores / sort keys
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
