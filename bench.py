@@ -236,7 +236,7 @@ def main():
     def step_resident(j):
         # pipelined submit: the NMS (and, multi-GPU, the all-gather of the padded detections -- the only data that crosses
         # GPUs) of this batch runs on the post-process stream underneath the next batch's network
-        return pipe.submit(devf[j % n_rot], gather=world > 1)
+        return pipe.submit(devf[j % n_rot], gather=world > 1, src_ready=True)  # frames are resident before the timed region
 
     def barrier():
         if world > 1:

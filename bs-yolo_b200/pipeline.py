@@ -34,10 +34,12 @@ class DetectPipeline:
         self.conf, self.iou, self.max_det, self.classes, self.agnostic = conf, iou, max_det, classes, agnostic
         self._slot = 0
         self._post_stream = torch.cuda.Stream(self.device)
+        self._pre_stream = torch.cuda.Stream(self.device)
         self._copy_stream = None
         self._fwd_done = [torch.cuda.Event() for _ in self.engines]
+        self._pre_done = [torch.cuda.Event() for _ in self.engines]
         self._post_done = [torch.cuda.Event() for _ in self.engines]
-        for e in self._post_done:
+        for e in self._post_done + self._fwd_done:
             e.record(torch.cuda.current_stream(self.device))
 
     @property
@@ -45,19 +47,33 @@ class DetectPipeline:
         return self.engine.n_launches + 1 + 2  # network ops + preprocess + NMS (score, select)
 
     def submit(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None,
-               gather: bool = False, host_out=None):
-        """Enqueue one batch: src_u8 (B,h,w,3) uint8 BGR on this device.  Preprocess + network go to the current stream,
-        NMS (+ scale_boxes, + the multi-GPU gather, + the device->host copy into `host_out`) to the post-process stream.
+               gather: bool = False, host_out=None, src_ready=None):
+        """Enqueue one batch: src_u8 (B,h,w,3) uint8 BGR on this device.  The network goes to the current stream; the
+        preprocess kernel runs on its own stream (it only needs the frames and this slot's input buffer, so it overlaps the
+        previous batch's network), NMS (+ scale_boxes, + the multi-GPU gather, + the device->host copy into `host_out`) on
+        the post-process stream.  `src_ready`: an event after which the frames are complete, or True if they already are
+        (resident inputs); None (default) orders the preprocess after everything enqueued on the current stream so far.
         Returns (dets (B,max_det,6), counts (B,), event): the tensors are valid once `event` has completed; they must not
         be consumed on another stream before that.  ``consumed`` is recorded when the frames have been read."""
         k = self._slot
         self._slot = (k + 1) % len(self.engines)
         eng = self.engines[k]
         main = torch.cuda.current_stream(self.device)
+        pre = self._pre_stream
+        if src_ready is None:
+            src_ready = torch.cuda.Event()
+            src_ready.record(main)
+        with torch.cuda.stream(pre):
+            if src_ready is not True:
+                pre.wait_event(src_ready)
+            pre.wait_event(self._fwd_done[k])  # the network that last read this slot's input buffer has finished
+            src_u8.record_stream(pre)            # (allocator: the frames are read on this stream)
+            eng.preprocess(src_u8, auto=self.auto)
+            self._pre_done[k].record(pre)
+            if consumed is not None:
+                consumed.record(pre)
+        main.wait_event(self._pre_done[k])
         main.wait_event(self._post_done[k])  # the NMS that last read this slot's y has finished
-        eng.preprocess(src_u8, auto=self.auto)
-        if consumed is not None:
-            consumed.record(main)
         eng.forward()
         self._fwd_done[k].record(main)
         post = self._post_stream
@@ -129,11 +145,11 @@ class DetectPipeline:
             nxt = next(it, None)
             if nxt is not None:
                 upload(nxt, k ^ 1)  # overlaps the compute of batch i
-            main.wait_event(copied[k])
             if outs[k] is None:
                 outs[k] = (torch.empty(world * self.B, self.max_det, 6, dtype=torch.float32).pin_memory(),
                            torch.empty(world * self.B, dtype=torch.int32).pin_memory())
-            _, _, done[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k])
+            _, _, done[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k],
+                                        src_ready=copied[k])
             if pending is not None:
                 done[pending].synchronize()
                 yield outs[pending]
