@@ -140,6 +140,20 @@ void conv_tc_plan_destroy(ConvTcPlan *p);
 int launch_conv_tc(const ConvTcPlan *p, cudaStream_t st);
 int conv_tc_plan_trace(ConvTcPlan *p, cudaStream_t st);  // debug: one traced launch, timeline printed to stderr
 
+// fused Bottleneck (two chained 3x3 convs + residual) on the tensor cores, conv_pair.cu
+struct PairParams {
+  const bf16 *in; int in_cs;
+  void *out; int out_cs;
+  const void *w1, *w2;        // bf16 [chid][9*cin], [cout][9*chid]
+  const float *b1, *b2;       // fp32 [chid], [cout]
+  int B, H, W, cin, chid, cout, add;
+};
+struct ConvPairPlan;
+bool conv_pair_supported(const PairParams &p, char *why, int why_len);
+int conv_pair_plan_create(const PairParams &p, int device, ConvPairPlan **out);
+void conv_pair_plan_destroy(ConvPairPlan *p);
+int launch_conv_pair(const ConvPairPlan *p, cudaStream_t st);
+
 int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, cudaStream_t st);
 int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, int scale,
                     cudaStream_t st);

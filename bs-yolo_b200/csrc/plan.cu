@@ -37,6 +37,7 @@ struct ResolvedOp {
   b2y_op op;
   ConvParams cp;
   ConvTcPlan *tc = nullptr;
+  ConvPairPlan *pair = nullptr;
   int impl = 0;
 };
 
@@ -134,10 +135,34 @@ int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
   return B2Y_OK;
 }
 
+int resolve_pair(b2y_plan *pl, ResolvedOp &r, int idx, PairParams &q) {
+  Resolver R{pl};
+  const b2y_op &o = r.op;
+  const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+  if (!R.ok) return B2Y_ERR_INVALID;
+  B2Y_REQUIRE(bi->dtype == B2Y_BF16 && bo->dtype == B2Y_BF16 && bi->H == bo->H && bi->W == bo->W &&
+                  o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C,
+              B2Y_ERR_INVALID, "op %d: fused Bottleneck views", idx);
+  q.in = reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0]));
+  q.in_cs = bi->C;
+  q.out = R.ptr(o.out, o.out_coff);
+  q.out_cs = bo->C;
+  q.w1 = R.wptr(o.w_off);
+  q.b1 = reinterpret_cast<const float *>(R.wptr(o.b_off));
+  q.w2 = R.wptr(o.p_off[0]);
+  q.b2 = reinterpret_cast<const float *>(R.wptr(o.p_off[1]));
+  B2Y_REQUIRE(q.w1 && q.b1 && q.w2 && q.b2, B2Y_ERR_INVALID, "op %d: fused Bottleneck needs both weight sets", idx);
+  q.B = pl->B; q.H = bi->H; q.W = bi->W;
+  q.cin = o.cin; q.chid = o.ip[0]; q.cout = o.cout; q.add = o.ip[1];
+  return B2Y_OK;
+}
+
 int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
   Resolver R{pl};
   const b2y_op &o = r.op;
   switch (o.kind) {
+    case B2Y_OP_CONV_PAIR:
+      return launch_conv_pair(r.pair, st);
     case B2Y_OP_CONV: {
       if (r.impl == B2Y_IMPL_TCGEN05) {
         static const char *tr = getenv("B2Y_TRACE_OP");  // debug: comma-free single op index, eager launches only
@@ -276,7 +301,13 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
     ResolvedOp &r = pl->ops[i];
     r.op = ops[i];
     const int k = r.op.kind;
-    if (k == B2Y_OP_CONV || k == B2Y_OP_DWCONV) {
+    if (k == B2Y_OP_CONV_PAIR) {
+      PairParams q;
+      rc = resolve_pair(pl, r, i, q);
+      if (rc != B2Y_OK) break;
+      rc = conv_pair_plan_create(q, device, &r.pair);
+      r.impl = B2Y_IMPL_TCGEN05;
+    } else if (k == B2Y_OP_CONV || k == B2Y_OP_DWCONV) {
       rc = resolve_conv(pl, r, i);
       if (rc != B2Y_OK) break;
       if (k == B2Y_OP_CONV) {
@@ -306,8 +337,10 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
 
 extern "C" int b2y_plan_destroy(b2y_plan *pl) {
   if (!pl) return B2Y_OK;
-  for (auto &r : pl->ops)
+  for (auto &r : pl->ops) {
     if (r.tc) conv_tc_plan_destroy(r.tc);
+    if (r.pair) conv_pair_plan_destroy(r.pair);
+  }
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   if (pl->graph) cudaGraphDestroy(pl->graph);
   delete pl;
@@ -353,6 +386,11 @@ void op_regions(const b2y_plan *pl, const ResolvedOp &r, std::vector<Region> &ou
     } else {
       out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
     }
+    return;
+  }
+  if (o.kind == B2Y_OP_CONV_PAIR) {
+    out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
+    out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
     return;
   }
   if (o.kind == B2Y_OP_SPPF_POOL) {

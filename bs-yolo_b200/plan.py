@@ -111,7 +111,7 @@ class Plan:
     """Flat op list + buffers + packed weights for one (H, W) input size (batch is bound later)."""
 
     def __init__(self, ir: Node, H: int, W: int, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
-                 fuse_decode: bool = True, dw_dense: bool = True, fold_upsample: bool = True):
+                 fuse_decode: bool = True, dw_dense: bool = True, fold_upsample: bool = True, fuse_pairs: bool = True):
         if H % 32 or W % 32:
             raise ValueError(f"input {H}x{W} must be a multiple of the max stride 32 (utils/checks.py:120-171)")
         self.ir, self.H, self.W = ir, H, W
@@ -120,6 +120,7 @@ class Plan:
         # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
         self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
         import os
+        self.fuse_pairs = fuse_pairs and os.environ.get("B2Y_FUSE_PAIRS", "1") != "0"  # thin Bottlenecks as one kernel
         self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
         # Upsample + Concat + C3k2.cv1 -> half-resolution partial sum + pre-activation add (B2Y_FOLD_UPSAMPLE=0: A/B knob)
         self.fold_upsample = fold_upsample and os.environ.get("B2Y_FOLD_UPSAMPLE", "1") != "0"
@@ -139,9 +140,9 @@ class Plan:
 
     @classmethod
     def empty(cls, H: int, W: int, nc: int = 1, conv_impl: int = A.IMPL_AUTO, keep_fp32: bool = False,
-              fuse_decode: bool = True, dw_dense: bool = True, fold_upsample: bool = True) -> "Plan":
+              fuse_decode: bool = True, dw_dense: bool = True, fold_upsample: bool = True, fuse_pairs: bool = True) -> "Plan":
         """A plan with no ops (unit tests append single ops through the same lowering helpers)."""
-        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode, dw_dense, fold_upsample)
+        return cls(dict(nc=nc, layers=[]), H, W, conv_impl, keep_fp32, fuse_decode, dw_dense, fold_upsample, fuse_pairs)
 
     # ------------------------------------------------------------------ buffers / views
     def new_buf(self, C, H, W, dtype=A.BF16, name="", exact=False) -> int:
@@ -264,8 +265,36 @@ class Plan:
 
     # ------------------------------------------------------------------ blocks
     def bottleneck(self, n, x, dest):
-        t = self.conv(n["cv1"], x, pad16=True)
-        return self.conv(n["cv2"], t, dest, res=x if n["add"] else None, res_mode=A.RES_ADD if n["add"] else A.RES_NONE)
+        """Bottleneck (block.py:3405-3419).  The thin ones -- c1 == c2 in {16,32,64}, two 3x3 s1 convs, residual -- run as
+        ONE kernel (OP_CONV_PAIR): the hidden map stays in shared memory, the residual is read back from the input tile."""
+        cv1, cv2 = n["cv1"], n["cv2"]
+        chid = _r(cv1["c2"], 16)
+        if (self.fuse_pairs and self.conv_impl != A.IMPL_SIMT and n["add"] and x.real == x.c == cv2["c2"] and x.c in (16, 32, 64)
+                and chid in (16, 32, 64) and (x.c // 16, chid // 16) in ((1, 1), (2, 1), (2, 2), (4, 2), (4, 4))
+                and all(cv[k] == v for cv in (cv1, cv2) for k, v in (("k", (3, 3)), ("s", (1, 1)), ("p", (1, 1)), ("g", 1), ("act", "silu")))
+                and A.lib().b2y_conv_pair_fits(x.c, chid, 64, x.H, x.W)):  # (the fit does not depend on the batch beyond tile counts)
+            c1, c2 = x.c, cv2["c2"]
+            if dest is None:
+                dest = self.full(self.new_buf(c2, x.H, x.W, name=n["name"]), c2)
+            assert dest.c == c2 and (dest.H, dest.W) == (x.H, x.W)
+            w1 = torch.zeros(chid, 9, c1)
+            w1[:cv1["c2"]] = cv1["weight"].permute(0, 2, 3, 1).reshape(cv1["c2"], 9, c1)
+            b1 = torch.zeros(chid)
+            b1[:cv1["c2"]] = cv1["bias"]
+            w2 = torch.zeros(c2, 9, chid)
+            w2[:, :, :cv1["c2"]] = cv2["weight"].permute(0, 2, 3, 1).reshape(c2, 9, cv1["c2"])
+            op = OpSpec(A.OP_CONV_PAIR, n["name"], [x], dest, None, A.RES_NONE, c1, c2, c2, (3, 3), (1, 1), (1, 1), 1,
+                        A.IMPL_TCGEN05, self.blob.add(_bf16_bits(w1.reshape(chid, -1))), self.blob.add(b1.numpy().astype(np.float32)),
+                        p_off=(self.blob.add(_bf16_bits(w2.reshape(c2, -1))), self.blob.add(cv2["bias"].numpy().astype(np.float32)), -1, -1),
+                        ip=(chid, 1))
+            if self.keep_fp32:
+                op.w_fp32 = (w1.reshape(chid, -1).clone(), w2.reshape(c2, -1).clone())
+            op.flops = 2 * 9 * x.H * x.W * (cv1["c2"] * c1 + c2 * cv1["c2"])
+            op.bytes_alg = (c1 + c2) * x.H * x.W * 2 + 9 * (cv1["c2"] * c1 + c2 * cv1["c2"]) * 2
+            self.ops.append(op)
+            return dest
+        t = self.conv(cv1, x, pad16=True)
+        return self.conv(cv2, t, dest, res=x if n["add"] else None, res_mode=A.RES_ADD if n["add"] else A.RES_NONE)
 
     def pmsfa(self, n, x, dest):
         c = n["c"]

@@ -88,3 +88,47 @@ def run_case(name: str, impl: int, B: int | None = None, seed: int = 0, device=0
     got = eng.buffer(out.buf).float().cpu()
     ref = emu.bufs[out.buf]
     return got, ref, eng.op_impl(0)
+
+
+# ---- fused Bottleneck (OP_CONV_PAIR) cases: name -> (c, hidden, H, W, B)
+PAIR_CASES = {
+    "pair_16_8_160": (16, 8, 160, 160, 4),
+    "pair_32_16_80": (32, 16, 80, 80, 3),
+    "pair_64_32_40": (64, 32, 40, 40, 5),
+    "pair_32_32_40_odd": (32, 32, 37, 53, 3),
+    "pair_16_16_small": (16, 16, 12, 20, 2),
+    "pair_64_32_20": (64, 32, 20, 20, 9),
+}
+
+
+def run_pair_case(name: str, device=0):
+    """Fused Bottleneck on the GPU vs the emulator (bf16 storage of the hidden map emulated); returns (gpu, ref)."""
+    from bs_yolo_b200.engine import Engine
+    from plan_emulator import PlanEmulator
+
+    c, hid, H, W, B = PAIR_CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+
+    def cnode(nm, c1, c2):
+        return dict(type="Conv", name=nm, c1=c1, c2=c2, k=(3, 3), s=(1, 1), p=(1, 1), g=1, act="silu",
+                    weight=torch.from_numpy((rng.standard_normal((c2, c1, 3, 3)) / np.sqrt(c1 * 9)).astype(np.float32)),
+                    bias=torch.from_numpy(rng.standard_normal(c2).astype(np.float32) * 0.1))
+
+    node = dict(type="Bottleneck", name=name, cv1=cnode(name + ".cv1", c, hid), cv2=cnode(name + ".cv2", hid, c), add=True)
+    plan = Plan.empty(64, 64)
+    xb = plan.new_buf(2 * c, H, W, name="x")  # input and output are channel slices of wider buffers, as in C3k2
+    x = View(xb, c, c, H, W)
+    ob = plan.new_buf(3 * c, H, W, name="out")
+    out = plan.bottleneck(node, x, View(ob, c, c, H, W))
+    assert plan.ops[-1].kind == A.OP_CONV_PAIR and len(plan.ops) == 1, "case must take the fused path"
+    eng = Engine(None, B, 64, 64, device=device, use_graph=False, plan=plan)
+    g = torch.Generator().manual_seed(3)
+    emu = PlanEmulator(plan, B, round_bf16=True)
+    for i, b in enumerate(plan.bufs):
+        v = torch.randn(B, b.H, b.W, b.C, generator=g).to(torch.bfloat16)
+        eng.buffer(i).copy_(v)
+        emu.bufs[i] = v.float()
+    eng.forward()
+    torch.cuda.synchronize()
+    emu.run()
+    return eng.buffer(out.buf).float().cpu(), emu.bufs[out.buf]

@@ -90,6 +90,23 @@ class PlanEmulator:
             return
         self._epilogue(op, y)
 
+    def op_conv_pair(self, op):
+        chid = op.ip[0]
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        if op.w_fp32 is not None and not self.round:
+            w1f, w2f = op.w_fp32
+        else:
+            w1f, w2f = self.bf16(op.w_off, chid * 9 * op.cin), self.bf16(op.p_off[0], op.cout * 9 * chid)
+        w1 = w1f.reshape(chid, 3, 3, op.cin).permute(0, 3, 1, 2)
+        w2 = w2f.reshape(op.cout, 3, 3, chid).permute(0, 3, 1, 2)
+        h = F.silu(F.conv2d(x, w1, self.f32(op.b_off, chid), padding=1))
+        if self.round:  # the hidden map is rounded to bf16 on its way into shared memory
+            h = h.to(torch.bfloat16).float()
+        y = F.silu(F.conv2d(h, w2, self.f32(op.p_off[1], op.cout), padding=1))
+        if op.ip[1]:
+            y = y + x
+        self.put(op.out, y.permute(0, 2, 3, 1), op.cout)
+
     def op_dwconv(self, op):
         kh, kw = op.k
         c = op.cout

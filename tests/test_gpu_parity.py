@@ -118,6 +118,17 @@ def test_conv_kernels_vs_emulator(case, impl):
     assert rel < 4e-3, rel  # same bf16 inputs/weights, fp32 accumulation; only bf16 output rounding + sum order
 
 
+@pytest.mark.parametrize("case", list(convcase.PAIR_CASES))
+def test_fused_bottleneck_vs_emulator(case):
+    """OP_CONV_PAIR (Bottleneck block.py:3405-3419 as one kernel): both convs, the zeroed hidden halo at the image border,
+    the residual read back from shared memory, channel-sliced input/output; untouched channels of the output buffer stay."""
+    got, ref = convcase.run_pair_case(case)
+    rel = float((got - ref).norm() / (ref.norm() + 1e-12))
+    assert rel < 5e-3, rel
+    c = convcase.PAIR_CASES[case][0]
+    assert torch.equal(got[..., :c], ref[..., :c]) and torch.equal(got[..., 2 * c:], ref[..., 2 * c:])
+
+
 DW_CASES = {  # name -> (C, k, s, H, W, act, res, in_total, in_off)
     "dw3_64_80": (64, (3, 3), 1, 80, 80, True, None, None, 0),
     "dw3_80_40_res": (80, (3, 3), 1, 40, 40, True, "add", None, 0),

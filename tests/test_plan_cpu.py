@@ -81,12 +81,19 @@ def test_structure_and_alignment():
     n_conv = sum(k in (A.OP_CONV, A.OP_DWCONV) for k in kinds)
     # SURVEY C.1 lists 88 convs incl. DFL's (fused into decode here); pe is split per head (+1); the two Upsample+Concat
     # pairs of the neck are folded into the consuming C3k2.cv1 as a half-resolution partial conv each (+2)
-    assert n_conv == 90
+    n_pair = sum(k == A.OP_CONV_PAIR for k in kinds)
+    # the thin Bottlenecks of yolo11n (layers 2, 4, 13, 16, 19 and the two of layer 6's C3k) run as one fused kernel each;
+    # the 64->64->64 ones of layers 8 / 22 do not fit (two resident 73 KB weight matrices) and stay two convs
+    assert n_pair == 7
+    assert n_conv + 2 * n_pair == 90
     assert sum(k == A.OP_RESAMPLE for k in kinds) == 0  # every concat AND both nearest-2x upsamples are fused away
     assert sum(o.res_mode == A.RES_PREADD_UP2 for o in plan.ops) == 2
-    plain = Plan(_graph("yolo11n"), 640, 640, fold_upsample=False)
-    assert sum(o.kind == A.OP_RESAMPLE for o in plain.ops) == 2 and len(plain.ops) == len(plan.ops)
+    plain = Plan(_graph("yolo11n"), 640, 640, fold_upsample=False, fuse_pairs=False)
+    assert sum(o.kind == A.OP_RESAMPLE for o in plain.ops) == 2 and len(plain.ops) == len(plan.ops) + n_pair
+    assert sum(o.kind in (A.OP_CONV, A.OP_DWCONV) for o in plain.ops) == 88
     for o in plan.ops:
+        if o.kind == A.OP_CONV_PAIR:
+            assert o.cin == o.cout and o.cin in (16, 32, 64) and o.ip[0] in (16, 32, 64) and o.ins[0].coff % 8 == 0, o.name
         if o.kind == A.OP_CONV:  # tensor-core path preconditions hold for every dense conv of yolo11n
             assert o.cin % 16 == 0 and o.cout_pad % 16 == 0 and o.ins[0].coff % 8 == 0, o.name
     flops, nbytes = plan.work_per_image()
