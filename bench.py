@@ -356,9 +356,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, s_, kind = cpu_arm(model, imgsz, 64, 16, cores, 1, 1)
+        n_cpu = 512 if imgsz <= 640 else 32  # ~10 s of CPU work on the box's host cores
+        v, s_, kind = cpu_arm(model, imgsz, n_cpu, 16, cores, 1, 0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"64 synthetic {imgsz}x{imgsz} frames (4 batches of 16) after one warm-up pass, "
+               "sample": f"{n_cpu} synthetic {imgsz}x{imgsz} frames (batches of 16) after a warm-up call, "
                          + ("reference YOLO.predict(device='cpu')" if kind == "reference" else "oracle torch-fp32 port")
                          + f", {cores} threads, {s_:.1f} s"}
 

@@ -459,6 +459,12 @@ int conv_pair_plan_create(const PairParams &p, int device, ConvPairPlan **out) {
   const long long max_ctas = (long long)num_sms * per_sm;
   pl->grid = (int)(g.ntiles < max_ctas ? g.ntiles : max_ctas);
   pl->fn = pick_pair(p.cin / 16, p.chid / 16);
+  {
+    const char *vb = getenv("B2Y_VERBOSE");
+    if (vb && vb[0] == '1')
+      fprintf(stderr, "[b2y pair] %dx%d c %d hid %d: TH %d TW %d MB %d NB1 %d tiles %lld grid %d smem %zu tmem %d\n", p.H, p.W,
+              p.cin, p.chid, g.TH, g.TW, g.MB, g.NB1, g.ntiles, pl->grid, pl->smem, g.tmem_cols);
+  }
   B2Y_CUDA_CHECK(cudaFuncSetAttribute(pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   *out = pl;
   return B2Y_OK;

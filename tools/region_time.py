@@ -13,8 +13,10 @@ torch.cuda.synchronize()
 names = [o.name for o in eng.plan.ops]
 def idx(prefix):
     return [i for i, n in enumerate(names) if n.startswith(prefix)]
-regions = {"all": (0, len(names)), "stem..model.4": (0, idx("model.5")[0]), "model.5..10": (idx("model.5")[0], idx("model.11")[0]),
-           "neck 11..22": (idx("model.11")[0], idx("model.23")[0]), "head": (idx("model.23")[0], len(names))}
+def first(layer):  # first op of the first top-level layer >= `layer` that still has ops (folded layers have none)
+    return min(i for i, n in enumerate(names) if int(n.split(".")[1]) >= layer)
+regions = {"all": (0, len(names)), "stem..model.4": (0, first(5)), "model.5..10": (first(5), first(11)),
+           "neck 11..22": (first(11), first(23)), "head": (first(23), len(names))}
 # finer: each top-level layer
 tops = {}
 for i, n in enumerate(names):
