@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define B2Y_ABI_VERSION 1
+#define B2Y_ABI_VERSION 2
 #if defined(__GNUC__)
 #define B2Y_API __attribute__((visibility("default")))
 #else
