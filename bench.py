@@ -243,15 +243,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    prof_range = os.environ.get("B2Y_CUDA_PROFILER_RANGE") == "1"  # `ncu --profile-from-start off`: only the timed steps
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if prof_range:
+            torch.cuda.cudart().cudaProfilerStart()
         t0 = time.perf_counter()
         e0.record()
         for j in range(steps):
             fn(j)
         e1.record()
         barrier()
+        if prof_range:
+            torch.cuda.cudart().cudaProfilerStop()
         wall = (time.perf_counter() - t0) * 1e3
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -374,7 +380,7 @@ def main():
                                 "each step streams GBs of activations", "weights": "seeded synthetic checkpoint (bs_yolo_b200.arch, seed 0)",
                        "conf": 0.25, "iou": 0.7, "max_det": 300},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * imgsz * imgsz * 3,
-                    "d2h_bytes_per_step": batch * (pipe.max_det * 6 * 4 + 4), "ms_per_step": max(ms_e2e, wall_e2e) / K},
+                    "d2h_bytes_per_step": world * batch * (pipe.max_det * 6 * 4 + 4), "ms_per_step": max(ms_e2e, wall_e2e) / K},
             "gpu_launches": pipe.launches_per_batch * K, "launches_per_step": pipe.launches_per_batch,
             "clocks": clocks, "stages": stages, "roofline": roof, "cpu_baseline": cpu, "wall_ms_per_step": wall / K,
         }
