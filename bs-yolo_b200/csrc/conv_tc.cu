@@ -139,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, kEpiThreads);
+      mbar_init(tempty0 + 8 * s, EPI == 1 ? kEpiWarps : kEpiThreads);  // lean epilogue: one arrival per warp
     }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -325,74 +325,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int oc_shift = g.oc == 64 ? 6 : (g.oc == 32 ? 5 : 4);
     if constexpr (EPI == 1) {
       // ---- lean epilogue (the common case: bf16 output through the staging buffer + TMA store, no ragged chunks).
-      // A warp's work items are (block j, pair of 16-column chunks): it owns a contiguous half of the chunk range (or,
-      // for 16-channel outputs, every other block), drains 32 columns per TMEM load, and has the NEXT item's residual
-      // rows in flight while it does the math of the current one.  Everything that does not depend on the chunk
-      // (staging row address, swizzle term, residual row pointer) is hoisted out of it.
-      const bool by_block = (nch == 1);  // one chunk per block: split the blocks between the two warps of a quadrant
-      const int c_lo = by_block ? 0 : (half ? (nch + 1) >> 1 : 0);
-      const int c_hi = by_block ? 1 : (half ? nch : (nch + 1) >> 1);
-      const int j_lo = by_block ? half : 0, j_step = by_block ? 2 : 1;
+      // The tile's accumulators are MB*BN/16 chunks of 16 TMEM columns (chunk f = block f / nch, columns 16*(f % nch)).
+      // A work item is a pair of adjacent chunks (one 32-column tcgen05.ld); the two warps of a lane quadrant take the
+      // even / odd items (single chunks when the tile has only one pair).  The epilogue warps are latency-bound (two per
+      // scheduler): everything per thread that does not depend on the chunk is computed once per tile, the residual rows
+      // of the next item are prefetched into L1 while the current one is processed, and the accumulator stage is released
+      // with one mbarrier arrival per warp.
+      const int nchq = g.BN >> 4, nflat_q = g.MB * nchq;
+      const bool pair_mode = nflat_q > 2;
+      const int n_items = pair_mode ? (nflat_q + 1) >> 1 : nflat_q;
+      const uint32_t nch_mul = (65536u + (uint32_t)nchq - 1u) / (uint32_t)nchq;  // f / nch == (f * mul) >> 16 for f < 256
       const uint32_t oc_mask = (uint32_t)g.oc - 1u, sw_mask = (uint32_t)g.o_sw_mask, orb = (uint32_t)g.o_row_bytes;
-      const int act = g.act, res_mode = g.res_mode, MBq = g.MB, BNq = g.BN, THq = g.TH;
       const uint32_t obox = (uint32_t)g.obox_bytes;
-      const bool has_items = (c_lo < c_hi) && (j_lo < MBq);
+      const uint32_t row_off0 = rr0 * orb, blk_off = blk_out_rows * orb;
+      const int act = g.act, res_mode = g.res_mode, THq = g.TH, BNq = g.BN;
+      const size_t res_blk = (size_t)THq * g.Wo * g.res_cs;             // residual elements between consecutive blocks
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
       for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(g, tile);
         const int wo = tc.tw_i * g.TW + tw, n0 = tc.nt * BNq;
         const int ho0 = tc.th_i * rows_tile + th;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * MBq * BNq);
+        const uint32_t taddr = tlane + (uint32_t)(as * nflat_q * 16);
         const uint32_t o_stage = o_base + (uint32_t)(os * g.o_stage_bytes);
         const bool col_ok = row_ok && wo < g.Wo;
+        const float *bias_t = bias_s + n0;
+        const size_t pix0 = ((size_t)tc.b * g.Ho + ho0) * g.Wo + wo;
+        const bf16 *res0 = g.res + pix0 * g.res_cs + n0;
 
-        // residual rows of item (j, c): 2 x 32 B per chunk, requested one item ahead
-        auto res_ptr = [&](int j, int c) -> const uint4 * {
-          const int ho = ho0 + j * THq;
-          if (!(col_ok && ho < g.Ho)) return nullptr;
-          size_t pix = ((size_t)tc.b * g.Ho + ho) * g.Wo + wo;
+        auto chunk_jc = [&](int f, int &j, int &c) {
+          j = (int)(((uint32_t)f * nch_mul) >> 16);
+          c = f - j * nchq;
+        };
+        // residual rows (2 x 16 B) of chunk f; nullptr outside the image
+        auto res_ptr = [&](int f) -> const uint4 * {
+          int j, c;
+          chunk_jc(f, j, c);
+          if (!(col_ok && ho0 + j * THq < g.Ho)) return nullptr;
           if (res_mode == B2Y_RES_PREADD_UP2) {  // half-resolution map: pixel (b, y/2, x/2) of the real (unflattened) image
+            const size_t pix = pix0 + (size_t)j * THq * g.Wo;
             const int rb = (int)(pix / (size_t)g.real_hw);
             const int a = (int)(pix - (size_t)rb * g.real_hw);
             const int y = a / g.real_w, x = a - y * g.real_w;
-            pix = ((size_t)rb * (g.real_hw >> 2)) + (size_t)(y >> 1) * (g.real_w >> 1) + (x >> 1);
+            const size_t hp = ((size_t)rb * (g.real_hw >> 2)) + (size_t)(y >> 1) * (g.real_w >> 1) + (x >> 1);
+            return reinterpret_cast<const uint4 *>(g.res + hp * g.res_cs + n0 + c * 16);
           }
-          return reinterpret_cast<const uint4 *>(g.res + pix * g.res_cs + n0 + c * 16);
+          return reinterpret_cast<const uint4 *>(res0 + (size_t)j * res_blk + c * 16);
         };
-        uint4 rc[4];  // residual rows of the current item: rc[0..1] first chunk, rc[2..3] second chunk
-        bool rcA_ok = false, rcB_ok = false;
-        auto res_load1 = [&](int j, int c, uint4 *dst) -> bool {
-          const uint4 *rp = res_ptr(j, c);
+        auto res_load = [&](int f, uint4 *r) -> bool {
+          const uint4 *rp = res_ptr(f);
           if (rp) {
-            dst[0] = __ldg(rp);
-            dst[1] = __ldg(rp + 1);
+            r[0] = __ldg(rp);
+            r[1] = __ldg(rp + 1);
           }
           return rp != nullptr;
         };
-        auto res_prefetch1 = [&](int j, int c) {  // next item: pull its rows into L1 without holding registers
-          const uint4 *rp = res_ptr(j, c);
+        auto res_prefetch = [&](int f) {  // next item: pull its rows into L1 without holding registers
+          const uint4 *rp = res_ptr(f);
           if (rp) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
         };
-        // item = two 16-column chunks: (j, c) and (j, c+1) of one block, or -- 16-channel outputs -- block j and block
-        // j + j_step; B is absent at the ragged end
-        auto item_b = [&](int j, int c, int &jb, int &cb) -> bool {
-          if (by_block) { jb = j + j_step; cb = c; return jb < MBq; }
-          jb = j; cb = c + 1;
-          return cb < c_hi;
+        // item p -> first chunk and whether it has a second one
+        auto item_f = [&](int p, bool &two) -> int {
+          const int f0 = pair_mode ? 2 * p : p;
+          two = pair_mode && (f0 + 1 < nflat_q);
+          return f0;
         };
-        if (res_mode && has_items) {  // independent of the MMAs: in flight across the accumulator wait below
-          int jb, cb;
-          rcA_ok = res_load1(j_lo, c_lo, rc);
-          rcB_ok = item_b(j_lo, c_lo, jb, cb) && res_load1(jb, cb, rc + 2);
-        }
 
-        mbar_wait(tfull0 + 8 * as, aphase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elected) trace_evt(g, 2, eslot);  // [5i] accumulators ready
-        bool reclaimed = false, released = false;
-
-        auto epi16 = [&](float(&v)[16], const int c, const uint32_t rowaddr, const uint32_t xr, const uint4 *r, const bool r_ok) {
+        // bias (+SiLU) (+residual) of one chunk, packed to bf16 into the swizzled staging tile
+        auto finish = [&](int f, float(&v)[16], const uint4 *r, const bool r_ok) {
+          int j, c;
+          chunk_jc(f, j, c);
           const int col = c * 16;
-          const float4 *bp = reinterpret_cast<const float4 *>(bias_s + n0 + col);
+          const float4 *bp = reinterpret_cast<const float4 *>(bias_t + col);
           if (res_mode == B2Y_RES_PREADD_UP2 && r_ok) {  // pre-activation: conv + upsampled half-resolution partial sum
             float rf[16];
             unpack8(r[0], rf);
@@ -424,7 +427,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int q = 0; q < 16; ++q) v[q] = (res_mode == B2Y_RES_ADD) ? v[q] + rf[q] : v[q] * rf[q];
           }
           if (row_ok) {
-            const uint32_t dst = rowaddr + (uint32_t)(col >> oc_shift) * obox;
+            const uint32_t rowoff = row_off0 + (uint32_t)j * blk_off;
+            const uint32_t xr = ((rowoff >> 7) & sw_mask) << 4;
+            const uint32_t dst = o_stage + rowoff + (uint32_t)(col >> oc_shift) * obox;
             const uint32_t u = (((uint32_t)col & oc_mask) * 2u);  // byte offset of the chunk inside the staging row
             const uint4 p0 = pack8(v), p1 = pack8(v + 8);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (u ^ xr)), "r"(p0.x), "r"(p0.y), "r"(p0.z), "r"(p0.w) : "memory");
@@ -432,65 +437,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         };
 
-        const int j_inc = by_block ? 2 * j_step : j_step;
-        for (int j = j_lo; j < MBq && has_items; j += j_inc) {
-          for (int c = c_lo; c < c_hi; c += 2) {
-            int jb, cb;
-            const bool two = item_b(j, c, jb, cb);  // warp-uniform
-            const bool last = (j + j_inc >= MBq) && (c + 2 >= c_hi);
-            const bool first = (j == j_lo) && (c == c_lo);
-            const uint32_t rowoffA = (rr0 + (uint32_t)j * blk_out_rows) * orb;
-            const uint32_t rowoffB = (rr0 + (uint32_t)jb * blk_out_rows) * orb;
-            float va[16], vb[16];
-            const uint32_t ta = taddr + (uint32_t)(j * BNq + c * 16);
-            if (two && !by_block) tmem_ld32_issue(ta, va, vb);
-            else {
-              tmem_ld16_issue(ta, va);
-              if (two) tmem_ld16_issue(taddr + (uint32_t)(jb * BNq + cb * 16), vb);
-            }
-            if (res_mode) {
-              if (!first) {  // (the first item's rows were requested before the accumulator wait)
-                rcA_ok = res_load1(j, c, rc);
-                rcB_ok = two && res_load1(jb, cb, rc + 2);
-              }
-              if (!last) {
-                const int jn = (c + 2 < c_hi) ? j : j + j_inc, cn = (c + 2 < c_hi) ? c + 2 : c_lo;  // next item
-                int jnb, cnb;
-                res_prefetch1(jn, cn);
-                if (item_b(jn, cn, jnb, cnb)) res_prefetch1(jnb, cnb);
-              }
-            }
-            if (!reclaimed) {
-              // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
-              if (warp == 2) {
-                if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              }
-              named_bar_sync(1, kEpiThreads);
-              reclaimed = true;
-              if (elected) trace_evt(g, 2, eslot);  // [5i+1] staging buffer reclaimed (all warps arrived)
-            }
-            tmem_ld_wait(va);
-            if (two) tmem_ld_wait(vb);
-            if (last) {
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              mbar_arrive(tempty0 + 8 * as);  // last load of this tile landed: the MMA warp may overwrite the stage
-              released = true;
-            }
-            epi16(va, c, o_stage + rowoffA, ((rowoffA >> 7) & sw_mask) << 4, rc, res_mode && rcA_ok);
-            if (two) epi16(vb, cb, o_stage + rowoffB, ((rowoffB >> 7) & sw_mask) << 4, rc + 2, res_mode && rcB_ok);
-          }
+        uint4 rc[4];  // residual rows of the current item: rc[0..1] first chunk, rc[2..3] second chunk
+        bool rcA_ok = false, rcB_ok = false;
+        const bool has_items = half < n_items;
+        if (res_mode && has_items) {  // independent of the MMAs: in flight across the accumulator wait below
+          bool two;
+          const int f0 = item_f(half, two);
+          rcA_ok = res_load(f0, rc);
+          rcB_ok = two && res_load(f0 + 1, rc + 2);
         }
-        if (!reclaimed) {  // a warp without items still takes part in the barrier protocol
+
+        mbar_wait(tfull0 + 8 * as, aphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elected) trace_evt(g, 2, eslot);  // [5i] accumulators ready
+
+        bool reclaimed = false;
+        for (int p = half; p < n_items; p += 2) {
+          bool two;
+          const int f0 = item_f(p, two);  // warp-uniform
+          float va[16], vb[16];
+          if (two) tmem_ld32_issue(taddr + (uint32_t)(f0 * 16), va, vb);
+          else tmem_ld16_issue(taddr + (uint32_t)(f0 * 16), va);
+          const bool last = p + 2 >= n_items;
+          if (res_mode) {
+            if (p != half) {  // (the first item's rows were requested before the accumulator wait)
+              rcA_ok = res_load(f0, rc);
+              rcB_ok = two && res_load(f0 + 1, rc + 2);
+            }
+            if (!last) {
+              bool two_n;
+              const int fn = item_f(p + 2, two_n);
+              res_prefetch(fn);
+              if (two_n) res_prefetch(fn + 1);
+            }
+          }
+          tmem_ld_wait(va);
+          if (two) tmem_ld_wait(vb);
+          if (last) {  // this warp's last tcgen05.ld of the tile has landed: the MMA warp may overwrite the stage
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+          }
+          if (!reclaimed) {
+            // the staging buffer about to be written was last read by the TMA store issued o_stages tiles ago
+            if (warp == 2) {
+              if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            named_bar_sync(1, kEpiThreads);
+            reclaimed = true;
+            if (elected) trace_evt(g, 2, eslot);  // [5i+1] staging buffer reclaimed (all warps arrived)
+          }
+          finish(f0, va, rc, res_mode && rcA_ok);
+          if (two) finish(f0 + 1, vb, rc + 2, res_mode && rcB_ok);
+        }
+        if (!has_items) {  // a warp without items still takes part in the barrier protocol
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * as);
           if (warp == 2) {
             if (g.o_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
           named_bar_sync(1, kEpiThreads);
-        }
-        if (!released) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(tempty0 + 8 * as);
+          if (elected) trace_evt(g, 2, eslot);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (elected) trace_evt(g, 2, eslot);  // [5i+2] this thread's math + staging writes done
