@@ -39,7 +39,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kNumThreads = 64 + kEpiThreads;
 constexpr int kMaxStages = 8;
-constexpr int kMaxMB = 4;
+constexpr int kMaxMB = 8;
 
 struct TcGeom {
   int B, Ho, Wo, cin, cout, cout_pad;

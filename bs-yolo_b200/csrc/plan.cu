@@ -558,7 +558,7 @@ extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
   cudaEvent_t e0, e1;
   B2Y_CUDA_CHECK(cudaEventCreate(&e0));
   B2Y_CUDA_CHECK(cudaEventCreate(&e1));
-  const int mbs[3] = {1, 2, 4};
+  const int mbs[4] = {1, 2, 4, 8};
   const char *vb = getenv("B2Y_VERBOSE");
   const bool verbose = vb && vb[0] == '1';
   int op_index = -1;
@@ -572,7 +572,7 @@ extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
       fprintf(stderr, "[b2y autotune] op %3d %dx%d s%d cin %4d cout %4d map %dx%d:", op_index, r.cp.kh, r.cp.kw, r.cp.sh,
               r.cp.cin, r.cp.cout, r.cp.Ho, r.cp.Wo);
     for (int per_sm = 1; per_sm <= 3; ++per_sm)
-      for (int mi = 0; mi < 3; ++mi) {
+      for (int mi = 0; mi < 4; ++mi) {
         ConvTcPlan *cand = nullptr;
         if (conv_tc_plan_create(r.cp, pl->device, TcConfig{mbs[mi], per_sm}, &cand) != B2Y_OK) continue;
         float ms = 1e30f;

@@ -16,6 +16,8 @@ ultralytics/nn/tasks.py:138-165):
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Any
 
@@ -198,7 +200,7 @@ class Plan:
                 rows = 4 if mode == 1 else c2
                 op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + c2 * c1 * 2
         elif (self.dw_dense and g == c1 == c2 and (kh, kw) == (3, 3) and (sh, sw) in ((1, 1), (2, 2)) and (ph, pw) == (1, 1)
-              and c1 % 16 == 0 and c1 <= 256 and x.c == c1 and self.conv_impl != A.IMPL_SIMT
+              and c1 % 16 == 0 and c1 <= int(os.environ.get("B2Y_DW_DENSE_MAXC", 128)) and x.c == c1 and self.conv_impl != A.IMPL_SIMT
               and (sh == 1 or (x.H % 2 == 0 and x.W % 2 == 0))):
             # Depthwise 3x3 on the tensor cores: the same implicit-GEMM kernel with a diagonal weight matrix
             # (W[co][tap][ci] = w[co][tap] iff ci == co) run in groups of 16 channels (ip[5] = 1): K-chunk kc only feeds

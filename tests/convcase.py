@@ -33,6 +33,9 @@ CASES = {
     "k1_32_64_160_mb": dict(c1=32, c2=64, k=1, s=1, H=160, W=160, B=8),
     "k3s2_16_32_320_mb": dict(c1=16, c2=32, k=3, s=2, H=320, W=320, B=12),
     "k3_64_64_80_mb": dict(c1=64, c2=64, k=3, s=1, H=80, W=80, B=24),
+    # thin outputs on big maps: 8-block tiles (MB = 8)
+    "k3_16_16_320_mb8": dict(c1=16, c2=16, k=3, s=1, H=320, W=320, B=6, res="add"),
+    "k1_16_32_320_mb8": dict(c1=16, c2=32, k=1, s=1, H=320, W=320, B=6),
 }
 
 
