@@ -347,7 +347,16 @@ def main():
                 traffic = tr["conv_tc_dram_bytes_per_step"] / max(tr["conv_tc_launches_per_step"], 1)
         except Exception:
             pass
-        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+        # which roof bounds the kernel on this workload: its launches' summed per-layer floors (yolo11n / BS-YOLO: HBM;
+        # yolo11x@1280: the tensor pipe -- sustained cuBLAS figure, the kernel runs inside a long step)
+        tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        t_hbm = sum(L["bytes"] for L in dom) / (hbm * 1e9)
+        t_tc = sum(L["flops"] for L in dom) / (tf_peak * 1e12)
+        tensor_bound = t_tc > t_hbm
+        tfl = f_dom / t_dom / 1e12
+        roof = {"bound": "tensor" if tensor_bound else "hbm", "achieved": tfl if tensor_bound else ach,
+                "peak": tf_peak if tensor_bound else hbm, "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                "frac": (tfl / tf_peak) if tensor_bound else ach / hbm, "traffic": traffic,
                 "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv), all its launches of one step" if dom and dom[0]["impl"] == 2 else "conv_simt_kernel",
                 "launches_per_step": len(dom), "avg_launch_ms": t_dom * 1e3 / max(len(dom), 1),
                 "algorithmic_bytes_per_launch": b_dom / max(len(dom), 1), "tflops": f_dom / t_dom / 1e12,
