@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2y.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 BF16, F32 = 0, 1
@@ -33,7 +33,7 @@ class Op(C.Structure):
 
 
 EXPORTS = ["b2y_abi_version", "b2y_last_error", "b2y_plan_create", "b2y_plan_destroy", "b2y_plan_run",
-           "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_conv_pair_fits", "b2y_preprocess",
+           "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_set_mid_op", "b2y_plan_wait_mid", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_conv_pair_fits", "b2y_preprocess",
            "b2y_decode", "b2y_nms_workspace_bytes", "b2y_nms", "b2y_scale_boxes"]
 
 _lib = None
@@ -61,6 +61,8 @@ def lib():
     L.b2y_plan_graph_build.argtypes = [vp, vp]
     L.b2y_plan_graph_launch.argtypes = [vp, vp]
     L.b2y_plan_autotune.argtypes = [vp, vp]
+    L.b2y_plan_set_mid_op.argtypes = [vp, i32]
+    L.b2y_plan_wait_mid.argtypes = [vp, vp]
     L.b2y_plan_num_launches.argtypes = [vp]
     L.b2y_plan_op_impl.argtypes = [vp, i32]
     L.b2y_conv_pair_fits.argtypes = [i32, i32, i32, i32, i32]

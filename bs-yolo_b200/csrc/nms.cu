@@ -53,10 +53,18 @@ __global__ void __launch_bounds__(256) nms_score_kernel(NmsParams p) {
   if (a >= p.A) return;
   const float *cls = p.pred + ((size_t)b * (4 + p.nc) + 4) * p.A + a;
   if (!p.multi_label) {
-    float best = cls[0];
-    int bc = 0;
-    for (int c = 1; c < p.nc; ++c) {
-      const float s = cls[(size_t)c * p.A];
+    float best = __ldg(cls);
+    int bc = 0, c = 1;
+    for (; c + 8 <= p.nc; c += 8) {  // eight independent (coalesced, A-strided) loads in flight per thread
+      float s[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = __ldg(cls + (size_t)(c + k) * p.A);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (s[k] > best) { best = s[k]; bc = c + k; }  // strict >: the first index wins ties (ops.py:269, probed)
+    }
+    for (; c < p.nc; ++c) {
+      const float s = __ldg(cls + (size_t)c * p.A);
       if (s > best) { best = s; bc = c; }
     }
     const bool ok = (best > p.conf) && class_ok(p.cm, bc);

@@ -53,6 +53,11 @@ struct b2y_plan {
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<cudaStream_t> lane_streams;  // capture-time only (multi-lane graph build)
   std::vector<cudaEvent_t> lane_events;
+  // "the wide layers are done" marker: recorded in front of op `mid_op` (graph: external event-record node), so that a
+  // caller can park unrelated kernels (pre-/post-processing of neighbouring batches) under the thin, latency-bound layers
+  cudaEvent_t mid_event = nullptr;
+  int mid_op = -1;
+  bool mid_recorded = false;
 };
 
 namespace {
@@ -157,7 +162,25 @@ int resolve_pair(b2y_plan *pl, ResolvedOp &r, int idx, PairParams &q) {
   return B2Y_OK;
 }
 
+// Kernel nodes inherit the priority of the stream they are captured on: the network graph is captured at the highest
+// priority, so that the pre-/post-processing kernels of the neighbouring batches (preprocess, NMS: default-priority side
+// streams of DetectPipeline) only fill SMs the network leaves idle instead of delaying its next layer.  B2Y_GRAPH_PRIO=0
+// keeps the default priority.
+static int capture_priority() {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
+  const char *e = getenv("B2Y_GRAPH_PRIO");
+  return (e && e[0] == '0') ? least : greatest;
+}
+
 int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
+  if (idx == pl->mid_op && pl->mid_event) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    B2Y_CUDA_CHECK(cudaEventRecordWithFlags(pl->mid_event, st,
+                                            cs == cudaStreamCaptureStatusNone ? cudaEventRecordDefault : cudaEventRecordExternal));
+    if (cs == cudaStreamCaptureStatusNone) pl->mid_recorded = true;
+  }
   Resolver R{pl};
   const b2y_op &o = r.op;
   switch (o.kind) {
@@ -343,6 +366,7 @@ extern "C" int b2y_plan_destroy(b2y_plan *pl) {
   }
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   if (pl->graph) cudaGraphDestroy(pl->graph);
+  if (pl->mid_event) cudaEventDestroy(pl->mid_event);
   delete pl;
   return B2Y_OK;
 }
@@ -447,7 +471,7 @@ int capture_lanes(b2y_plan *pl, cudaStream_t origin, int max_lanes) {
     if (L < 0) {
       if ((int)streams.size() < max_lanes) {
         cudaStream_t s2 = nullptr;
-        e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        e = cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, capture_priority());
         if (e != cudaSuccess) { fail(e, "cudaStreamCreate"); break; }
         e = cudaStreamWaitEvent(s2, fork, 0);  // joins the capture
         if (e != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
@@ -492,13 +516,30 @@ int capture_lanes(b2y_plan *pl, cudaStream_t origin, int max_lanes) {
 }
 }  // namespace
 
+extern "C" int b2y_plan_set_mid_op(b2y_plan *pl, int32_t op_index) {
+  B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "set_mid_op: null plan");
+  B2Y_REQUIRE(op_index < (int)pl->ops.size(), B2Y_ERR_INVALID, "set_mid_op: op %d of %d", op_index, (int)pl->ops.size());
+  B2Y_REQUIRE(!pl->graph_exec, B2Y_ERR_INVALID, "set_mid_op: call before b2y_plan_graph_build");
+  if (op_index >= 0 && !pl->mid_event) B2Y_CUDA_CHECK(cudaEventCreateWithFlags(&pl->mid_event, cudaEventDisableTiming));
+  pl->mid_op = op_index < 0 ? -1 : op_index;
+  pl->mid_recorded = false;
+  return B2Y_OK;
+}
+
+extern "C" int b2y_plan_wait_mid(b2y_plan *pl, void *stream) {
+  B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "wait_mid: null plan");
+  if (pl->mid_event && pl->mid_op >= 0 && pl->mid_recorded)
+    B2Y_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, pl->mid_event, 0));
+  return B2Y_OK;
+}
+
 extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "graph_build: null plan");
   (void)stream;  // capture happens on a private stream: the caller's may be the legacy default stream, which cannot capture
   if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
   if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
   cudaStream_t st = nullptr;
-  B2Y_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  B2Y_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, capture_priority()));
   cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) {
     cudaStreamDestroy(st);
@@ -547,6 +588,7 @@ extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
 extern "C" int b2y_plan_graph_launch(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl && pl->graph_exec, B2Y_ERR_INVALID, "graph_launch: graph not built");
   B2Y_CUDA_CHECK(cudaGraphLaunch(pl->graph_exec, (cudaStream_t)stream));
+  if (pl->mid_event && pl->mid_op >= 0) pl->mid_recorded = true;
   return B2Y_OK;
 }
 

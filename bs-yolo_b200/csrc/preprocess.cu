@@ -68,57 +68,86 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreParams p) {
     o[0] = (uint8_t)bgr[0]; o[1] = (uint8_t)bgr[1]; o[2] = (uint8_t)bgr[2];
   }
 }
-// Network-input fast path (no resize): thread = one space-to-depth super-pixel = 2 x 2 source pixels.
+// Network-input fast path (no resize): one space-to-depth super-pixel = 2 x 2 source pixels per thread and round, kUnroll
+// rounds in flight (persistent grid, grid-stride over blocks of 256 * kUnroll consecutive super-pixels).
 // Reads 2 x 6 source bytes (three 16-bit loads per row: x is even, so the BGR pair is 2-byte aligned whenever the row
-// pitch and the placement are even), looks v/255 up in a 256-entry bf16 table (built per block with the same
-// correctly-rounded divide as the generic path, so both write identical bits) and stores the 16 channels
-// ((y&1)*2 + (x&1))*4 + {R,G,B,0} as two 16-byte vectors: consecutive lanes write consecutive 32-byte super-pixels.
+// pitch and the placement are even) and stores the 16 channels ((y&1)*2 + (x&1))*4 + {R,G,B,0} as two 16-byte vectors:
+// consecutive lanes write consecutive 32-byte super-pixels.  v/255 in bf16: float(v) * (1/255.f) rounded to bf16 gives the
+// same bits as the generic path's correctly rounded divide for all 256 byte values (checked exhaustively in the tests).
+constexpr int kPreUnroll = 4;
+
+__device__ __forceinline__ uint32_t norm2_bf16(uint32_t lo, uint32_t hi) {  // {bf16(lo/255), bf16(hi/255)} packed
+  const float k = 1.f / 255.f;
+  const float a = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | lo), 8388608.f), k);
+  const float b = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | hi), 8388608.f), k);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 __global__ void __launch_bounds__(256) preprocess_s2d_kernel(PreParams p) {
   pdl_launch_dependents();
-  __shared__ uint16_t lut[256];
-  {
-    const __nv_bfloat16 v = __float2bfloat16_rn(__fdiv_rn((float)threadIdx.x, 255.f));
-    lut[threadIdx.x] = *reinterpret_cast<const uint16_t *>(&v);
-  }
-  __syncthreads();
   pdl_wait();
   const int W2 = p.W >> 1, H2 = p.H >> 1;
   const long long total = (long long)p.B * H2 * W2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int xs = (int)(idx % W2);
-  const int ys = (int)((idx / W2) % H2);
-  const int b = (int)(idx / ((long long)W2 * H2));
-  const uint8_t *img = p.src + (size_t)b * p.h * p.w * 3;
-  uint32_t o[8];
+  const bool fast_ok = ((p.w & 1) == 0) && ((p.left & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.src) & 1) == 0);
+  for (long long base = (long long)blockIdx.x * (256 * kPreUnroll); base < total; base += (long long)gridDim.x * (256 * kPreUnroll)) {
+    uint32_t raw[kPreUnroll][2][3];  // per round and row: B0G0 | R0B1 | G1R1 (16-bit words)
 #pragma unroll
-  for (int row = 0; row < 2; ++row) {
-    const int uy = 2 * ys + row - p.top, ux = 2 * xs - p.left;
-    uint32_t px[2][3] = {{114, 114, 114}, {114, 114, 114}};  // B, G, R of the two pixels
-    if (uy >= 0 && uy < p.uh) {
-      const uint8_t *s = img + ((size_t)uy * p.w + ux) * 3;
-      if (ux >= 0 && ux + 1 < p.uw && ((reinterpret_cast<uintptr_t>(s) & 1) == 0)) {
-        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(s);
-        const uint32_t a = __ldg(s16), c = __ldg(s16 + 1), d = __ldg(s16 + 2);  // B0G0 | R0B1 | G1R1
-        px[0][0] = a & 255u; px[0][1] = a >> 8; px[0][2] = c & 255u;
-        px[1][0] = c >> 8; px[1][1] = d & 255u; px[1][2] = d >> 8;
-      } else {
+    for (int u = 0; u < kPreUnroll; ++u) {
+      const long long idx = base + u * 256 + threadIdx.x;
+      const int xs = (int)(idx % W2);
+      const int ys = (int)((idx / W2) % H2);
+      const int b = (int)(idx / ((long long)W2 * H2));
+      const uint8_t *img = p.src + (size_t)b * p.h * p.w * 3;
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-          if (ux + q >= 0 && ux + q < p.uw) {
-            px[q][0] = s[q * 3]; px[q][1] = s[q * 3 + 1]; px[q][2] = s[q * 3 + 2];
+      for (int row = 0; row < 2; ++row) {
+        const int uy = 2 * ys + row - p.top, ux = 2 * xs - p.left;
+        uint32_t px[2][3] = {{114, 114, 114}, {114, 114, 114}};  // B, G, R of the two pixels
+        bool packed = false;
+        if (idx < total && uy >= 0 && uy < p.uh) {
+          const uint8_t *s = img + ((size_t)uy * p.w + ux) * 3;
+          if (fast_ok && ux >= 0 && ux + 1 < p.uw) {
+            const uint16_t *s16 = reinterpret_cast<const uint16_t *>(s);
+            raw[u][row][0] = __ldg(s16);
+            raw[u][row][1] = __ldg(s16 + 1);
+            raw[u][row][2] = __ldg(s16 + 2);
+            packed = true;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              if (ux + q >= 0 && ux + q < p.uw) {
+                px[q][0] = s[q * 3]; px[q][1] = s[q * 3 + 1]; px[q][2] = s[q * 3 + 2];
+              }
           }
+        }
+        if (!packed) {
+          raw[u][row][0] = px[0][0] | (px[0][1] << 8);
+          raw[u][row][1] = px[0][2] | (px[1][0] << 8);
+          raw[u][row][2] = px[1][1] | (px[1][2] << 8);
+        }
       }
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      o[row * 4 + q * 2] = (uint32_t)lut[px[q][2]] | ((uint32_t)lut[px[q][1]] << 16);  // R, G
-      o[row * 4 + q * 2 + 1] = (uint32_t)lut[px[q][0]];                                 // B, 0
+    for (int u = 0; u < kPreUnroll; ++u) {
+      const long long idx = base + u * 256 + threadIdx.x;
+      if (idx >= total) continue;
+      uint32_t o[8];
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const uint32_t a = raw[u][row][0], c = raw[u][row][1], d = raw[u][row][2];
+        const uint32_t b0 = a & 255u, g0 = a >> 8, r0 = c & 255u, b1 = c >> 8, g1 = d & 255u, r1 = d >> 8;
+        o[row * 4 + 0] = norm2_bf16(r0, g0);          // R, G
+        o[row * 4 + 1] = norm2_bf16(b0, 0u) & 0xFFFFu;  // B, 0
+        o[row * 4 + 2] = norm2_bf16(r1, g1);
+        o[row * 4 + 3] = norm2_bf16(b1, 0u) & 0xFFFFu;
+      }
+      // one 256-bit store per super-pixel: every lane writes a whole 32-byte sector
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(reinterpret_cast<uint4 *>(p.dst) + (size_t)idx * 2),
+                   "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                   : "memory");
     }
   }
-  uint4 *dst = reinterpret_cast<uint4 *>(p.dst) + (size_t)idx * 2;
-  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 }  // namespace
 
@@ -136,9 +165,14 @@ extern "C" int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, 
   p.resize = !(uh == h && uw == w);
   p.scale_x = 1.0 / ((double)uw / (double)w);
   p.scale_y = 1.0 / ((double)uh / (double)h);
-  if (dst_format == 0 && !p.resize && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+  if (dst_format == 0 && !p.resize && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
     const long long nsp = (long long)B * (H >> 1) * (W >> 1);
-    b2y_launch(preprocess_s2d_kernel, dim3((unsigned)((nsp + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, p);
+    const long long blocks = (nsp + 256 * kPreUnroll - 1) / (256 * kPreUnroll);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long cap = (long long)sms * 8;  // persistent: 8 CTAs of 256 threads per SM
+    b2y_launch(preprocess_s2d_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), 0, (cudaStream_t)stream, p);
     B2Y_LAUNCH_CHECK();
     return B2Y_OK;
   }

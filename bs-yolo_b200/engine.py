@@ -38,7 +38,8 @@ def space_to_depth(x: torch.Tensor) -> torch.Tensor:
 
 class Engine:
     def __init__(self, ir, batch: int, H: int, W: int, device: int | torch.device = 0, conv_impl: int = A.IMPL_AUTO,
-                 use_graph: bool = True, plan: Plan | None = None, autotune: bool = True, fuse_decode: bool = True):
+                 use_graph: bool = True, plan: Plan | None = None, autotune: bool = True, fuse_decode: bool = True,
+                 mid_stride: int = 0):
         if not torch.cuda.is_available():
             raise A.B2YError("bs_yolo_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = A.lib()
@@ -63,6 +64,15 @@ class Engine:
         self._tuned = not autotune
         self.max_det_alloc = 0
         self._nms_ws = None
+        # mid-point marker (b2y_plan_set_mid_op): in front of the first op that works on a map of stride >= mid_stride --
+        # from there on the layers are thin and latency-bound, and DetectPipeline parks its side-stream kernels behind it
+        self.mid_op = -1
+        if mid_stride > 0:
+            for i, o in enumerate(self.plan.ops):
+                if getattr(o.out, "H", None) is not None and o.out.H * mid_stride <= H:
+                    self.mid_op = i
+                    break
+            A.check(self.lib.b2y_plan_set_mid_op(self.handle, self.mid_op))
 
     def __del__(self):
         try:
@@ -134,6 +144,10 @@ class Engine:
         else:
             A.check(self.lib.b2y_plan_run(self.handle, 0, -1, st))
         return self.y if self.plan.y_buf >= 0 else None
+
+    def wait_mid(self, stream: torch.cuda.Stream):
+        """Make `stream` wait until the most recent forward() has passed its mid-point marker (no-op without marker)."""
+        A.check(self.lib.b2y_plan_wait_mid(self.handle, stream.cuda_stream))
 
     def run_ops(self, first: int, last: int):
         A.check(self.lib.b2y_plan_run(self.handle, first, last, self._stream()))

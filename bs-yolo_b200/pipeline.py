@@ -3,20 +3,43 @@
 One pipeline = one GPU: preprocess + CUDA-graphed network + NMS (+ optional scale_boxes), i.e. the device-side body of
 BasePredictor.stream_inference's hot loop (ultralytics/engine/predictor.py:241-266): preprocess -> inference ->
 postprocess.  Batches are independent, so the pipeline is software-pipelined over two slots (two Engines = two activation
-workspaces and graphs): the post-process of batch i (NMS: one CTA per image, latency-bound, most SMs idle) runs on a second
-stream underneath the network of batch i+1, and -- in `predict_stream` -- so do the host<->device copies.
+workspaces and graphs).  The network's persistent kernels keep every SM busy through the wide, bandwidth-bound first half
+of the graph and leave most of them idle in the thin P4/P5 layers, so the side work is parked there: the preprocess of
+batch i waits for the mid-point marker of graph i-1, and the NMS (+ gather, + device->host copy) of batch i is enqueued
+only once graph i+1 has been launched, behind its marker (`Engine.wait_mid`).  In `predict_stream` the host<->device
+copies overlap as well.
 
     __call__(frames)        one batch, stream-synchronous semantics: the results are ready for the caller's stream
-    submit(frames)          one batch, pipelined: returns (dets, counts, event); the results are ready when `event` is
+    submit(frames)          one batch, pipelined: returns a Ticket; `ticket.result()` -> (dets, counts, event)
+    flush()                 enqueue the post-process of the last submitted batch (nothing left deferred)
     predict_stream(batches) end to end with host buffers: pinned frames in, pinned detections out, everything overlapped
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
 from . import _cabi as A
 from .engine import Engine, letterbox_geometry
 from .ops import nms_raw, scale_boxes_batched
+
+
+class Ticket:
+    """Handle of one submitted batch.  Its post-process is enqueued by the NEXT submit() (or by flush()/result())."""
+
+    def __init__(self, pipe, slot, rescale, gather, host_out):
+        self.pipe, self.slot, self.rescale, self.gather, self.host_out = pipe, slot, rescale, gather, host_out
+        self.dets = self.counts = self.event = None
+
+    def result(self):
+        """(dets (B,max_det,6), counts (B,), event): the tensors are valid once `event` has completed."""
+        if self.event is None:
+            self.pipe.flush()
+        return self.dets, self.counts, self.event
+
+    def __iter__(self):
+        return iter(self.result())
 
 
 class DetectPipeline:
@@ -26,13 +49,17 @@ class DetectPipeline:
         self.src_shape = tuple(src_shape)
         H, W, *_ = letterbox_geometry(self.src_shape, imgsz, auto)
         self.auto = auto
-        self.engines = [Engine(ir, batch, H, W, device=device, use_graph=use_graph, conv_impl=conv_impl)
+        self.defer = slots >= 2 and os.environ.get("B2Y_DEFER_POST", "1") != "0"
+        mid = int(os.environ.get("B2Y_MID_STRIDE", "16")) if self.defer else 0
+        self.engines = [Engine(ir, batch, H, W, device=device, use_graph=use_graph, conv_impl=conv_impl, mid_stride=mid)
                         for _ in range(max(1, slots))]
         self.engine = self.engines[0]
         self.device = self.engine.device
         self.B, self.H, self.W = batch, H, W
         self.conf, self.iou, self.max_det, self.classes, self.agnostic = conf, iou, max_det, classes, agnostic
         self._slot = 0
+        self._pending = None  # Ticket of the batch whose post-process has not been enqueued yet
+        self._last = None     # engine of the most recent forward()
         self._post_stream = torch.cuda.Stream(self.device)
         self._pre_stream = torch.cuda.Stream(self.device)
         self._copy_stream = None
@@ -47,14 +74,16 @@ class DetectPipeline:
         return self.engine.n_launches + 1 + 2  # network ops + preprocess + NMS (score, select)
 
     def submit(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None,
-               gather: bool = False, host_out=None, src_ready=None):
+               gather: bool = False, host_out=None, src_ready=None) -> Ticket:
         """Enqueue one batch: src_u8 (B,h,w,3) uint8 BGR on this device.  The network goes to the current stream; the
-        preprocess kernel runs on its own stream (it only needs the frames and this slot's input buffer, so it overlaps the
-        previous batch's network), NMS (+ scale_boxes, + the multi-GPU gather, + the device->host copy into `host_out`) on
-        the post-process stream.  `src_ready`: an event after which the frames are complete, or True if they already are
-        (resident inputs); None (default) orders the preprocess after everything enqueued on the current stream so far.
-        Returns (dets (B,max_det,6), counts (B,), event): the tensors are valid once `event` has completed; they must not
-        be consumed on another stream before that.  ``consumed`` is recorded when the frames have been read."""
+        preprocess kernel runs on its own stream (it only needs the frames and this slot's input buffer) behind the
+        mid-point marker of the previous batch's network; NMS (+ scale_boxes, + the multi-GPU gather, + the device->host
+        copy into `host_out`) of the PREVIOUS batch is enqueued on the post-process stream behind this batch's marker.
+        `src_ready`: an event after which the frames are complete, or True if they already are (resident inputs); None
+        (default) orders the preprocess after everything enqueued on the current stream so far.
+        Returns a Ticket; ``ticket.result()`` gives (dets (B,max_det,6), counts (B,), event) -- the tensors are valid once
+        `event` has completed and must not be consumed on another stream before that.  ``consumed`` is recorded when the
+        frames have been read."""
         k = self._slot
         self._slot = (k + 1) % len(self.engines)
         eng = self.engines[k]
@@ -67,33 +96,69 @@ class DetectPipeline:
             if src_ready is not True:
                 pre.wait_event(src_ready)
             pre.wait_event(self._fwd_done[k])  # the network that last read this slot's input buffer has finished
+            if self.defer and self._last is not None:
+                self._last.wait_mid(pre)         # ... and the previous batch's network is past its wide layers
             src_u8.record_stream(pre)            # (allocator: the frames are read on this stream)
             eng.preprocess(src_u8, auto=self.auto)
             self._pre_done[k].record(pre)
             if consumed is not None:
                 consumed.record(pre)
+        if self._pending is not None and self._pending.slot == k:
+            self._post(self._pending, None)      # (single slot: its y is about to be overwritten)
         main.wait_event(self._pre_done[k])
         main.wait_event(self._post_done[k])  # the NMS that last read this slot's y has finished
         eng.forward()
         self._fwd_done[k].record(main)
+        self._last = eng
+        ticket = Ticket(self, k, rescale, gather, host_out)
+        if self.defer:
+            if self._pending is not None:
+                self._post(self._pending, eng)  # previous batch: under this network's thin layers
+            self._pending = ticket
+        else:
+            self._post(ticket, None)
+        return ticket
+
+    def _post(self, t: Ticket, behind: Engine | None):
+        """Enqueue the post-process of ticket `t` (behind the mid-point marker of `behind`'s latest forward, if given)."""
+        k = t.slot
+        eng = self.engines[k]
         post = self._post_stream
         with torch.cuda.stream(post):
             post.wait_event(self._fwd_done[k])
+            if behind is not None:
+                behind.wait_mid(post)
             dets, counts = nms_raw(eng.y, self.conf, self.iou, self.max_det, self.classes, self.agnostic)
-            if rescale:
+            if t.rescale:
                 scale_boxes_batched(dets, counts, (self.H, self.W), [self.src_shape] * self.B)
-            if gather:
+            if t.gather:
                 from .shard import gather_detections
                 dets, counts = gather_detections(dets, counts)
-            if host_out is not None:
-                host_out[0].copy_(dets, non_blocking=True)
-                host_out[1].copy_(counts, non_blocking=True)
+            if t.host_out is not None:
+                t.host_out[0].copy_(dets, non_blocking=True)
+                t.host_out[1].copy_(counts, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(post)
             self._post_done[k].record(post)
-        return dets, counts, self._post_done[k]
+        t.dets, t.counts, t.event = dets, counts, ev
+        if self._pending is t:
+            self._pending = None
+
+    def flush(self):
+        """Enqueue whatever post-process is still deferred (call before waiting for the last batch)."""
+        if self._pending is not None:
+            self._post(self._pending, None)
+
+    def drain(self):
+        """flush() and make the current stream wait for every slot's post-process (the end of a timed region)."""
+        self.flush()
+        main = torch.cuda.current_stream(self.device)
+        for e in self._post_done:
+            main.wait_event(e)
 
     def __call__(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None):
         """One batch with plain stream semantics: returns (dets (B,max_det,6), counts (B,)) usable on the current stream."""
-        dets, counts, ev = self.submit(src_u8, rescale, consumed)
+        dets, counts, ev = self.submit(src_u8, rescale, consumed).result()
         main = torch.cuda.current_stream(self.device)
         main.wait_event(ev)
         dets.record_stream(main)
@@ -116,7 +181,7 @@ class DetectPipeline:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
-        stage, copied, consumed, done, outs = [None, None], [None, None], [None, None], [None, None], [None, None]
+        stage, copied, consumed, tickets, outs = [None, None], [None, None], [None, None], [None, None], [None, None]
         for k in range(2):
             copied[k], consumed[k] = torch.cuda.Event(), torch.cuda.Event()
 
@@ -148,12 +213,12 @@ class DetectPipeline:
             if outs[k] is None:
                 outs[k] = (torch.empty(world * self.B, self.max_det, 6, dtype=torch.float32).pin_memory(),
                            torch.empty(world * self.B, dtype=torch.int32).pin_memory())
-            _, _, done[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k],
-                                        src_ready=copied[k])
+            tickets[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k],
+                                     src_ready=copied[k])
             if pending is not None:
-                done[pending].synchronize()
+                tickets[pending].result()[2].synchronize()  # (enqueued by the submit above)
                 yield outs[pending]
             pending = k
             i += 1
-        done[pending].synchronize()
+        tickets[pending].result()[2].synchronize()          # (flushes the last batch)
         yield outs[pending]

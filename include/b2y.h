@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define B2Y_ABI_VERSION 2
+#define B2Y_ABI_VERSION 3
 #if defined(__GNUC__)
 #define B2Y_API __attribute__((visibility("default")))
 #else
@@ -111,6 +111,14 @@ B2Y_API int b2y_plan_run(b2y_plan *plan, int32_t first, int32_t last, void *stre
 /* Capture the whole plan into a CUDA graph (stream must not be capturing) / replay it. */
 B2Y_API int b2y_plan_graph_build(b2y_plan *plan, void *stream);
 B2Y_API int b2y_plan_graph_launch(b2y_plan *plan, void *stream);
+/* Mid-point marker for callers that pipeline batches (no reference counterpart: BasePredictor.stream_inference,
+ * ultralytics/engine/predictor.py:241-266, runs preprocess -> inference -> postprocess strictly in sequence).
+ * set_mid_op: an event is recorded in front of op `op_index` in every later run / graph launch (-1: none; call before
+ * b2y_plan_graph_build).  wait_mid: make `stream` wait for that point of the most recent launch (no-op if the plan has not
+ * been launched with a marker yet).  The wide, bandwidth-bound layers come first in a detect network; kernels parked behind
+ * the marker (the NMS of the previous batch, the preprocess of the next) run under the thin, latency-bound layers. */
+B2Y_API int b2y_plan_set_mid_op(b2y_plan *plan, int32_t op_index);
+B2Y_API int b2y_plan_wait_mid(b2y_plan *plan, void *stream);
 /* Time the candidate tile configurations of every tcgen05 conv on the plan's own buffers and keep the fastest
  * (synchronises the stream; buffer contents are clobbered; an existing graph is dropped). */
 B2Y_API int b2y_plan_autotune(b2y_plan *plan, void *stream);

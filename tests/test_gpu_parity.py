@@ -350,6 +350,39 @@ def test_predict_stream_matches_synchronous_calls():
     assert list(pipe.predict_stream(iter([]))) == []
 
 
+def test_submit_tickets_with_deferred_postprocess():
+    """submit() defers a batch's NMS until the next network has been launched (parked behind its mid-point marker);
+    tickets resolve to the same detections as synchronous calls, in any order of result()/submit(), and flush() leaves
+    nothing pending.  Also with the marker disabled (eager engines, single slot)."""
+    from bs_yolo_b200.pipeline import DetectPipeline
+    g = _graph("yolo11n")
+    rng = np.random.default_rng(21)
+    frames = [torch.from_numpy(rng.integers(0, 256, (2, 160, 160, 3), dtype=np.uint8)).cuda() for _ in range(5)]
+    pipe = DetectPipeline(g, 2, 160, (160, 160))
+    assert pipe.defer and pipe.engine.mid_op > 0
+    ref = [tuple(t.cpu().clone() for t in pipe(f)) for f in frames]
+    tickets = [pipe.submit(f) for f in frames]
+    assert tickets[-1].event is None and all(t.event is not None for t in tickets[:-1])  # only the last one is pending
+    pipe.flush()
+    assert pipe._pending is None
+    for t, (dr, cr) in zip(tickets, ref):
+        d, c, ev = t.result()
+        ev.synchronize()
+        assert torch.equal(c.cpu(), cr) and torch.equal(d.cpu(), dr)
+    # result() before the next submit flushes that batch on its own
+    t0 = pipe.submit(frames[0])
+    d, c, ev = t0
+    ev.synchronize()
+    assert torch.equal(d.cpu(), ref[0][0])
+    for kw in (dict(slots=1), dict(use_graph=False)):
+        p2 = DetectPipeline(g, 2, 160, (160, 160), **kw)
+        ts = [p2.submit(f) for f in frames[:3]]
+        p2.drain()
+        torch.cuda.synchronize()
+        for t, (dr, cr) in zip(ts, ref):
+            assert torch.equal(t.result()[0].cpu(), dr) and torch.equal(t.result()[1].cpu(), cr)
+
+
 def test_sahi_tiled_inference_merge_bit_exact():
     """Config 5 (SAHI-style tiling): frame -> overlapping edge tiles -> per-tile pipeline -> shift -> global class-aware NMS.
     The merge (shift + xyxy->xywh + NMS) must equal, bit for bit, the oracle's NMS over the same per-tile detections."""
