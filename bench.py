@@ -391,9 +391,10 @@ def main():
                        "cache": f"inputs rotate over {n_rot} batches ({n_rot * batch * imgsz * imgsz * 3 / 1e6:.0f} MB > 126 MB L2); "
                                 "each step streams GBs of activations", "weights": "seeded synthetic checkpoint (bs_yolo_b200.arch, seed 0)",
                        "conf": 0.25, "iou": 0.7, "max_det": 300},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * imgsz * imgsz * 3,
-                    "d2h_bytes_per_step": world * batch * (pipe.max_det * 6 * 4 + 4), "ms_per_step": max(ms_e2e, wall_e2e) / K},
-            "gpu_launches": pipe.launches_per_batch * K, "launches_per_step": pipe.launches_per_batch,
+            # whole-job bytes per step: every rank uploads its shard and reads back the gathered detections of all ranks
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * batch * imgsz * imgsz * 3,
+                    "d2h_bytes_per_step": world * world * batch * (pipe.max_det * 6 * 4 + 4), "ms_per_step": max(ms_e2e, wall_e2e) / K},
+            "gpu_launches": world * pipe.launches_per_batch * K, "launches_per_step": pipe.launches_per_batch,
             "clocks": clocks, "stages": stages, "roofline": roof, "cpu_baseline": cpu, "wall_ms_per_step": wall / K,
         }
         print(json.dumps(line))

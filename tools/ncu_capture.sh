@@ -10,6 +10,7 @@ B2Y_PROFILE_TABLE=$OUT/optable_$TAG.json $CMD > $OUT/plain_$TAG.log 2>&1 || { ec
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
     --clock-control none --profile-from-start off --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "list rc $?"
+[ "$SEL" = "none" ] && SEL=""
 for L in $SEL; do
   ncu --set full --clock-control none --import-source on --profile-from-start off --launch-skip $L --launch-count 1 \
       -f -o $OUT/prof_${TAG}_L$L $CMD > $OUT/ncu_full_${TAG}_L$L.log 2>&1
