@@ -162,17 +162,6 @@ int resolve_pair(b2y_plan *pl, ResolvedOp &r, int idx, PairParams &q) {
   return B2Y_OK;
 }
 
-// Kernel nodes inherit the priority of the stream they are captured on: the network graph is captured at the highest
-// priority, so that the pre-/post-processing kernels of the neighbouring batches (preprocess, NMS: default-priority side
-// streams of DetectPipeline) only fill SMs the network leaves idle instead of delaying its next layer.  B2Y_GRAPH_PRIO=0
-// keeps the default priority.
-static int capture_priority() {
-  int least = 0, greatest = 0;
-  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
-  const char *e = getenv("B2Y_GRAPH_PRIO");
-  return (e && e[0] == '0') ? least : greatest;
-}
-
 int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
   if (idx == pl->mid_op && pl->mid_event) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -471,7 +460,7 @@ int capture_lanes(b2y_plan *pl, cudaStream_t origin, int max_lanes) {
     if (L < 0) {
       if ((int)streams.size() < max_lanes) {
         cudaStream_t s2 = nullptr;
-        e = cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, capture_priority());
+        e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
         if (e != cudaSuccess) { fail(e, "cudaStreamCreate"); break; }
         e = cudaStreamWaitEvent(s2, fork, 0);  // joins the capture
         if (e != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
@@ -539,7 +528,7 @@ extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
   if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
   if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
   cudaStream_t st = nullptr;
-  B2Y_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, capture_priority()));
+  B2Y_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) {
     cudaStreamDestroy(st);
