@@ -54,9 +54,14 @@ enum b2y_op_kind {
   B2Y_OP_MSCA_GATE = 11,/* MSCA: SE 1x1 convs + softmax(sigmoid()) over branches; MSCA.py:71-77                  */
   B2Y_OP_WSUM4 = 12,    /* MSCA: gate-weighted sum of the four branches; MSCA.py:84                              */
   B2Y_OP_DECODE = 13,   /* Detect._inference: DFL + dist2bbox + stride + sigmoid; head.py:100-131                */
-  B2Y_OP_CONV_PAIR = 14 /* Bottleneck in one kernel: out = x + SiLU(conv3x3(SiLU(conv3x3(x))))  (block.py:3405-3419), the
+  B2Y_OP_CONV_PAIR = 14,/* Bottleneck in one kernel: out = x + SiLU(conv3x3(SiLU(conv3x3(x))))  (block.py:3405-3419), the
                            hidden map never leaves the SM.  cin = cout in {16,32,64}; ip[0] = hidden channels (padded
                            to 16/32/64), ip[1] = 1: add the input; w_off/b_off = first conv, p_off[0]/p_off[1] = second */
+  B2Y_OP_C3K2 = 15      /* EXPERIMENTAL (never emitted by the default planner; B2Y_FUSE_C3K2=1): a whole C3k2 block with one
+                           Bottleneck (block.py:4148-4156, C2f.forward :3306-3310) in one kernel: cv1 1x1 cin -> 2c, Bottleneck
+                           c -> chid -> c with shortcut, cv2 1x1 3c -> cout.  ip[0] = c, ip[1] = chid (padded to 16);
+                           w_off = packed bf16 W0 [2c][cin] | W1 [chid][9c] | W2 [c][9 chid] | W3 [cout][3c],
+                           b_off = fp32 [2c | chid | c | cout] */
 };
 
 enum b2y_conv_impl { B2Y_IMPL_AUTO = 0, B2Y_IMPL_SIMT = 1, B2Y_IMPL_TCGEN05 = 2 };
@@ -127,6 +132,8 @@ B2Y_API int b2y_plan_num_launches(const b2y_plan *plan);
 B2Y_API int b2y_plan_op_impl(const b2y_plan *plan, int32_t i);
 /* Planner query, no device needed: 1 if B2Y_OP_CONV_PAIR has a kernel configuration for these channels and map size. */
 B2Y_API int b2y_conv_pair_fits(int32_t cin, int32_t chid, int32_t B, int32_t H, int32_t W);
+/* Same query for B2Y_OP_C3K2 (experimental). */
+B2Y_API int b2y_c3k2_fits(int32_t cin, int32_t c, int32_t chid, int32_t cout, int32_t B, int32_t H, int32_t W);
 
 /* ---- preprocess: LetterBox + BGR->RGB + /255 (ultralytics/data/augment.py:1535-1601,
  *      engine/predictor.py:116-134).  src: B x h x w x 3 uint8 (device).  The resized image (uw x uh, OpenCV
