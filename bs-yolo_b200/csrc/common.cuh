@@ -39,6 +39,30 @@ void b2y_set_error(const char *fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- device guard ------------------------------------------------------------------------------------------------
+// The C entry points may be called while another device is current (one thread driving several GPUs, Engine(device=1)):
+// every entry point makes the device that owns its memory current for the duration of the call and restores the caller's.
+struct B2YDeviceGuard {
+  int prev = -1, dev = -1;
+  explicit B2YDeviceGuard(int device) : dev(device) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~B2YDeviceGuard() {
+    if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+// device that owns a device pointer (-1 if it is not device memory known to the runtime)
+static inline int b2y_device_of(const void *ptr) {
+  cudaPointerAttributes at;
+  if (ptr == nullptr || cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+}
+
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
 // Every kernel of the library is launched through b2y_launch with programmatic stream serialization: kernel N+1 may
 // become resident (and run its prologue: barrier init, TMEM alloc, weight loads) while kernel N is still draining.

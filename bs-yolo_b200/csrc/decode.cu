@@ -103,5 +103,6 @@ int decode_launch(const void *const *raw, const int32_t *hs, const int32_t *ws, 
 
 extern "C" int b2y_decode(const void *const *raw, const int32_t *hs, const int32_t *ws, const float *strides,
                           int32_t n_levels, int32_t B, int32_t nc, void *y, void *stream) {
+  B2YDeviceGuard guard(b2y_device_of(y));
   return decode_launch(raw, hs, ws, strides, n_levels, B, nc, y, (cudaStream_t)stream);
 }

@@ -292,6 +292,7 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
                        const int32_t *classes, int32_t n_classes, void *workspace, size_t workspace_bytes, void *dets,
                        void *counts, void *kept_anchor, void *stream) {
   B2Y_REQUIRE(pred && dets && counts && workspace && B > 0 && nc > 0 && A > 0, B2Y_ERR_INVALID, "nms: bad arguments");
+  B2YDeviceGuard guard(b2y_device_of(pred));
   B2Y_REQUIRE(conf_thres >= 0.f && conf_thres <= 1.f, B2Y_ERR_INVALID,
               "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", (double)conf_thres);
   B2Y_REQUIRE(iou_thres >= 0.0 && iou_thres <= 1.0, B2Y_ERR_INVALID,
@@ -335,11 +336,8 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
   b2y_launch(nms_score_kernel, dim3(dim3(ceil_div(A, 256), B)), dim3(256), 0, st, p);
   B2Y_LAUNCH_CHECK();
   const size_t smem = SMEM_DYN;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2Y_CUDA_CHECK(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per device and cheap: set on every call (a once-per-process flag breaks the second GPU of a multi-device process)
+  B2Y_CUDA_CHECK(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   b2y_launch(nms_select_kernel, dim3(B), dim3(NT), smem, st, p);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
@@ -348,6 +346,7 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
 extern "C" int b2y_scale_boxes(void *dets, const void *counts, const void *geom, int32_t B, int32_t max_det,
                                void *stream) {
   B2Y_REQUIRE(dets && counts && geom && B > 0 && max_det > 0, B2Y_ERR_INVALID, "scale_boxes: bad arguments");
+  B2YDeviceGuard guard(b2y_device_of(dets));
   b2y_launch(scale_boxes_kernel, dim3(ceil_div(B * max_det, 256)), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<float *>(dets), reinterpret_cast<const int *>(counts), reinterpret_cast<const float *>(geom), B,
       max_det);

@@ -309,7 +309,7 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
                                int32_t device, b2y_plan **out) {
   B2Y_REQUIRE(ops && bufs && workspace && out && n_ops > 0 && n_bufs > 0 && batch > 0, B2Y_ERR_INVALID,
               "plan_create: bad arguments");
-  B2Y_CUDA_CHECK(cudaSetDevice(device));
+  B2YDeviceGuard guard(device);  // the caller's current device is restored on return
   b2y_plan *pl = new b2y_plan();
   pl->ws = reinterpret_cast<char *>(workspace);
   pl->ws_bytes = workspace_bytes;
@@ -364,6 +364,12 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
           }
           rc = conv_tc_plan_create(r.cp, device, TcConfig{0, 0}, &r.tc);
         }
+        if (impl != B2Y_IMPL_TCGEN05 && r.cp.epi_mode) {
+          b2y_set_error("op %d: fused Detect decode exists only in the tcgen05 conv epilogue (%s); lower the plan with "
+                        "fuse_decode=False", i, can_tc ? "SIMT forced" : why);
+          rc = B2Y_ERR_UNSUPPORTED;
+          break;
+        }
         r.impl = impl;
       }
     }
@@ -378,6 +384,7 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
 
 extern "C" int b2y_plan_destroy(b2y_plan *pl) {
   if (!pl) return B2Y_OK;
+  B2YDeviceGuard guard(pl->device);
   for (auto &r : pl->ops) {
     if (r.tc) conv_tc_plan_destroy(r.tc);
     if (r.pair) conv_pair_plan_destroy(r.pair);
@@ -392,6 +399,7 @@ extern "C" int b2y_plan_destroy(b2y_plan *pl) {
 
 extern "C" int b2y_plan_run(b2y_plan *pl, int32_t first, int32_t last, void *stream) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "plan_run: null plan");
+  B2YDeviceGuard guard(pl->device);
   const int n = (int)pl->ops.size();
   if (last < 0 || last > n) last = n;
   B2Y_REQUIRE(first >= 0 && first <= last, B2Y_ERR_INVALID, "plan_run: bad op range [%d,%d)", first, last);
@@ -507,6 +515,11 @@ int capture_lanes(b2y_plan *pl, cudaStream_t origin, int max_lanes) {
       if (e != cudaSuccess) { fail(e, "cudaStreamWaitEvent"); break; }
     }
     if (rc != B2Y_OK) break;
+    if (j == pl->mid_op && pl->mid_event) {
+      // the mid-point marker promises "every earlier op is done": join the tails of all other lanes before it is recorded
+      for (size_t L2 = 0; L2 < streams.size(); ++L2)
+        if ((int)L2 != L && lane_last[L2] >= 0 && ev[lane_last[L2]]) cudaStreamWaitEvent(streams[L], ev[lane_last[L2]], 0);
+    }
     rc = run_op(pl, pl->ops[j], j, streams[L]);
     if (rc != B2Y_OK) break;
     lane[j] = L;
@@ -537,6 +550,7 @@ int capture_lanes(b2y_plan *pl, cudaStream_t origin, int max_lanes) {
 
 extern "C" int b2y_plan_set_mid_op(b2y_plan *pl, int32_t op_index) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "set_mid_op: null plan");
+  B2YDeviceGuard guard(pl->device);
   B2Y_REQUIRE(op_index < (int)pl->ops.size(), B2Y_ERR_INVALID, "set_mid_op: op %d of %d", op_index, (int)pl->ops.size());
   B2Y_REQUIRE(!pl->graph_exec, B2Y_ERR_INVALID, "set_mid_op: call before b2y_plan_graph_build");
   if (op_index >= 0 && !pl->mid_event) B2Y_CUDA_CHECK(cudaEventCreateWithFlags(&pl->mid_event, cudaEventDisableTiming));
@@ -547,6 +561,7 @@ extern "C" int b2y_plan_set_mid_op(b2y_plan *pl, int32_t op_index) {
 
 extern "C" int b2y_plan_wait_mid(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "wait_mid: null plan");
+  B2YDeviceGuard guard(pl->device);
   if (pl->mid_event && pl->mid_op >= 0 && pl->mid_recorded)
     B2Y_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, pl->mid_event, 0));
   return B2Y_OK;
@@ -554,6 +569,7 @@ extern "C" int b2y_plan_wait_mid(b2y_plan *pl, void *stream) {
 
 extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "graph_build: null plan");
+  B2YDeviceGuard guard(pl->device);
   (void)stream;  // capture happens on a private stream: the caller's may be the legacy default stream, which cannot capture
   if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
   if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
@@ -606,6 +622,7 @@ extern "C" int b2y_plan_graph_build(b2y_plan *pl, void *stream) {
 
 extern "C" int b2y_plan_graph_launch(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl && pl->graph_exec, B2Y_ERR_INVALID, "graph_launch: graph not built");
+  B2YDeviceGuard guard(pl->device);
   B2Y_CUDA_CHECK(cudaGraphLaunch(pl->graph_exec, (cudaStream_t)stream));
   if (pl->mid_event && pl->mid_op >= 0) pl->mid_recorded = true;
   return B2Y_OK;
@@ -615,6 +632,7 @@ extern "C" int b2y_plan_graph_launch(b2y_plan *pl, void *stream) {
 // built and timed on the real buffers (their contents are overwritten by the next full run), the fastest is kept.
 extern "C" int b2y_plan_autotune(b2y_plan *pl, void *stream) {
   B2Y_REQUIRE(pl, B2Y_ERR_INVALID, "autotune: null plan");
+  B2YDeviceGuard guard(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0, e1;
   B2Y_CUDA_CHECK(cudaEventCreate(&e0));

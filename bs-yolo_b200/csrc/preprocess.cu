@@ -158,6 +158,7 @@ extern "C" int b2y_preprocess(const void *src, int32_t B, int32_t h, int32_t w, 
               "preprocess: letterbox geometry (%d,%d,%dx%d) does not fit %dx%d", top, left, uh, uw, H, W);
   B2Y_REQUIRE(dst_format >= 0 && dst_format <= 2, B2Y_ERR_INVALID, "preprocess: unknown dst_format %d", dst_format);
   B2Y_REQUIRE(dst_format != 0 || (H % 2 == 0 && W % 2 == 0), B2Y_ERR_INVALID, "preprocess: network input needs even H, W");
+  B2YDeviceGuard guard(b2y_device_of(dst));
   PreParams p;
   p.src = reinterpret_cast<const uint8_t *>(src);
   p.dst = dst;

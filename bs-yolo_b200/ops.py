@@ -128,15 +128,25 @@ def preprocess(images, imgsz=640, auto=True, stride=32, device="cuda"):
     return _letterbox_call(images, imgsz, auto, stride, device, 1)
 
 
-def scale_boxes_batched(dets: torch.Tensor, counts: torch.Tensor, img1_shape, img0_shapes):
-    """scale_boxes + clip_boxes (ops.py:92-127, 319-338) in place on padded dets (B, max_det, 6)."""
-    B, max_det, _ = dets.shape
+def scale_geometry(img1_shape, img0_shapes, device) -> torch.Tensor:
+    """Per-image (gain, padx, pady, w0, h0) rows of scale_boxes (ops.py:109-117) as one fp32 device tensor.  The values
+    are computed in Python doubles exactly like the reference and rounded to fp32 once; constant per (shape, shape) pair,
+    so pipelines build it once (a per-call pageable upload would stall the post-process stream)."""
     geom = []
     for (h0, w0) in img0_shapes:
         gain = min(img1_shape[0] / h0, img1_shape[1] / w0)
         padx = round((img1_shape[1] - w0 * gain) / 2 - 0.1)
         pady = round((img1_shape[0] - h0 * gain) / 2 - 0.1)
         geom.append([gain, padx, pady, w0, h0])
-    g = torch.tensor(geom, dtype=torch.float32).to(dets.device, non_blocking=True)
-    A.check(A.lib().b2y_scale_boxes(dets.data_ptr(), counts.data_ptr(), g.data_ptr(), B, max_det, _stream(dets.device)))
+    return torch.tensor(geom, dtype=torch.float32).to(device)
+
+
+def scale_boxes_batched(dets: torch.Tensor, counts: torch.Tensor, img1_shape=None, img0_shapes=None, geom: torch.Tensor | None = None):
+    """scale_boxes + clip_boxes (ops.py:92-127, 319-338) in place on padded dets (B, max_det, 6).  Pass a cached
+    ``geom`` (scale_geometry) on hot paths."""
+    B, max_det, _ = dets.shape
+    if geom is None:
+        geom = scale_geometry(img1_shape, img0_shapes, dets.device)
+    assert geom.shape == (B, 5) and geom.dtype == torch.float32 and geom.device == dets.device
+    A.check(A.lib().b2y_scale_boxes(dets.data_ptr(), counts.data_ptr(), geom.data_ptr(), B, max_det, _stream(dets.device)))
     return dets

@@ -22,7 +22,7 @@ import torch
 
 from . import _cabi as A
 from .engine import Engine, letterbox_geometry
-from .ops import nms_raw, scale_boxes_batched
+from .ops import nms_raw, scale_boxes_batched, scale_geometry
 
 
 class Ticket:
@@ -62,12 +62,14 @@ class DetectPipeline:
         self._last = None     # engine of the most recent forward()
         self._post_stream = torch.cuda.Stream(self.device)
         self._pre_stream = torch.cuda.Stream(self.device)
-        self._copy_stream = None
+        self._copy_stream = self._copy_stream2 = None
         self._fwd_done = [torch.cuda.Event() for _ in self.engines]
         self._pre_done = [torch.cuda.Event() for _ in self.engines]
         self._post_done = [torch.cuda.Event() for _ in self.engines]
         for e in self._post_done + self._fwd_done:
             e.record(torch.cuda.current_stream(self.device))
+        # scale_boxes geometry is constant per pipeline (fixed source shape): one upload here, none on the post stream
+        self._geom = scale_geometry((H, W), [self.src_shape] * batch, self.device)
 
     @property
     def launches_per_batch(self) -> int:
@@ -130,12 +132,13 @@ class DetectPipeline:
                 behind.wait_mid(post)
             dets, counts = nms_raw(eng.y, self.conf, self.iou, self.max_det, self.classes, self.agnostic)
             if t.rescale:
-                scale_boxes_batched(dets, counts, (self.H, self.W), [self.src_shape] * self.B)
+                scale_boxes_batched(dets, counts, geom=self._geom)
             if t.gather:
                 from .shard import gather_detections
-                dets, counts = gather_detections(dets, counts)
+                dets, counts = gather_detections(dets, counts, dst=0 if t.gather == "root" else None)
             if t.host_out is not None:
-                t.host_out[0].copy_(dets, non_blocking=True)
+                if t.host_out[0] is not None:
+                    t.host_out[0].copy_(dets, non_blocking=True)
                 t.host_out[1].copy_(counts, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(post)
@@ -165,33 +168,58 @@ class DetectPipeline:
         counts.record_stream(main)
         return dets, counts
 
-    def predict_host(self, frames: torch.Tensor, rescale: bool = False, gather: bool = False):
+    def predict_host(self, frames: torch.Tensor, rescale: bool = False, gather=False):
         """frames: pinned host uint8 (B,h,w,3). Returns host (dets, counts); blocks until they are valid."""
         return next(self.predict_stream(iter([frames]), rescale, gather))
 
-    def predict_stream(self, batches, rescale: bool = False, gather: bool = False):
+    def predict_stream(self, batches, rescale: bool = False, gather=False, device_dets: bool = False, uploaded=None):
         """Streaming end-to-end API (the analogue of ``predict(..., stream=True)``, engine/predictor.py:217-296): an
         iterable of pinned host uint8 batches (B,h,w,3) in, one host ``(dets, counts)`` pair per batch out, in order.
         The host->device copy of batch i+1 and the NMS + device->host copy of batch i-1 run on their own streams beside
         the network of batch i, and the result of batch i is handed out after batch i+1 has been enqueued, so neither
         PCIe nor the host-side wait idles the GPU.  The yielded tensors are pinned buffers that stay valid until two more
-        batches have been requested.  gather=True (multi-GPU): every rank receives all ranks' detections."""
+        batches have been requested.
+        gather (multi-GPU): False -- every rank yields its own shard; "root" -- rank 0 yields all ranks' detections
+        (world*B rows, rank-major; one NCCL gather of the padded detections per batch), the other ranks their own shard;
+        True / "all" -- every rank yields all ranks' detections (all-gather: world x the traffic, only if every rank
+        really consumes them).
+        device_dets: yield ``(dets on the device, counts on the host)`` -- for callers that keep boxes on the GPU (the
+        drop-in predictor builds ``Results`` from device views); only the counts cross PCIe.
+        uploaded: optional ``f(frames, event)`` called once the host->device copy of ``frames`` has been enqueued;
+        ``event`` completes when the copy has finished and the pinned buffer may be refilled (staging rings)."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
-        cs = self._copy_stream
+            self._copy_stream2 = torch.cuda.Stream(dev)
+        cs, cs2 = self._copy_stream, self._copy_stream2
+        split = int(os.environ.get("B2Y_H2D_SPLIT", "1")) >= 2  # A/B knob: the upload as two halves on two copy streams
         stage, copied, consumed, tickets, outs = [None, None], [None, None], [None, None], [None, None], [None, None]
+        half = [None, None]
         for k in range(2):
-            copied[k], consumed[k] = torch.cuda.Event(), torch.cuda.Event()
+            copied[k], consumed[k], half[k] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
         def upload(frames, k):
             if stage[k] is None or stage[k].shape != frames.shape:
                 stage[k] = torch.empty(frames.shape, dtype=torch.uint8, device=dev)
+            n = frames.shape[0] // 2
+            if split and n:
+                with torch.cuda.stream(cs2):
+                    cs2.wait_event(consumed[k])
+                    stage[k][n:].copy_(frames[n:], non_blocking=True)
+                    half[k].record(cs2)
             with torch.cuda.stream(cs):
                 cs.wait_event(consumed[k])  # the preprocess kernel that last read this slot has finished
-                stage[k].copy_(frames, non_blocking=True)
+                if split and n:
+                    stage[k][:n].copy_(frames[:n], non_blocking=True)
+                    cs.wait_event(half[k])
+                else:
+                    stage[k].copy_(frames, non_blocking=True)
                 copied[k].record(cs)
+                if uploaded is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    uploaded(frames, ev)
 
         it = iter(batches)
         nxt = next(it, None)
@@ -200,10 +228,11 @@ class DetectPipeline:
         consumed[0].record(main)
         consumed[1].record(main)
         upload(nxt, 0)
-        world = 1
+        rows = self.B
         if gather:
             import torch.distributed as dist
-            world = dist.get_world_size()
+            if gather != "root" or dist.get_rank() == 0:
+                rows = dist.get_world_size() * self.B
         i, pending = 0, None
         while nxt is not None:
             k = i & 1
@@ -211,14 +240,21 @@ class DetectPipeline:
             if nxt is not None:
                 upload(nxt, k ^ 1)  # overlaps the compute of batch i
             if outs[k] is None:
-                outs[k] = (torch.empty(world * self.B, self.max_det, 6, dtype=torch.float32).pin_memory(),
-                           torch.empty(world * self.B, dtype=torch.int32).pin_memory())
+                outs[k] = (None if device_dets else torch.empty(rows, self.max_det, 6, dtype=torch.float32).pin_memory(),
+                           torch.empty(rows, dtype=torch.int32).pin_memory())
             tickets[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k],
                                      src_ready=copied[k])
             if pending is not None:
-                tickets[pending].result()[2].synchronize()  # (enqueued by the submit above)
-                yield outs[pending]
+                yield self._resolve(tickets[pending], outs[pending], device_dets, main)  # (enqueued by the submit above)
             pending = k
             i += 1
-        tickets[pending].result()[2].synchronize()          # (flushes the last batch)
-        yield outs[pending]
+        yield self._resolve(tickets[pending], outs[pending], device_dets, main)           # (flushes the last batch)
+
+    @staticmethod
+    def _resolve(ticket, out, device_dets, main):
+        dets, _, ev = ticket.result()
+        ev.synchronize()
+        if not device_dets:
+            return out
+        dets.record_stream(main)  # allocated on the post-process stream, consumed by the caller's
+        return dets, out[1]

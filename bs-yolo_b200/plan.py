@@ -117,11 +117,12 @@ class Plan:
         if H % 32 or W % 32:
             raise ValueError(f"input {H}x{W} must be a multiple of the max stride 32 (utils/checks.py:120-171)")
         self.ir, self.H, self.W = ir, H, W
+        if os.environ.get("B2Y_FORCE_SIMT") == "1":  # debug knob: the whole plan on the CUDA-core validation twin
+            conv_impl = A.IMPL_SIMT
         self.conv_impl = conv_impl
         self.keep_fp32 = keep_fp32  # tests only: keep unrounded packed conv weights next to the bf16 blob
         # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
         self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
-        import os
         self.fuse_pairs = fuse_pairs and os.environ.get("B2Y_FUSE_PAIRS", "1") != "0"  # thin Bottlenecks as one kernel
         # EXPERIMENTAL, off by default: whole C3k2 blocks (cv1 -> Bottleneck -> cv2) as one kernel (csrc/c3k2_fused.cu)
         self.fuse_c3k2 = os.environ.get("B2Y_FUSE_C3K2", "0") == "1"
@@ -493,12 +494,19 @@ class Plan:
         self.A = sum(x.H * x.W for x in xs)
         self.y_buf = self.new_buf(self.A, 4 + nc, 1, A.F32, n["name"] + ".y")
         a_off = 0
+        # The fused decode lives in the tcgen05 conv epilogue, which needs cin % 16 == 0.  The box branch has c2 =
+        # max(16, ch0/4, 64) and the class branch c3 = max(ch0, min(nc, 100)) hidden channels (head.py:41-42): a width such as
+        # 100 (nc >= 100 on an n-scale model) is zero-padded to the next multiple of 16 by the producing conv (pad16); if a
+        # level still cannot take the tensor-core path the whole plan falls back to raw head maps + OP_DECODE (decode.cu).
+        fuse = self.fuse_decode
         for i, x in enumerate(xs):
-            t = self.conv(n["cv2"][i][1], self.conv(n["cv2"][i][0], x))
+            t = self.conv(n["cv2"][i][1], self.conv(n["cv2"][i][0], x), pad16=fuse)
             c3 = n["cv3"][i]
             s = self.conv(c3[0][1], self.conv(c3[0][0], x))
-            s = self.conv(c3[1][1], self.conv(c3[1][0], s))
-            if self.fuse_decode:
+            s = self.conv(c3[1][1], self.conv(c3[1][0], s), pad16=fuse)
+            if fuse and (t.c % 16 or s.c % 16):
+                raise NotImplementedError(f"{n['name']}: head conv input widths {t.c}/{s.c} cannot be padded to 16")
+            if fuse:
                 stride = float(n["stride"][i])
                 self.conv(n["cv2"][i][2], t, out_dtype=A.F32, decode=(1, a_off, stride))
                 self.conv(c3[2], s, out_dtype=A.F32, decode=(2, a_off, stride))
@@ -509,7 +517,7 @@ class Plan:
                 self.conv(n["cv2"][i][2], t, self.sub(head, 0, 64), out_dtype=A.F32)
                 self.conv(c3[2], s, self.sub(head, 64, nc), out_dtype=A.F32)
             a_off += x.H * x.W
-        if not self.fuse_decode:
+        if not fuse:
             op = OpSpec(A.OP_DECODE, n["name"] + ".decode", list(self.head_bufs), self.y_buf, cin=no, cout=4 + nc,
                         ip=(nc, len(xs)), fp=tuple(float(s) for s in n["stride"]))
             op.bytes_alg = self.A * (no * 4 + (4 + nc) * 4)

@@ -12,12 +12,23 @@ stage of ``BasePredictor.stream_inference`` (engine/predictor.py:217-296) runs o
     inference    (AutoBackend.forward -> DetectionModel._predict_once)    -> CUDA-graphed plan (b2y_plan_graph_launch)
     postprocess  (models/yolo/detect/predict.py:23-41)                    -> b2y_nms + b2y_scale_boxes
 
+A list of same-shape uint8 frames (``predict(list_of_ndarrays)``, batched file/video sources) takes the pipelined route:
+``preprocess`` only records the frames, ``inference`` streams them in chunks of ``B2Y_PREDICT_BATCH`` (64) through
+``DetectPipeline.predict_stream`` (pinned staging ring filled by a thread pool -> H2D -> preprocess -> network -> NMS ->
+scale_boxes, neighbouring chunks overlapped; boxes stay on the GPU, only the counts cross PCIe) and builds the
+``Results`` of chunk i under the GPU work of chunk i+1.  Ragged lists and tensor sources take the single-engine route.
+
 ``stream_inference`` itself is inherited, so callbacks, ``Results``, ``Results.speed`` and the per-predictor lock keep
 working.  There is no CPU fallback: a non-CUDA device, ``half=True``, ``augment``, ``visualize`` and ``embed`` raise.
 
 The reference package is imported lazily (it is not a dependency of the kernels or of bench.py).
 """
 from __future__ import annotations
+
+import os
+import queue
+import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -43,6 +54,80 @@ class PreprocessedBatch:
         return self.shape[0]
 
 
+class HostFrames:
+    """A list of same-shape uint8 BGR frames still in host memory (the common ``predict(list_of_ndarrays)`` /
+    batched-file-source case): ``inference`` streams them through a DetectPipeline in chunks -- pinned staging filled
+    by a thread pool, host->device copies, preprocess, network and NMS of neighbouring chunks overlapped."""
+
+    def __init__(self, frames, src_hw, canvas_hw, device):
+        self.frames = frames
+        self.src_hw, self.canvas_hw = src_hw, canvas_hw
+        self.shape = torch.Size((len(frames), 3, *canvas_hw))
+        self.device = device
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class _Staging:
+    """Ring of pinned (B,h,w,3) uint8 buffers filled by a worker thread (+ a copy pool: numpy releases the GIL while it
+    copies), so that staging chunk i+1 overlaps the GPU work of chunk i and the ``Results`` construction of chunk i-1.
+    A buffer is refilled only after the host->device copy that read it has completed (CUDA event from `uploaded`)."""
+
+    DEPTH = 4
+
+    def __init__(self, B, h, w):
+        self.B, self.h, self.w = B, h, w
+        self.bufs = [torch.empty(B, h, w, 3, dtype=torch.uint8).pin_memory() for _ in range(self.DEPTH)]
+        self.views = [b.numpy() for b in self.bufs]
+        self.free = [threading.Event() for _ in range(self.DEPTH)]
+        self.copied = [None] * self.DEPTH
+        for f in self.free:
+            f.set()
+        self.pool = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1)))
+
+    def uploaded(self, frames, event):  # called by DetectPipeline.predict_stream once the H2D copy has been enqueued
+        for r, b in enumerate(self.bufs):
+            if frames is b:
+                self.copied[r] = event
+                self.free[r].set()
+                return
+
+    def chunks(self, frames):
+        """Generator of pinned chunk tensors over `frames` (the last chunk is padded with stale rows)."""
+        n, B = len(frames), self.B
+        q: queue.Queue = queue.Queue(maxsize=2)
+
+        def fill_one(args):
+            dst, src = args
+            np.copyto(dst, src)
+
+        def produce():
+            try:
+                for c, lo in enumerate(range(0, n, B)):
+                    r = c % self.DEPTH
+                    self.free[r].wait()
+                    if self.copied[r] is not None:
+                        self.copied[r].synchronize()
+                        self.copied[r] = None
+                    self.free[r].clear()
+                    view = self.views[r]
+                    list(self.pool.map(fill_one, [(view[j - lo], frames[j]) for j in range(lo, min(lo + B, n))]))
+                    q.put(self.bufs[r])
+                q.put(None)
+            except BaseException as e:  # noqa: BLE001 -- surfaced in the consumer thread
+                q.put(e)
+
+        threading.Thread(target=produce, daemon=True).start()
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+
 class B200Backend:
     """Stands where ``AutoBackend`` stands (engine/predictor.py:308-321): the attributes the predictor reads
     (pt, triton, fp16, stride, names, device, imx, dynamic) and ``warmup`` / ``eval`` / ``__call__``."""
@@ -60,6 +145,7 @@ class B200Backend:
         self.nc = self.ir["nc"]
         self.use_graph = use_graph
         self._engines: dict[tuple[int, int, int], Engine] = {}
+        self._pipes: dict[tuple, tuple] = {}
 
     def engine(self, B: int, H: int, W: int) -> Engine:
         key = (B, H, W)
@@ -67,9 +153,26 @@ class B200Backend:
         if e is None:
             if len(self._engines) >= 4:  # a stream of changing shapes must not accumulate workspaces
                 self._engines.pop(next(iter(self._engines)))
-            e = Engine(self.ir, B, H, W, device=self.device, use_graph=self.use_graph)
+            with torch.cuda.device(self.device):
+                e = Engine(self.ir, B, H, W, device=self.device, use_graph=self.use_graph)
             self._engines[key] = e
         return e
+
+    def pipeline(self, B: int, src_hw, imgsz):
+        """(DetectPipeline, staging ring) for chunks of B same-shape frames; cached per (B, source shape, imgsz)."""
+        from .pipeline import DetectPipeline
+
+        key = (B, tuple(src_hw), tuple(imgsz))
+        hit = self._pipes.get(key)
+        if hit is None:
+            if len(self._pipes) >= 3:
+                self._pipes.pop(next(iter(self._pipes)))
+            with torch.cuda.device(self.device):
+                pipe = DetectPipeline(self.ir, B, tuple(imgsz), tuple(src_hw), device=self.device.index or 0, auto=True,
+                                      use_graph=self.use_graph)
+            hit = (pipe, _Staging(B, *src_hw))
+            self._pipes[key] = hit
+        return hit
 
     def eval(self):
         return self
@@ -79,14 +182,18 @@ class B200Backend:
         autotuned and graph-captured on first use instead, so there is nothing shape-independent to warm."""
 
     def __call__(self, im, augment=False, visualize=False, embed=None):
+        """AutoBackend.forward for a pt model returns the model's output: Detect's eval-mode ``(y, x)`` (head.py:74).
+        Here: ``(y, None)`` -- y (B, 4+nc, A) fp32; the raw per-level maps never exist (decode is fused into the head
+        convs' epilogues).  A (B,3,H,W) float tensor handed to the backend directly is space-to-depth'd into the input."""
         if augment or visualize or embed:
             raise NotImplementedError("augment / visualize / embed are not on the B200 detect path")
         if isinstance(im, PreprocessedBatch):
             eng = im.engine
-        else:  # a (B,3,H,W) float tensor handed to the backend directly
+        else:
             eng = self.engine(int(im.shape[0]), int(im.shape[2]), int(im.shape[3]))
             eng.set_input(im.float())
-        return eng.forward()  # (B, 4+nc, A) fp32 == Detect._inference's y (head.py:131)
+        with torch.cuda.device(self.device):
+            return eng.forward(), None
 
     forward = __call__
 
@@ -98,6 +205,8 @@ def _build_class():
 
     class B200DetectionPredictor(DetectionPredictor):
         """DetectionPredictor whose preprocess / inference / postprocess run as hand-written sm_100a kernels."""
+
+        max_chunk = int(os.environ.get("B2Y_PREDICT_BATCH", "64"))  # frames per pipelined chunk of a same-shape list
 
         def setup_model(self, model, verbose=True):
             if self.args.half:
@@ -124,32 +233,50 @@ def _build_class():
             H, W = geo[0][0], geo[0][1]
             if any((g[0], g[1]) != (H, W) for g in geo):
                 raise ValueError("letterboxed images of one batch must share one canvas size")
+            if same and self.model.stride == 32 and all(x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 3 for x in im):
+                # the hot case: nothing is copied here; `inference` streams the frames through the pipelined path
+                return HostFrames(im, shapes[0][:2], (H, W), dev)
             eng = self.model.engine(len(im), H, W)
             lib, st = A.lib(), torch.cuda.current_stream(dev).cuda_stream
             dst = eng.input_nhwc
-            if same:  # one H2D copy + one kernel for the whole batch
-                src = torch.from_numpy(np.ascontiguousarray(np.stack(im))).to(dev, non_blocking=True)
-                _, _, top, left, uh, uw = geo[0]
-                A.check(lib.b2y_preprocess(src.data_ptr(), len(im), shapes[0][0], shapes[0][1], dst.data_ptr(), H, W, top, left,
+            keep = []  # ragged batch: LetterBox(auto=False) per image into that image's slot of the input buffer
+            for i, x in enumerate(im):
+                src = torch.from_numpy(np.ascontiguousarray(x)).pin_memory().to(dev, non_blocking=True)
+                keep.append(src)
+                _, _, top, left, uh, uw = geo[i]
+                A.check(lib.b2y_preprocess(src.data_ptr(), 1, x.shape[0], x.shape[1], dst[i].data_ptr(), H, W, top, left,
                                            uh, uw, 0, st))
-                self._keep = src
-            else:  # ragged batch: LetterBox(auto=False) per image into that image's slot of the input buffer
-                keep = []
-                for i, x in enumerate(im):
-                    src = torch.from_numpy(np.ascontiguousarray(x)).to(dev, non_blocking=True)
-                    keep.append(src)
-                    _, _, top, left, uh, uw = geo[i]
-                    A.check(lib.b2y_preprocess(src.data_ptr(), 1, x.shape[0], x.shape[1], dst[i].data_ptr(), H, W, top, left,
-                                               uh, uw, 0, st))
-                self._keep = keep
+            self._keep = keep
             return PreprocessedBatch(eng)
 
         def inference(self, im, *args, **kwargs):
             if self.args.augment or self.args.visualize or self.args.embed:
                 raise NotImplementedError("augment / visualize / embed are not on the B200 detect path")
-            return self.model(im)
+            if not isinstance(im, HostFrames):
+                return self.model(im)
+            a = self.args
+            n = len(im)
+            B = min(n, self.max_chunk)
+            new_shape = tuple(self.imgsz) if not isinstance(self.imgsz, int) else (self.imgsz, self.imgsz)
+            pipe, staging = self.model.pipeline(B, im.src_hw, new_shape)
+            pipe.conf, pipe.iou, pipe.max_det = a.conf, a.iou, a.max_det
+            pipe.classes, pipe.agnostic = a.classes, bool(a.agnostic_nms)
+            names, paths, origs = self.model.names, self.batch[0], im.frames
+            results = []
+            with torch.cuda.device(self.device):
+                stream = pipe.predict_stream(staging.chunks(im.frames), rescale=True, device_dets=True,
+                                             uploaded=staging.uploaded)
+                for c, (dets, counts) in enumerate(stream):
+                    lo = c * B
+                    cnt = counts.tolist()
+                    # Results are built here, chunk by chunk, under the GPU work of the following chunks
+                    results.extend(Results(origs[lo + i], path=paths[lo + i], names=names, boxes=dets[i, : cnt[i]])
+                                   for i in range(min(B, n - lo)))
+            return results
 
         def postprocess(self, preds, img, orig_imgs):
+            if isinstance(img, HostFrames):  # already post-processed chunk by chunk in `inference`
+                return preds
             if isinstance(preds, (list, tuple)):
                 preds = preds[0]
             a = self.args

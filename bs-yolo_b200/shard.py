@@ -50,17 +50,63 @@ def tile_owner(t: int, world: int) -> int:
     return t % world
 
 
-def gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None):
-    """All-gather equal-sized shards of padded detections: (b, max_det, 6) fp32 + (b,) int32 per rank ->
-    (world*b, max_det, 6), (world*b,) on every rank, rank-major (== unit order for contiguous shards)."""
+def gather_detections(dets: torch.Tensor, counts: torch.Tensor, group=None, dst: int | None = None):
+    """Gather equal-sized shards of padded detections, (b, max_det, 6) fp32 + (b,) int32 per rank, rank-major (== unit
+    order for contiguous shards).  ``dst=None``: all-gather, every rank receives (world*b, ...).  ``dst=r``: only rank r
+    receives the whole set (one consumer: world x less traffic than the all-gather); the other ranks get their own shard
+    back unchanged."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    out_d = torch.empty((world * dets.shape[0], *dets.shape[1:]), dtype=dets.dtype, device=dets.device)
-    out_c = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
-    dist.all_gather_into_tensor(out_d, dets.contiguous(), group=group)
-    dist.all_gather_into_tensor(out_c, counts.contiguous(), group=group)
-    return out_d, out_c
+    if dst is None:
+        out_d = torch.empty((world * dets.shape[0], *dets.shape[1:]), dtype=dets.dtype, device=dets.device)
+        out_c = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
+        dist.all_gather_into_tensor(out_d, dets.contiguous(), group=group)
+        dist.all_gather_into_tensor(out_c, counts.contiguous(), group=group)
+        return out_d, out_c
+    rank = dist.get_rank(group)
+    # one packed message per rank: the counts ride in a trailing row block of the fp32 buffer (bit-cast, not converted)
+    b, k = dets.shape[0], dets.shape[1] * dets.shape[2]
+    packed = torch.empty(b, k + 1, dtype=torch.float32, device=dets.device)
+    packed[:, :k] = dets.reshape(b, k)
+    packed[:, k] = counts.view(torch.float32) if counts.dtype == torch.int32 else counts.to(torch.int32).view(torch.float32)
+    if rank == dst:
+        parts = [torch.empty_like(packed) for _ in range(world)]
+        dist.gather(packed, parts, dst=dst, group=group)
+        allp = torch.cat(parts, 0)
+        return (allp[:, :k].reshape(world * b, *dets.shape[1:]).contiguous(), allp[:, k].contiguous().view(torch.int32))
+    dist.gather(packed, None, dst=dst, group=group)
+    return dets, counts
+
+
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pin the calling process to the CPU cores of the NUMA node the GPU hangs off (NVML's ideal-CPU mask), so that the
+    pinned staging rings allocated afterwards are first-touched in local memory and the copy/launch threads do not cross
+    sockets.  Returns a short description (also when nothing could be done -- containers often hide the topology)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + j for i, w in enumerate(words) for j in range(64) if (w >> j) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return f"gpu{phys}: no narrower CPU set than the current {len(allowed)} cores"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu{phys}: bound to {len(cpus)} cores {min(cpus)}-{max(cpus)}"
+    except Exception as e:  # noqa: BLE001 -- binding is an optimisation, never a requirement
+        return f"not bound ({type(e).__name__}: {e})"
 
 
 def merge_prediction(dets: torch.Tensor, counts: torch.Tensor, origins: torch.Tensor, nc: int) -> torch.Tensor:

@@ -7,7 +7,8 @@
  *   walk the order; an unsuppressed box i is kept and suppresses every later unsuppressed j with
  *   inter/(area_i+area_j-inter) > thr, inter = max(0,xx2-xx1)*max(0,yy2-yy1), fp32 arithmetic, the
  *   fp32 quotient compared against the *double* threshold; returns kept indices in walk order.
- * Pinned against torchvision itself in tests/test_oracle_post.py and against tests/golden/nms_*.npz.
+ * Pinned against torchvision itself in tests/test_oracle_vs_reference.py (live, build container) and against the
+ * committed reference outputs tests/golden/nms.npz in tests/test_oracle_golden.py.
  *
  * Build: gcc -O2 -fPIC -shared -ffp-contract=off -o oracle/_build/liboracle.so oracle/nms_ref.c
  * (-ffp-contract=off: no FMA contraction, every op rounds to fp32 like the reference's scalar code). */

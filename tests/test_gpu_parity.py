@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 import torch
 
+import boxmatch
 import kat
 from bs_yolo_b200 import _cabi as A
 from bs_yolo_b200 import arch, ir, ops
@@ -264,25 +265,128 @@ def test_end_to_end_640_vs_oracle(model, B):
     n = counts.cpu().tolist()
     for i in range(B):
         assert dets[i, : n[i]].cpu().numpy().tobytes() == ref_same[i].tobytes()
-    # final boxes vs the all-fp32 oracle pipeline: IoU >= 0.99 and |dconf| <= 1e-2 for matched boxes
-    ref_dets = oracle_post.non_max_suppression(y_ref.numpy(), 0.25, 0.7, max_det=300)
-    matched = total = 0
+    # final boxes vs the all-fp32 oracle pipeline (north_star gate): every reference box matched at IoU >= 0.99 and
+    # |dconf| <= 1e-2, or its miss individually explained (tests/boxmatch.py); same for our extras against the
+    # reference's candidates.  Nothing may stay unexplained.
+    ref_dets = oracle_post.non_max_suppression(y_ref.numpy().copy(), 0.25, 0.7, max_det=300)
+    y_np, yref_np = y.cpu().numpy(), y_ref.numpy()
+    fwd = rev = None
     for i in range(B):
         ours, ref = dets[i, : n[i]].cpu().numpy(), ref_dets[i]
-        total += ref.shape[0]
-        for r in ref:
-            c = ours[ours[:, 5] == r[5]]
-            if not len(c):
-                continue
-            ix = np.maximum(0, np.minimum(c[:, 2], r[2]) - np.maximum(c[:, 0], r[0]))
-            iy = np.maximum(0, np.minimum(c[:, 3], r[3]) - np.maximum(c[:, 1], r[1]))
-            inter = ix * iy
-            iou = inter / ((c[:, 2] - c[:, 0]) * (c[:, 3] - c[:, 1]) + (r[2] - r[0]) * (r[3] - r[1]) - inter)
-            j = int(iou.argmax())
-            if iou[j] >= 0.99 and abs(c[j, 4] - r[4]) <= 1e-2:
-                matched += 1
-    # bf16 can flip candidates sitting within 1e-2 of the conf threshold or reorder near-tied NMS decisions
-    assert matched >= 0.9 * total, (matched, total)
+        a = boxmatch.audit(ref, ours, boxmatch.candidates(y_np[i], 0.25), 0.25, 0.7)
+        b = boxmatch.audit(ours, ref, boxmatch.candidates(yref_np[i], 0.25), 0.25, 0.7)
+        fwd, rev = (a, b) if fwd is None else (boxmatch.merge(fwd, a), boxmatch.merge(rev, b))
+    boxmatch.assert_gate(f"e2e_640_{model}:reference_boxes_in_ours", fwd)
+    boxmatch.assert_gate(f"e2e_640_{model}:our_boxes_in_reference", rev)
+
+
+def test_scale_boxes_bit_exact_vs_oracle():
+    """b2y_scale_boxes (scale_boxes + clip_boxes, utils/ops.py:92-127, 319-338) is elementwise IEEE fp32: bit-exact against
+    the oracle for landscape / portrait / up-scaled / odd-sized sources, boxes hanging over every border, empty images."""
+    rng = np.random.default_rng(17)
+    img1 = (384, 640)
+    img0s = [(360, 640), (1080, 1920), (481, 321), (37, 500), (97, 113), (384, 640), (2160, 3840), (100, 75)]
+    B, K = len(img0s), 300
+    d = rng.uniform(-40, 700, (B, K, 6)).astype(np.float32)
+    d[..., 2:4] = d[..., 0:2] + rng.uniform(0, 200, (B, K, 2)).astype(np.float32)
+    counts = np.array([300, 17, 0, 1, 299, 150, 300, 64], np.int32)
+    dev, cnt = torch.from_numpy(d).cuda(), torch.from_numpy(counts).cuda()
+    ops.scale_boxes_batched(dev, cnt, img1, img0s)
+    got = dev.cpu().numpy()
+    for b in range(B):
+        ref = oracle_post.scale_boxes(img1, d[b, : counts[b]], img0s[b])
+        assert got[b, : counts[b]].tobytes() == ref.tobytes(), f"image {b} ({img0s[b]})"
+        assert got[b, counts[b]:].tobytes() == d[b, counts[b]:].tobytes()  # rows past the count are left alone
+    geom = ops.scale_geometry(img1, img0s, dev.device)   # cached-geometry call path (pipelines)
+    dev2 = torch.from_numpy(d).cuda()
+    ops.scale_boxes_batched(dev2, cnt, geom=geom)
+    assert torch.equal(dev2, dev)
+
+
+@pytest.mark.parametrize("src,dst", [((100, 75), 160), ((37, 50), 128), ((240, 320), 640)])
+def test_letterbox_upscaling_vs_oracle(src, dst):
+    """Up-scaling LetterBox (scaleup=True, augment.py:1575-1586): the oracle's integer emulation of cv2 INTER_LINEAR is
+    exact when down-scaling (golden fixtures); when up-scaling OpenCV's SIMD path may differ by 1 LSB on <= 0.1 % of the
+    pixels (SURVEY a1 fine print) -- against the oracle itself the kernel must be bit-exact."""
+    img = np.random.default_rng(src[0]).integers(0, 256, (*src, 3), dtype=np.uint8)
+    got = ops.letterbox([img], dst, auto=False).cpu().numpy()[0]
+    ref = oracle_post.letterbox(img, (dst, dst), auto=False)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_sppf_pool_kernel_vs_torch():
+    """sppf_pool_kernel (SPPF's three chained 5x5 max-pools, block.py:3145-3149) at kernel level: exact (max of bf16
+    values), written into the 3 channel slices of the concat buffer, the first slice untouched; odd map, C not x64."""
+    import torch.nn.functional as F
+    from bs_yolo_b200.engine import Engine
+    from bs_yolo_b200.plan import OpSpec, Plan
+    for c_, H, W in ((128, 20, 20), (24, 13, 27), (384, 40, 40)):
+        plan = Plan.empty(64, 64)
+        sb = plan.new_buf(4 * c_, H, W, name="cat")
+        s = plan.full(sb, 4 * c_)
+        op = OpSpec(A.OP_SPPF_POOL, "pool", [plan.sub(s, 0, c_)], plan.sub(s, c_, 3 * c_), cin=c_, cout=3 * c_)
+        plan.ops.append(op)
+        B = 3
+        eng = Engine(None, B, 64, 64, use_graph=False, plan=plan)
+        x = torch.randn(B, H, W, 4 * c_, generator=torch.Generator().manual_seed(c_)).to(torch.bfloat16)
+        eng.buffer(sb).copy_(x)
+        eng.forward()
+        torch.cuda.synchronize()
+        got = eng.buffer(sb).float().cpu()
+        y = [x[..., :c_].float().permute(0, 3, 1, 2)]
+        for _ in range(3):
+            y.append(F.max_pool2d(y[-1], 5, 1, 2))
+        ref = torch.cat(y, 1).permute(0, 2, 3, 1)
+        assert torch.equal(got, ref), (c_, H, W)
+
+
+@pytest.mark.parametrize("nh,N_hw,B", [(2, (20, 20), 3), (6, (40, 40), 2), (6, (13, 21), 1)])
+def test_attention_kernel_vs_torch(nh, N_hw, B):
+    """C2PSA attention core (block.py:4277-4286) at kernel level, including yolo11x@1280's size (nh = 6, N = 1600):
+    softmax(Q^T K / sqrt(kd)) V on the same bf16 qkv operand, against fp32 torch.  Tolerance: the probabilities are
+    rounded to bf16 for the P.V GEMM (rel-L2 <= 6e-3 measured bound 1e-2 of north_star)."""
+    from bs_yolo_b200.engine import Engine
+    from bs_yolo_b200.plan import OpSpec, Plan
+    kd, hd = 32, 64
+    H, W = N_hw
+    N = H * W
+    plan = Plan.empty(64, 64)
+    qb = plan.new_buf(nh * (2 * kd + hd), H, W, name="qkv")
+    ob = plan.new_buf(nh * hd, H, W, name="out")
+    plan.ops.append(OpSpec(A.OP_ATTN, "attn", [plan.full(qb)], plan.full(ob), cin=nh * (2 * kd + hd), cout=nh * hd,
+                           ip=(nh, kd, hd)))
+    eng = Engine(None, B, 64, 64, use_graph=False, plan=plan)
+    qkv = (torch.randn(B, H, W, nh * (2 * kd + hd), generator=torch.Generator().manual_seed(nh * N)) * 1.5).to(torch.bfloat16)
+    eng.buffer(qb).copy_(qkv)
+    eng.forward()
+    torch.cuda.synchronize()
+    got = eng.buffer(ob).float().cpu().reshape(B, N, nh, hd)
+    t = qkv.float().reshape(B, N, nh, 2 * kd + hd).permute(0, 2, 3, 1)  # (B, nh, 2kd+hd, N)
+    q, k, v = t.split([kd, kd, hd], dim=2)
+    attn = ((q.transpose(-2, -1) @ k) * kd ** -0.5).softmax(-1)
+    ref = (v @ attn.transpose(-2, -1)).permute(0, 3, 1, 2)  # (B, N, nh, hd)
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel < 1e-2, rel
+
+
+def test_yolo11x_1280_heads_vs_oracle():
+    """BASELINE.json configs[3] at its real size: stock yolo11x @ 1280x1280 (B = 1): the three raw head maps against the
+    fp32 oracle, rel-L2 <= 1e-2 per level (north_star bf16 gate); C2PSA runs with nh = 6, N = 1600; fused decode ==
+    unfused decode on the same network."""
+    g = _graph("yolo11x")
+    x = torch.from_numpy(np.random.default_rng(11).random((1, 3, 1280, 1280), dtype=np.float32))
+    eng = _run_engine(g, x, fuse_decode=False)
+    y_ref, raws_ref = oracle_net.forward(g, x)
+    for i, r in enumerate(raws_ref):
+        got = eng.raw(i).permute(0, 3, 1, 2).float().cpu()
+        rel = float((got - r).norm() / r.norm())
+        assert rel < 1e-2, (i, rel)
+    assert eng.A == 33600
+    y_unfused = eng.y.clone()
+    del eng
+    fused = _run_engine(g, x)
+    assert float((fused.y[:, :4] - y_unfused[:, :4]).abs().max()) < 4e-2   # px at stride <= 32 on a 1280 canvas
+    assert float((fused.y[:, 4:] - y_unfused[:, 4:]).abs().max()) < 1e-5
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])

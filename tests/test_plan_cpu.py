@@ -141,3 +141,27 @@ def test_bsyolo_wiring_follows_yaml_literally():
     plan = Plan(_graph("bsyolo_n"), 640, 640)
     assert plan.layer_out[21].c == 448  # 64 + the 384-channel Concat output of layer 13
     assert plan.bufs[plan.y_buf].H == 16 and plan.A == 8400
+
+
+@pytest.mark.parametrize("force_simt", [False, True])
+def test_detect_head_width_not_multiple_of_16(force_simt, monkeypatch):
+    """nc = 100 on an n-scale model gives a class-branch width c3 = max(ch0, min(nc, 100)) = 100 (head.py:42): the fused
+    decode convs get cin padded to 112 by their producer; with the CUDA-core twin forced (B2Y_FORCE_SIMT=1) the plan
+    falls back to raw head maps + the decode kernel.  Either way the lowered plan reproduces the oracle."""
+    if force_simt:
+        monkeypatch.setenv("B2Y_FORCE_SIMT", "1")
+    spec = arch.build_spec("yolo11n", nc=100)
+    g = ir.build_ir(spec, arch.synth_state_dict(spec, 3))
+    plan = Plan(g, 64, 64, keep_fp32=True)
+    dec = [o for o in plan.ops if o.kind == A.OP_CONV and len(o.ip) > 1 and o.ip[1]]
+    if force_simt:
+        assert not dec and plan.ops[-1].kind == A.OP_DECODE and all(o.impl == A.IMPL_SIMT for o in plan.ops if o.kind == A.OP_CONV)
+        assert not any(o.kind == A.OP_CONV_PAIR for o in plan.ops)
+    else:
+        assert len(dec) == 6 and all(o.cin % 16 == 0 for o in dec) and {o.cin for o in dec if o.ip[1] == 2} == {112}
+    x = torch.from_numpy(np.random.default_rng(1).random((1, 3, 64, 64), dtype=np.float32))
+    emu = PlanEmulator(plan, 1)
+    emu.set_input(x)
+    emu.run()
+    y, _ = oracle_net.forward(g, x)
+    assert float((emu.y() - y).abs().max()) < 1e-3
