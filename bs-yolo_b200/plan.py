@@ -78,7 +78,8 @@ class OpSpec:
     ip: tuple = ()
     fp: tuple = ()
     flops: int = 0        # 2*MAC, per image
-    bytes_alg: int = 0    # algorithmic bytes (in + out + weights), per image (weights counted once)
+    bytes_alg: int = 0    # algorithmic bytes (in + out + weights) of ONE image; a batch of B moves bytes_batch(B)
+    bytes_w: int = 0      # the weight part of bytes_alg: read once per batch, not once per image
     w_fp32: Any = None    # tests only (Plan(keep_fp32=True))
 
 
@@ -196,12 +197,14 @@ class Plan:
                 op.w_fp32 = wp.reshape(cpad, -1).clone()
             op.flops = 2 * c2 * c1 * kh * kw * Ho * Wo
             esz = 4 if out_dtype == A.F32 else 2
-            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * esz + c2 * c1 * kh * kw * 2
+            op.bytes_w = c2 * c1 * kh * kw * 2
+            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * esz + op.bytes_w
             if decode is not None:
                 mode, a_off, stride = decode
                 op.ip, op.fp = (0, mode, a_off, self.A, self.nc), (float(stride),)
                 rows = 4 if mode == 1 else c2
-                op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + c2 * c1 * 2
+                op.bytes_w = c2 * c1 * 2
+                op.bytes_alg = c1 * x.H * x.W * 2 + rows * Ho * Wo * 4 + op.bytes_w
         elif (self.dw_dense and g == c1 == c2 and (kh, kw) == (3, 3) and (sh, sw) in ((1, 1), (2, 2)) and (ph, pw) == (1, 1)
               and c1 % 16 == 0 and c1 <= int(os.environ.get("B2Y_DW_DENSE_MAXC", 128)) and x.c == c1 and self.conv_impl != A.IMPL_SIMT
               and (sh == 1 or (x.H % 2 == 0 and x.W % 2 == 0))):
@@ -218,7 +221,8 @@ class Plan:
             op = self.ops[-1]
             op.ip = (0, 0, 0, 0, 0, 1)
             op.flops = 2 * c2 * kh * kw * Ho * Wo
-            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + c2 * kh * kw * 2
+            op.bytes_w = c2 * kh * kw * 2
+            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + op.bytes_w
             return out
         else:
             assert g == c1 == c2, f"{n['name']}: only depthwise grouped convs are on the hot path"
@@ -230,7 +234,8 @@ class Plan:
                         A.IMPL_SIMT, self.blob.add(wp.numpy().astype(np.float32)),
                         self.blob.add(b.numpy().astype(np.float32)))
             op.flops = 2 * c2 * kh * kw * Ho * Wo
-            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + c2 * kh * kw * 2
+            op.bytes_w = c2 * kh * kw * 2
+            op.bytes_alg = c1 * x.H * x.W * 2 + c2 * Ho * Wo * 2 + op.bytes_w
         self.ops.append(op)
         return dest
 
@@ -257,7 +262,8 @@ class Plan:
         if self.keep_fp32:
             op.w_fp32 = wp.reshape(cpad, -1).clone()
         op.flops = 2 * c2 * 27 * Ho * Wo
-        op.bytes_alg = 3 * self.H * self.W * 2 + c2 * Ho * Wo * 2 + c2 * 27 * 2
+        op.bytes_w = c2 * 27 * 2
+        op.bytes_alg = 3 * self.H * self.W * 2 + c2 * Ho * Wo * 2 + op.bytes_w
         self.ops.append(op)
         return dest
 
@@ -295,7 +301,8 @@ class Plan:
             if self.keep_fp32:
                 op.w_fp32 = (w1.reshape(chid, -1).clone(), w2.reshape(c2, -1).clone())
             op.flops = 2 * 9 * x.H * x.W * (cv1["c2"] * c1 + c2 * cv1["c2"])
-            op.bytes_alg = (c1 + c2) * x.H * x.W * 2 + 9 * (cv1["c2"] * c1 + c2 * cv1["c2"]) * 2
+            op.bytes_w = 9 * (cv1["c2"] * c1 + c2 * cv1["c2"]) * 2
+            op.bytes_alg = (c1 + c2) * x.H * x.W * 2 + op.bytes_w
             self.ops.append(op)
             return dest
         t = self.conv(cv1, x, pad16=True)
@@ -391,7 +398,8 @@ class Plan:
             op.w_fp32 = (w0.clone(), w1.reshape(chid, -1).clone(), w2.reshape(c, -1).clone(), w3.clone())
         hw = x.H * x.W
         op.flops = 2 * hw * (2 * c * cin + 9 * (b1["c2"] * c + c * b1["c2"]) + cout * 3 * c)
-        op.bytes_alg = (cin + cout) * hw * 2 + (2 * c * cin + 18 * b1["c2"] * c + cout * 3 * c) * 2
+        op.bytes_w = (2 * c * cin + 18 * b1["c2"] * c + cout * 3 * c) * 2
+        op.bytes_alg = (cin + cout) * hw * 2 + op.bytes_w
         self.ops.append(op)
         return dest
 
@@ -462,7 +470,7 @@ class Plan:
         self.ops.append(OpSpec(A.OP_MSCA_GATE, n["name"] + ".se", [gap], gate, cin=c, cout=c,
                                p_off=(self.blob.add(se_w.numpy().astype(np.float32)),
                                       self.blob.add(se_b.numpy().astype(np.float32)), -1, -1),
-                               flops=2 * 4 * c * c, bytes_alg=4 * c * c * 4))
+                               flops=2 * 4 * c * c, bytes_alg=4 * c * c * 4, bytes_w=4 * c * c * 4))
         xa = self.full(self.new_buf(c, x.H, x.W, name=n["name"] + ".xatt"), c)
         self.ops.append(OpSpec(A.OP_WSUM4, n["name"] + ".wsum", list(br), xa, res=gate, cin=c, cout=c,
                                bytes_alg=5 * c * x.H * x.W * 2))
@@ -696,4 +704,13 @@ class Plan:
 
     # ------------------------------------------------------------------ roofline accounting
     def work_per_image(self) -> tuple[int, int]:
+        """(FLOPs, algorithmic bytes) of one image at batch 1 (weights included once)."""
         return sum(o.flops for o in self.ops), sum(o.bytes_alg for o in self.ops)
+
+    @staticmethod
+    def op_bytes(o: OpSpec, B: int) -> int:
+        """Algorithmic bytes of op `o` for a batch of B images: activations scale with B, weights are read once."""
+        return (o.bytes_alg - o.bytes_w) * B + o.bytes_w
+
+    def work_per_batch(self, B: int) -> tuple[int, int]:
+        return B * sum(o.flops for o in self.ops), sum(self.op_bytes(o, B) for o in self.ops)

@@ -144,3 +144,79 @@ def sahi_predict(pipe, frame_u8: torch.Tensor, tile: int = 640, overlap: float =
     pred = merge_prediction(dets, counts, org, pipe.engine.nc)
     md, mc = nms_raw(pred, pipe.conf, pipe.iou if iou is None else iou, pipe.max_det)
     return md[0], mc[0], (dets, counts, org)
+
+
+class SahiSharder:
+    """BASELINE.json config 5 across the GPUs of one box: every rank owns one frame per step, slices it into SAHI tiles
+    on its GPU, and the tiles are sharded round-robin (tile t -> GPU t mod world) with ONE all_to_all of uint8 tiles;
+    every GPU then runs its tile batch (``per`` tiles of each of the ``world`` frames) through the detect pipeline, the
+    padded per-tile detections return to the frame owners with a second all_to_all, and each owner merges its frame with
+    one global class-aware NMS (`merge_prediction` + the same NMS kernel as the per-image NMS).  These two exchanges are
+    the only cross-GPU traffic (world == 1: none).  Host logic only -- `make_pipe(B)` builds the per-GPU detector (a
+    DetectPipeline on the GPU; any callable ``tiles (B,t,t,3) uint8 -> (dets (B,K,6), counts (B,))`` in the CPU tests)."""
+
+    def __init__(self, make_pipe, frame_hw, tile: int = 640, world: int = 1, rank: int = 0, group=None, overlap: float = 0.0,
+                 iou: float | None = None, nms_fn=None):
+        self.H, self.W = frame_hw
+        self.tile, self.world, self.rank, self.group = tile, world, rank, group
+        self.origins = sahi_tiles(self.H, self.W, tile, overlap)
+        self.T = len(self.origins)
+        self.per = -(-self.T // world)              # tiles of one frame per GPU (the last GPUs may get a padding tile)
+        self.B = self.per * world                   # tile batch per GPU and step: `per` tiles from each of `world` frames
+        # destination-major send order: block d = this frame's tiles for GPU d (tile_owner), padded with -1
+        self.send_order = []
+        for d in range(world):
+            mine = [t for t in range(self.T) if tile_owner(t, world) == d]
+            self.send_order += mine + [-1] * (self.per - len(mine))
+        self.pipe = make_pipe(self.B)
+        self.max_det = getattr(self.pipe, "max_det", 300)
+        self.nc = self.pipe.engine.nc if hasattr(self.pipe, "engine") else getattr(self.pipe, "nc")
+        self.conf = getattr(self.pipe, "conf", 0.25)
+        self.iou = iou if iou is not None else getattr(self.pipe, "iou", 0.7)
+        self._nms = nms_fn
+        self._dev_cache = None
+
+    def _consts(self, device):
+        if self._dev_cache is None or self._dev_cache[0] != device:
+            valid = torch.tensor([t >= 0 for t in self.send_order], device=device)
+            org = torch.tensor([self.origins[max(t, 0)] for t in self.send_order], dtype=torch.float32, device=device)
+            # permutation that puts the received results back into tile order (ties in the merge NMS break by index, so the
+            # merged result equals the single-GPU one bit for bit); padding slots go last
+            order = sorted(range(self.B), key=lambda i: (self.send_order[i] < 0, self.send_order[i]))
+            self._dev_cache = (device, valid, org, torch.tensor(order, device=device))
+        return self._dev_cache[1:]
+
+    def slice_tiles(self, frame: torch.Tensor) -> torch.Tensor:
+        t = self.tile
+        return torch.stack([frame[y:y + t, x:x + t] for x, y in (self.origins[max(i, 0)] for i in self.send_order)])
+
+    def predict_frame(self, frame_u8: torch.Tensor):
+        """frame_u8 (H,W,3) uint8 BGR on this rank's device -> (dets (max_det,6) in frame coordinates, count) for THIS
+        rank's frame.  Collective: every rank of the group calls it once per step."""
+        import torch.distributed as dist
+
+        assert tuple(frame_u8.shape) == (self.H, self.W, 3) and frame_u8.dtype == torch.uint8
+        tiles = self.slice_tiles(frame_u8)
+        if self.world > 1:
+            recv = torch.empty_like(tiles)
+            dist.all_to_all_single(recv, tiles, group=self.group)   # block s of recv: my share of rank s's frame
+            tiles = recv
+        dets, counts = self.pipe(tiles)
+        K = dets.shape[1]
+        if self.world > 1:
+            packed = torch.empty(self.B, K * 6 + 1, dtype=torch.float32, device=dets.device)
+            packed[:, :K * 6] = dets.reshape(self.B, K * 6)
+            packed[:, K * 6] = counts.to(torch.int32).view(torch.float32)   # bit-cast: the count rides in the fp32 message
+            back = torch.empty_like(packed)
+            dist.all_to_all_single(back, packed, group=self.group)  # block d of back: GPU d's results for my frame's tiles
+            dets = back[:, :K * 6].reshape(self.B, K, 6)
+            counts = back[:, K * 6].contiguous().view(torch.int32)
+        valid, org, order = self._consts(dets.device)
+        counts = torch.where(valid, counts.to(torch.int32), torch.zeros_like(counts, dtype=torch.int32))
+        dets, counts, org = dets.index_select(0, order), counts.index_select(0, order), org.index_select(0, order)
+        pred = merge_prediction(dets, counts, org, self.nc)
+        nms = self._nms
+        if nms is None:
+            from .ops import nms_raw as nms
+        md, mc = nms(pred, self.conf, self.iou, self.max_det)
+        return md[0], mc[0]

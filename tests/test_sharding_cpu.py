@@ -129,3 +129,123 @@ def test_tile_merge_prediction_feeds_global_nms():
         from ultralytics.utils import ops
         r = ops.non_max_suppression(torch.from_numpy(pred.numpy().copy()), 0.25, 0.5, max_det=300)[0].numpy()
         assert out.tobytes() == r.tobytes()
+
+
+def _worker_root(rank, world, port, n_units, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard.shard_range(n_units, world, rank)
+        g = torch.Generator().manual_seed(99)
+        all_d = torch.rand(n_units, 5, 6, generator=g)
+        all_c = torch.randint(0, 6, (n_units,), generator=g, dtype=torch.int32)
+        d, c = shard.gather_detections(all_d[lo:hi], all_c[lo:hi], dst=0)  # one consumer: only rank 0 gets everything
+        if rank == 0:
+            ok = torch.equal(d, all_d) and torch.equal(c, all_c) and c.dtype == torch.int32
+        else:
+            ok = torch.equal(d, all_d[lo:hi]) and torch.equal(c, all_c[lo:hi])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_detections_to_root_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_root, args=(r, 2, port, 8, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
+class _FakeTileDetector:
+    """Stands in for a DetectPipeline in the CPU tests of SahiSharder: deterministic detections derived from the tile's
+    pixels only (so a tile yields the same boxes whichever rank and batch slot runs it)."""
+
+    max_det, nc, conf, iou = 6, 3, 0.25, 0.5
+
+    def __init__(self, B):
+        self.B = B
+
+    def __call__(self, tiles):
+        assert tiles.shape[0] == self.B and tiles.dtype == torch.uint8
+        B, K = self.B, self.max_det
+        dets = torch.zeros(B, K, 6)
+        counts = torch.zeros(B, dtype=torch.int32)
+        for b in range(B):
+            h = int(tiles[b].to(torch.int64).sum()) % 1000003
+            g = torch.Generator().manual_seed(h)
+            n = int(torch.randint(1, K + 1, (1,), generator=g))
+            xy = torch.rand(n, 2, generator=g) * 40
+            wh = torch.rand(n, 2, generator=g) * 20 + 4
+            dets[b, :n, :2], dets[b, :n, 2:4] = xy, xy + wh
+            dets[b, :n, 4] = torch.rand(n, generator=g).sort(descending=True).values * 0.7 + 0.3
+            dets[b, :n, 5] = torch.randint(0, self.nc, (n,), generator=g).float()
+            counts[b] = n
+        return dets, counts
+
+
+def _oracle_nms(pred, conf, iou, max_det):
+    out = oracle_post.non_max_suppression(pred.numpy().copy(), conf, iou, max_det=max_det)[0]
+    d = torch.zeros(1, max_det, 6)
+    d[0, : len(out)] = torch.from_numpy(out)
+    return d, torch.tensor([len(out)], dtype=torch.int32)
+
+
+def _sahi_frames(world):
+    return [torch.from_numpy(np.random.default_rng(70 + r).integers(0, 256, (150, 230, 3), dtype=np.uint8)) for r in range(world)]
+
+
+def _worker_sahi(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = shard.SahiSharder(_FakeTileDetector, (150, 230), 64, world=world, rank=rank, nms_fn=_oracle_nms)
+        d, c = sh.predict_frame(_sahi_frames(world)[rank])
+        q.put((rank, d.numpy().tobytes(), int(c), sh.B, sh.per))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sahi_sharder_exchange_equals_single_gpu_merge(world):
+    """Tiles sharded over `world` ranks (all_to_all out, detections all_to_all back, merge at the frame owner) give, bit
+    for bit, the single-process merge of every rank's frame (a 150x230 frame has 3 x 4 = 12 tiles of 64: 6 or 4 per rank;
+    tile counts that do not divide are covered by test_sahi_sharder_pads_uneven_tile_counts)."""
+    single = shard.SahiSharder(_FakeTileDetector, (150, 230), 64, world=1, rank=0, nms_fn=_oracle_nms)
+    assert single.T == 12 and single.B == 12
+    want = [single.predict_frame(f) for f in _sahi_frames(world)]
+    assert all(int(c) > 0 for _, c in want)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sahi, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, blob, cnt, B, per in res:
+        assert (B, per) == (12, 12 // world)
+        assert cnt == int(want[rank][1]) and blob == want[rank][0].numpy().tobytes(), f"rank {rank}"
+
+
+def test_sahi_sharder_pads_uneven_tile_counts():
+    sh = shard.SahiSharder(_FakeTileDetector, (100, 170), 64, world=1, rank=0, nms_fn=_oracle_nms)
+    assert sh.T == 6
+    # 6 tiles over 4 ranks: 2 per rank, ranks 2 and 3 carry one padding slot each (never merged)
+    sh4 = shard.SahiSharder(lambda B: _FakeTileDetector(B), (100, 170), 64, world=4, rank=0, nms_fn=_oracle_nms)
+    assert (sh4.per, sh4.B) == (2, 8) and sh4.send_order == [0, 4, 1, 5, 2, -1, 3, -1]
+    valid, org, order = sh4._consts(torch.device("cpu"))
+    assert valid.tolist() == [True, True, True, True, True, False, True, False]
+    assert [sh4.send_order[i] for i in order.tolist()] == [0, 1, 2, 3, 4, 5, -1, -1]
