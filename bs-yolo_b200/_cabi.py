@@ -7,16 +7,16 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2y.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 BF16, F32 = 0, 1
 (OP_CONV, OP_DWCONV, _OP_RESERVED3, OP_SPPF_POOL, OP_RESAMPLE, OP_ATTN, OP_ROWCOL_MEAN, OP_ELA_GATE, OP_ELA_APPLY, OP_GAP4,
- OP_MSCA_GATE, OP_WSUM4, OP_DECODE, OP_CONV_PAIR, OP_C3K2) = range(1, 16)
+ OP_MSCA_GATE, OP_WSUM4, OP_DECODE, OP_CONV_PAIR, OP_C3K2, OP_PMSFA_DW, OP_MSCA_BRANCH) = range(1, 18)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 RES_NONE, RES_ADD, RES_MUL, RES_PREADD_UP2 = 0, 1, 2, 3
 OP_NAMES = {1: "conv", 2: "dwconv", 4: "sppf_pool", 5: "resample", 6: "attn", 7: "rowcol_mean", 8: "ela_gate",
-            9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode", 14: "conv_pair", 15: "c3k2"}
+            9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode", 14: "conv_pair", 15: "c3k2", 16: "pmsfa_dw", 17: "msca_branch"}
 
 
 class Buf(C.Structure):

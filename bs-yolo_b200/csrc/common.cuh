@@ -192,14 +192,33 @@ int c3k2_plan_create(const C3k2Params &p, int device, C3k2Plan **out);
 void c3k2_plan_destroy(C3k2Plan *p);
 int launch_c3k2(const C3k2Plan *p, cudaStream_t st);
 
+// fused depthwise tail of a PMSFA block, pmsfa_dw.cu
+struct PmsfaParams {
+  const bf16 *in; int in_cs;
+  bf16 *out; int out_cs;
+  const float *w2, *b2, *w3, *b3;  // conv2 [25][c/2], [c/2]; conv3 [49][c/4], [c/4]
+  int B, H, W, c;
+};
+int launch_pmsfa_dw(const PmsfaParams &p, cudaStream_t st);
+
+// MSCAAttention up to the four branch maps + their global average pools, msca.cu
+struct MscaParams {
+  const bf16 *in; int in_cs;
+  bf16 *out; int out_cs;          // four branch maps: channel slices [jC, (j+1)C) of `out`
+  float *gap;                     // (B, 4, C) fp32
+  const float *params;            // packed, see plan.msca
+  int B, H, W, C;
+};
+int launch_msca_branch(const MscaParams &p, cudaStream_t st);
+
 int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, cudaStream_t st);
 int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, int scale,
                     cudaStream_t st);
 int launch_attention(const bf16 *qkv, int qkv_cs, bf16 *out, int out_cs, int B, int N, int nh, int kd, int hd,
                      cudaStream_t st);
-int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, float *rowm, float *colm, cudaStream_t st);
+int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, int nbands, float *rowm, float *colm, cudaStream_t st);
 int launch_ela_gate(const float *rowm, const float *colm, const float *params, int c, int B, int H, int W, int ks,
-                    int groups, float eps, float *hgate, float *wgate, float *chgate, cudaStream_t st);
+                    int groups, float eps, int nbands, float *hgate, float *wgate, float *chgate, cudaStream_t st);
 int launch_ela_apply(const bf16 *x, int cs, bf16 *out, int out_cs, int c, int B, int H, int W, const float *hgate,
                      const float *wgate, const float *chgate, float ch_c, float sp_c, float res_c, cudaStream_t st);
 int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, float *gap, cudaStream_t st);

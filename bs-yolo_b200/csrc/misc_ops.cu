@@ -128,7 +128,97 @@ __global__ void rowcol_mean_kernel(const bf16 *__restrict__ x, int cs, int c, in
   }
 }
 
-int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, float *rowm, float *colm, cudaStream_t st) {
+// Banded single-pass variant (the fast path; C in {64,128,256}, W*C/8 <= 1024): one CTA = 8 rows of one image, read
+// ONCE with fully coalesced 16-byte loads.  Thread t owns the 16-byte chunks t and t + 512 of every row (chunk k = pixel
+// k / (C/8), channel octet k % (C/8); 512 % (C/8) == 0, so a thread's octet and columns are the same in every row):
+// column sums accumulate in registers, row sums are reduced by warp shuffles over the lanes that share an octet and then
+// across the 16 warps through shared memory in a fixed order (deterministic).  The column sums of the band are written as
+// partial sums colm[b][w][band][c] (already divided by H); ela_gate adds the bands.
+constexpr int ELA_BAND = 8, ELA_NT = 512, ELA_R = 4;
+
+__global__ void __launch_bounds__(ELA_NT) ela_stats_kernel(const bf16 *__restrict__ x, int cs, int c, int H, int W, int nbands,
+                                                           float *__restrict__ rowm, float *__restrict__ colm) {
+  pdl_launch_dependents();
+  extern __shared__ float red[];  // [ELA_R][16 warps][c]
+  const int b = blockIdx.x / nbands, band = blockIdx.x % nbands;
+  const int n_oct = c >> 3, cpr = W * n_oct;  // 16-byte chunks per row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int o = tid % n_oct;
+  const int h0 = band * ELA_BAND, h1 = min(h0 + ELA_BAND, H);
+  const bool has[2] = {tid < cpr, tid + ELA_NT < cpr};
+  const int wq[2] = {tid / n_oct, (tid + ELA_NT) / n_oct};
+  float cs_acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs_acc[j][i] = 0.f;
+  const bf16 *img = x + (size_t)b * H * W * cs + o * 8;
+  pdl_wait();
+  for (int r0 = h0; r0 < h1; r0 += ELA_R) {
+    uint4 v[ELA_R][2];
+#pragma unroll
+    for (int r = 0; r < ELA_R; ++r)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        v[r][j] = (r0 + r < h1 && has[j]) ? __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(r0 + r) * W + wq[j]) * cs))
+                                           : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int r = 0; r < ELA_R; ++r) {
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float f[8];
+        unpack8(v[r][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rs[i] += f[i];
+          cs_acc[j][i] += f[i];
+        }
+      }
+      for (int st = n_oct; st < 32; st <<= 1)  // lanes l, l ^ st share the octet (n_oct is a power of two <= 32)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], st);
+      if (lane < n_oct) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[(r * (ELA_NT / 32) + warp) * c + lane * 8 + i] = rs[i];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < ELA_R * c; i += ELA_NT) {
+      const int r = i / c, ch = i % c;
+      if (r0 + r < h1) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ELA_NT / 32; ++w) s += red[(r * (ELA_NT / 32) + w) * c + ch];
+        rowm[((size_t)b * H + r0 + r) * c + ch] = s / (float)W;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    if (has[j]) {
+      float *d = colm + (((size_t)b * W + wq[j]) * nbands + band) * c + o * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = cs_acc[j][i] / (float)H;
+    }
+}
+
+bool ela_fast_path(int c, int W, int cs, const void *x) {
+  return (c == 64 || c == 128 || c == 256) && W * (c >> 3) <= 2 * ELA_NT && cs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, int nbands, float *rowm, float *colm, cudaStream_t st) {
+  if (nbands >= 1) {  // the planner asked for the banded layout of colm (it applies the same shape test)
+    B2Y_REQUIRE(ela_fast_path(c, W, cs, x) && nbands == ceil_div(H, ELA_BAND), B2Y_ERR_INVALID,
+                "ELA stats: banded layout requested for an unsupported shape (c %d, W %d, bands %d)", c, W, nbands);
+    const size_t smem = (size_t)ELA_R * (ELA_NT / 32) * c * sizeof(float);
+    if (smem > 48 * 1024)
+      B2Y_CUDA_CHECK(cudaFuncSetAttribute(ela_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    b2y_launch(ela_stats_kernel, dim3(B * nbands), dim3(ELA_NT), smem, st, x, cs, c, H, W, nbands, rowm, colm);
+    B2Y_LAUNCH_CHECK();
+    return B2Y_OK;
+  }
   const int bt = c >= 128 ? 128 : 64;
   dim3 grid(H + W, ceil_div(c, bt), B);
   b2y_launch(rowcol_mean_kernel, dim3(grid), dim3(bt), 0, st, x, cs, c, H, W, rowm, colm);
@@ -141,27 +231,36 @@ int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, float 
 //   chgate[b,ch]     = sigmoid(ch_w[ch][centre] * mean(x[b,:,:,ch]))  (ELA.py:49-58: Conv1d on a length-1 sequence)
 __global__ void __launch_bounds__(256) ela_gate_kernel(const float *__restrict__ rowm, const float *__restrict__ colm,
                                                        const float *__restrict__ params, int c, int H, int W, int ks,
-                                                       int groups, float eps, float *__restrict__ hgate,
+                                                       int groups, float eps, int nbands, float *__restrict__ hgate,
                                                        float *__restrict__ wgate, float *__restrict__ chgate) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];  // conv outputs for this group: [cpg][L]
+  extern __shared__ float sm[];  // conv outputs for this group: [cpg][L], then the group's means [L][cpg]
   __shared__ float red[64];
   const int b = blockIdx.x / groups, g = blockIdx.x % groups;
   const int cpg = c / groups;
   const float *sp_w = params, *gn_w = params + (size_t)c * ks, *gn_b = gn_w + c, *ch_w = gn_b + c;
   for (int dir = 0; dir < 2; ++dir) {
     const int L = dir == 0 ? H : W;
-    const float *src = (dir == 0 ? rowm : colm) + (size_t)b * L * c;
+    const int nb = dir == 0 ? 1 : nbands;  // column means arrive as per-band partial sums: add them in band order
+    const float *src = (dir == 0 ? rowm : colm) + (size_t)b * L * nb * c;
     float *dst = (dir == 0 ? hgate : wgate) + (size_t)b * L * c;
     const int n = cpg * L;
+    float *mean_s = sm + cpg * (H > W ? H : W);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
+      float m = 0.f;
+      for (int k = 0; k < nb; ++k) m += src[((size_t)l * nb + k) * c + ch];
+      mean_s[i] = m;
+    }
+    __syncthreads();
     float s1 = 0.f, s2 = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
       float a = 0.f;
       for (int t = 0; t < ks; ++t) {
         const int ll = l + 2 * t - (ks - 1);  // dilation 2, padding ks-1
-        if (ll >= 0 && ll < L) a = fmaf(sp_w[ch * ks + t], src[(size_t)ll * c + ch], a);
+        if (ll >= 0 && ll < L) a = fmaf(sp_w[ch * ks + t], mean_s[ll * cpg + ci], a);
       }
       sm[i] = a;
       s1 += a;
@@ -203,12 +302,13 @@ __global__ void __launch_bounds__(256) ela_gate_kernel(const float *__restrict__
 }
 
 int launch_ela_gate(const float *rowm, const float *colm, const float *params, int c, int B, int H, int W, int ks,
-                    int groups, float eps, float *hgate, float *wgate, float *chgate, cudaStream_t st) {
+                    int groups, float eps, int nbands, float *hgate, float *wgate, float *chgate, cudaStream_t st) {
   B2Y_REQUIRE(c % groups == 0, B2Y_ERR_INVALID, "ELA: channels %d not divisible by groups %d", c, groups);
   const int L = H > W ? H : W;
-  const size_t smem = (size_t)(c / groups) * L * sizeof(float);
+  const size_t smem = (size_t)(c / groups) * L * sizeof(float) * 2;
   B2Y_REQUIRE(smem <= 48 * 1024, B2Y_ERR_UNSUPPORTED, "ELA gate: group tile too large");
-  b2y_launch(ela_gate_kernel, dim3(B * groups), dim3(256), smem, st, rowm, colm, params, c, H, W, ks, groups, eps, hgate, wgate, chgate);
+  b2y_launch(ela_gate_kernel, dim3(B * groups), dim3(256), smem, st, rowm, colm, params, c, H, W, ks, groups, eps,
+             nbands < 1 ? 1 : nbands, hgate, wgate, chgate);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -239,9 +339,74 @@ __global__ void __launch_bounds__(256) ela_apply_kernel(const bf16 *__restrict__
   *reinterpret_cast<uint4 *>(out + (size_t)pix * out_cs + c0) = pack8(v);
 }
 
+// Fast path (same shapes as ela_stats_kernel): CTA = 8 rows of one image, thread = the 16-byte chunks t, t + 512 of every
+// row.  A thread's column gate and channel gate are loop invariants held in registers; per row it reads one 32-byte row
+// gate (shared by all threads of its octet: L1 hits), so the kernel moves 16 B in + 16 B out per chunk and little else --
+// the per-pixel version above re-read 96 B of gates for every 16 B of x.
+__global__ void __launch_bounds__(ELA_NT) ela_apply_band_kernel(const bf16 *__restrict__ x, int cs, bf16 *__restrict__ out,
+                                                                int out_cs, int c, int H, int W, int nbands,
+                                                                const float *__restrict__ hgate, const float *__restrict__ wgate,
+                                                                const float *__restrict__ chgate, float ch_c, float sp_c,
+                                                                float res_c) {
+  pdl_launch_dependents();
+  const int b = blockIdx.x / nbands, band = blockIdx.x % nbands;
+  const int n_oct = c >> 3, cpr = W * n_oct;
+  const int tid = threadIdx.x, o = tid % n_oct;
+  const int h0 = band * ELA_BAND, h1 = min(h0 + ELA_BAND, H);
+  const bool has[2] = {tid < cpr, tid + ELA_NT < cpr};
+  const int wq[2] = {tid / n_oct, (tid + ELA_NT) / n_oct};
+  pdl_wait();
+  float a[8], wg[2][8];
+  {
+    const float4 c0 = __ldg(reinterpret_cast<const float4 *>(chgate + (size_t)b * c + o * 8));
+    const float4 c1 = __ldg(reinterpret_cast<const float4 *>(chgate + (size_t)b * c + o * 8) + 1);
+    const float cg[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = ch_c * cg[i];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float *g = wgate + ((size_t)b * W + (has[j] ? wq[j] : 0)) * c + o * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4 *>(g)), g1 = __ldg(reinterpret_cast<const float4 *>(g) + 1);
+      wg[j][0] = g0.x; wg[j][1] = g0.y; wg[j][2] = g0.z; wg[j][3] = g0.w;
+      wg[j][4] = g1.x; wg[j][5] = g1.y; wg[j][6] = g1.z; wg[j][7] = g1.w;
+    }
+  }
+  const bf16 *img = x + (size_t)b * H * W * cs + o * 8;
+  bf16 *oimg = out + (size_t)b * H * W * out_cs + o * 8;
+  uint4 v[ELA_BAND][2];
+#pragma unroll
+  for (int r = 0; r < ELA_BAND; ++r)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (h0 + r < h1 && has[j]) v[r][j] = __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(h0 + r) * W + wq[j]) * cs));
+#pragma unroll
+  for (int r = 0; r < ELA_BAND; ++r) {
+    if (h0 + r >= h1) break;
+    const float *hgp = hgate + ((size_t)b * H + h0 + r) * c + o * 8;
+    const float4 h0v = __ldg(reinterpret_cast<const float4 *>(hgp)), h1v = __ldg(reinterpret_cast<const float4 *>(hgp) + 1);
+    const float hg[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (has[j]) {
+        float f[8];
+        unpack8(v[r][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = f[i] * (a[i] + sp_c * (hg[i] * wg[j][i])) + res_c * f[i];
+        *reinterpret_cast<uint4 *>(oimg + ((size_t)(h0 + r) * W + wq[j]) * out_cs) = pack8(f);
+      }
+  }
+}
+
 int launch_ela_apply(const bf16 *x, int cs, bf16 *out, int out_cs, int c, int B, int H, int W, const float *hgate,
                      const float *wgate, const float *chgate, float ch_c, float sp_c, float res_c, cudaStream_t st) {
   B2Y_REQUIRE(c % 8 == 0 && cs % 8 == 0 && out_cs % 8 == 0, B2Y_ERR_UNSUPPORTED, "ELA apply: channels must be x8");
+  if (ela_fast_path(c, W, cs, x) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int nbands = ceil_div(H, ELA_BAND);
+    b2y_launch(ela_apply_band_kernel, dim3(B * nbands), dim3(ELA_NT), 0, st, x, cs, out, out_cs, c, H, W, nbands, hgate, wgate,
+               chgate, ch_c, sp_c, res_c);
+    B2Y_LAUNCH_CHECK();
+    return B2Y_OK;
+  }
   const long long total = (long long)B * H * W * (c / 8);
   b2y_launch(ela_apply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, cs, out, out_cs, c, total, H, W, hgate, wgate,
                                                                     chgate, ch_c, sp_c, res_c);

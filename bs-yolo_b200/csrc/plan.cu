@@ -237,14 +237,14 @@ int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
       const b2y_buf *bi = R.buf(o.in[0]);
       if (!R.ok) return B2Y_ERR_INVALID;
       return launch_rowcol_mean(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C, o.cin, pl->B,
-                                bi->H, bi->W, reinterpret_cast<float *>(R.ptr(o.out, 0)),
+                                bi->H, bi->W, o.ip[0], reinterpret_cast<float *>(R.ptr(o.out, 0)),
                                 reinterpret_cast<float *>(R.ptr(o.in[1], 0)), st);
     }
     case B2Y_OP_ELA_GATE:
       return launch_ela_gate(reinterpret_cast<const float *>(R.ptr(o.in[0], 0)),
                              reinterpret_cast<const float *>(R.ptr(o.in[1], 0)),
                              reinterpret_cast<const float *>(R.wptr(o.p_off[0])), o.cin, pl->B, o.ip[2], o.ip[3],
-                             o.ip[0], o.ip[1], o.fp[0], reinterpret_cast<float *>(R.ptr(o.out, 0)),
+                             o.ip[0], o.ip[1], o.fp[0], o.ip[4], reinterpret_cast<float *>(R.ptr(o.out, 0)),
                              reinterpret_cast<float *>(R.ptr(o.in[2], 0)), reinterpret_cast<float *>(R.ptr(o.in[3], 0)),
                              st);
     case B2Y_OP_ELA_APPLY: {
@@ -280,6 +280,37 @@ int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
                               reinterpret_cast<const float *>(R.wptr(o.p_off[0])),
                               reinterpret_cast<const float *>(R.wptr(o.p_off[1])), o.cin, pl->B,
                               reinterpret_cast<float *>(R.ptr(o.out, 0)), st);
+    case B2Y_OP_PMSFA_DW: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      B2Y_REQUIRE(bi->dtype == B2Y_BF16 && bo->dtype == B2Y_BF16 && bi->H == bo->H && bi->W == bo->W && o.cin == o.cout &&
+                      o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C && o.in[0] != o.out,
+                  B2Y_ERR_INVALID, "op %d: fused PMSFA depthwise views", idx);
+      PmsfaParams q;
+      q.in = reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])); q.in_cs = bi->C;
+      q.out = reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)); q.out_cs = bo->C;
+      q.w2 = reinterpret_cast<const float *>(R.wptr(o.w_off)); q.b2 = reinterpret_cast<const float *>(R.wptr(o.b_off));
+      q.w3 = reinterpret_cast<const float *>(R.wptr(o.p_off[0])); q.b3 = reinterpret_cast<const float *>(R.wptr(o.p_off[1]));
+      B2Y_REQUIRE(q.w2 && q.b2 && q.w3 && q.b3, B2Y_ERR_INVALID, "op %d: fused PMSFA depthwise needs both weight sets", idx);
+      q.B = pl->B; q.H = bi->H; q.W = bi->W; q.c = o.cin;
+      return launch_pmsfa_dw(q, st);
+    }
+    case B2Y_OP_MSCA_BRANCH: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out), *bg = R.buf(o.res);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      B2Y_REQUIRE(bi->dtype == B2Y_BF16 && bo->dtype == B2Y_BF16 && bg->dtype == B2Y_F32 && bi->H == bo->H && bi->W == bo->W &&
+                      o.cout == 4 * o.cin && o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C &&
+                      bg->C * bg->H * bg->W >= 4 * o.cin,
+                  B2Y_ERR_INVALID, "op %d: fused MSCA branch views", idx);
+      MscaParams q;
+      q.in = reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])); q.in_cs = bi->C;
+      q.out = reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)); q.out_cs = bo->C;
+      q.gap = reinterpret_cast<float *>(R.ptr(o.res, 0));
+      q.params = reinterpret_cast<const float *>(R.wptr(o.w_off));
+      B2Y_REQUIRE(q.params, B2Y_ERR_INVALID, "op %d: fused MSCA branch needs its packed parameters", idx);
+      q.B = pl->B; q.H = bi->H; q.W = bi->W; q.C = o.cin;
+      return launch_msca_branch(q, st);
+    }
     case B2Y_OP_DECODE: {
       const void *raw[4];
       int32_t hs[4], wsz[4];
@@ -442,6 +473,17 @@ void op_regions(const b2y_plan *pl, const ResolvedOp &r, std::vector<Region> &ou
   if (o.kind == B2Y_OP_CONV_PAIR || o.kind == B2Y_OP_C3K2) {
     out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
     out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
+    return;
+  }
+  if (o.kind == B2Y_OP_PMSFA_DW) {
+    out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
+    out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
+    return;
+  }
+  if (o.kind == B2Y_OP_MSCA_BRANCH) {
+    out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
+    out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
+    whole(o.res, true);
     return;
   }
   if (o.kind == B2Y_OP_SPPF_POOL) {

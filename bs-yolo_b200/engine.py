@@ -52,7 +52,7 @@ class Engine:
         self.offsets = [b.offset for b in bufs]
         with torch.cuda.device(self.device):
             self.ws = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=self.device)
-            blob = self.plan.blob.tobytes()
+            blob = self.plan.blob.tobytes() or bytes(256)  # (plans of weight-less ops only: unit tests)
             self.weights = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device)
             handle = C.c_void_p()
             A.check(self.lib.b2y_plan_create(ops, len(ops), bufs, len(bufs), self.ws.data_ptr(), ws_bytes,

@@ -62,6 +62,11 @@ class DetectPipeline:
         self._last = None     # engine of the most recent forward()
         self._post_stream = torch.cuda.Stream(self.device)
         self._pre_stream = torch.cuda.Stream(self.device)
+        # B2Y_DUAL_NET=1: the network graphs of consecutive batches (one per slot) run on their own streams, i.e. two
+        # batches are in flight at once -- the thin, latency-bound P4/P5 and head layers of one graph fill the dependency
+        # bubbles of the other.  Default: both on the caller's stream (batch i+1's network starts when batch i's ended).
+        self.dual_net = len(self.engines) >= 2 and os.environ.get("B2Y_DUAL_NET", "0") == "1"
+        self._net_streams = [torch.cuda.Stream(self.device) for _ in self.engines] if self.dual_net else None
         self._copy_stream = self._copy_stream2 = None
         self._fwd_done = [torch.cuda.Event() for _ in self.engines]
         self._pre_done = [torch.cuda.Event() for _ in self.engines]
@@ -107,10 +112,17 @@ class DetectPipeline:
                 consumed.record(pre)
         if self._pending is not None and self._pending.slot == k:
             self._post(self._pending, None)      # (single slot: its y is about to be overwritten)
-        main.wait_event(self._pre_done[k])
-        main.wait_event(self._post_done[k])  # the NMS that last read this slot's y has finished
-        eng.forward()
-        self._fwd_done[k].record(main)
+        net = main
+        if self.dual_net:
+            net = self._net_streams[k]
+            ordered = torch.cuda.Event()
+            ordered.record(main)
+            net.wait_event(ordered)          # keeps the caller's stream order (everything enqueued before this submit)
+        net.wait_event(self._pre_done[k])
+        net.wait_event(self._post_done[k])   # the NMS that last read this slot's y has finished
+        with torch.cuda.stream(net):
+            eng.forward()
+            self._fwd_done[k].record(net)
         self._last = eng
         ticket = Ticket(self, k, rescale, gather, host_out)
         if self.defer:
@@ -156,7 +168,7 @@ class DetectPipeline:
         """flush() and make the current stream wait for every slot's post-process (the end of a timed region)."""
         self.flush()
         main = torch.cuda.current_stream(self.device)
-        for e in self._post_done:
+        for e in self._post_done + self._fwd_done:
             main.wait_event(e)
 
     def __call__(self, src_u8: torch.Tensor, rescale: bool = False, consumed: torch.cuda.Event | None = None):

@@ -309,8 +309,28 @@ class Plan:
         return self.conv(cv2, t, dest, res=x if n["add"] else None, res_mode=A.RES_ADD if n["add"] else A.RES_NONE)
 
     def pmsfa(self, n, x, dest):
+        """PMSFA (block.py:3035-3053).  Default: conv1 (tensor cores) -> ONE fused depthwise kernel (OP_PMSFA_DW: conv2 5x5 on
+        the first half, conv3 7x7 on its first quarter, the cat) -> conv4 (+ x in the epilogue).  B2Y_FUSE_PMSFA=0 or the
+        CUDA-core twin: one launch per conv plus the cat copy."""
         c = n["c"]
         cat = self.full(self.new_buf(c, x.H, x.W, name=n["name"] + ".cat"), c)
+        fused = (self.conv_impl != A.IMPL_SIMT and os.environ.get("B2Y_FUSE_PMSFA", "1") != "0" and c in (16, 32, 64, 128)
+                 and all(n[k]["act"] == "silu" and n[k]["s"] == (1, 1) for k in ("conv2", "conv3"))
+                 and n["conv2"]["k"] == (5, 5) and n["conv3"]["k"] == (7, 7))
+        if fused:
+            t = self.conv(n["conv1"], x)  # [a | b | h]
+            c2, c3 = n["conv2"], n["conv3"]
+            w2 = c2["weight"].reshape(c // 2, 25).t().contiguous().numpy().astype(np.float32)
+            w3 = c3["weight"].reshape(c // 4, 49).t().contiguous().numpy().astype(np.float32)
+            op = OpSpec(A.OP_PMSFA_DW, n["name"] + ".dw", [t], cat, cin=c, cout=c, act=1,
+                        w_off=self.blob.add(w2), b_off=self.blob.add(c2["bias"].numpy().astype(np.float32)),
+                        p_off=(self.blob.add(w3), self.blob.add(c3["bias"].numpy().astype(np.float32)), -1, -1))
+            hw = x.H * x.W
+            op.flops = 2 * hw * (25 * (c // 2) + 49 * (c // 4))
+            op.bytes_w = (25 * (c // 2) + 49 * (c // 4)) * 4
+            op.bytes_alg = 2 * c * hw * 2 + op.bytes_w
+            self.ops.append(op)
+            return self.conv(n["conv4"], cat, dest, res=x, res_mode=A.RES_ADD)
         self.conv(n["conv1"], x, cat)
         t2 = self.conv(n["conv2"], self.sub(cat, 0, c // 2))
         self.conv(n["conv3"], self.sub(t2, 0, c // 4), self.sub(cat, 0, c // 4))
@@ -449,21 +469,48 @@ class Plan:
     def scdown(self, n, x, dest):
         return self.conv(n["cv2"], self.conv(n["cv1"], x), dest)
 
+    MSCA_STRIPS = (5, 7, 11, 21)
+
     def msca(self, n, x, dest):
+        """MSCAAttention (MSCA.py:52-88).  Default: ONE kernel up to the four branch maps and their global average pools
+        (OP_MSCA_BRANCH), then the SE gate, the gate-weighted sum and conv4 (x u in the epilogue).  B2Y_FUSE_MSCA=0, the
+        CUDA-core twin, or a map too large for shared memory: one launch per depthwise conv + the pooling kernel."""
         c = n["c"]
-        attn = self.conv(n["conv0"], x)
         s, t = n["dilconv"]["weight"].reshape(c), n["dilconv"]["bias"]
-        br = []
-        for b in range(4):
-            u = self.conv(n[f"conv{b}_1"], attn)
-            n2 = n[f"conv{b}_2"]
-            wb = None
-            if b < 3:  # fold the shared per-channel 1x1 "dilconv" (MSCA.py:28-29,57,61,65) into the strip conv
-                wb = (n2["weight"] * s.view(c, 1, 1, 1), n2["bias"] * s + t)
-            br.append(self.conv(n2, u, wb=wb))
-        gap = self.new_buf(4 * c, 1, 1, A.F32, n["name"] + ".gap")
-        self.ops.append(OpSpec(A.OP_GAP4, n["name"] + ".gap", list(br), gap, cin=c, cout=c,
-                               bytes_alg=4 * c * x.H * x.W * 2))
+        strips = [(n[f"conv{b}_1"]["k"], n[f"conv{b}_2"]["k"]) for b in range(4)]
+        fused = (self.conv_impl != A.IMPL_SIMT and os.environ.get("B2Y_FUSE_MSCA", "1") != "0" and c % 8 == 0
+                 and x.H * x.W <= 1600 and x.real == x.c == c and n["conv0"]["k"] == (5, 5)
+                 and strips == [((1, k), (k, 1)) for k in self.MSCA_STRIPS])
+        if fused:
+            rows = [n["conv0"]["weight"].reshape(c, 25).t(), n["conv0"]["bias"].reshape(1, c)]
+            for b, k in enumerate(self.MSCA_STRIPS):
+                n1, n2 = n[f"conv{b}_1"], n[f"conv{b}_2"]
+                w2, b2 = n2["weight"].reshape(c, k), n2["bias"]
+                if b < 3:  # fold the shared per-channel 1x1 "dilconv" (MSCA.py:28-29,57,61,65) into the second strip
+                    w2, b2 = w2 * s.view(c, 1), b2 * s + t
+                rows += [n1["weight"].reshape(c, k).t(), n1["bias"].reshape(1, c), w2.t(), b2.reshape(1, c)]
+            params = torch.cat(rows, 0).contiguous()
+            assert params.shape == (122, c)
+            br4 = self.full(self.new_buf(4 * c, x.H, x.W, name=n["name"] + ".branches"), 4 * c)
+            gap = self.new_buf(4 * c, 1, 1, A.F32, n["name"] + ".gap")
+            hw = x.H * x.W
+            self.ops.append(OpSpec(A.OP_MSCA_BRANCH, n["name"] + ".branches", [x], br4, res=gap, cin=c, cout=4 * c,
+                                   w_off=self.blob.add(params.numpy().astype(np.float32)),
+                                   flops=2 * 113 * c * hw, bytes_alg=5 * c * hw * 2 + 122 * c * 4, bytes_w=122 * c * 4))
+            br = [self.sub(br4, b * c, c) for b in range(4)]
+        else:
+            attn = self.conv(n["conv0"], x)
+            br = []
+            for b in range(4):
+                u = self.conv(n[f"conv{b}_1"], attn)
+                n2 = n[f"conv{b}_2"]
+                wb = None
+                if b < 3:  # fold the shared per-channel 1x1 "dilconv" (MSCA.py:28-29,57,61,65) into the strip conv
+                    wb = (n2["weight"] * s.view(c, 1, 1, 1), n2["bias"] * s + t)
+                br.append(self.conv(n2, u, wb=wb))
+            gap = self.new_buf(4 * c, 1, 1, A.F32, n["name"] + ".gap")
+            self.ops.append(OpSpec(A.OP_GAP4, n["name"] + ".gap", list(br), gap, cin=c, cout=c,
+                                   bytes_alg=4 * c * x.H * x.W * 2))
         gate = self.new_buf(4 * c, 1, 1, A.F32, n["name"] + ".gate")
         se_w = torch.stack([n[f"SE{j}"]["weight"].reshape(c, c) for j in range(1, 5)])
         se_b = torch.stack([n[f"SE{j}"]["bias"] for j in range(1, 5)])
@@ -480,17 +527,20 @@ class Plan:
         c, ks = n["c"], n["ks"]
         if dest is None:
             dest = self.full(self.new_buf(c, x.H, x.W, name=n["name"]), c)
+        # banded single-pass statistics (misc_ops.cu:ela_stats_kernel): colm holds per-band partial column means
+        banded = c in (64, 128, 256) and x.W * (c // 8) <= 1024 and x.coff % 8 == 0 and self.bufs[x.buf].C % 8 == 0
+        nb = -(-x.H // 8) if banded else 0
         rowm = self.new_buf(c, x.H, 1, A.F32, n["name"] + ".rowm")
-        colm = self.new_buf(c, x.W, 1, A.F32, n["name"] + ".colm")
-        self.ops.append(OpSpec(A.OP_ROWCOL_MEAN, n["name"] + ".means", [x, colm], rowm, cin=c, cout=c,
-                               bytes_alg=2 * c * x.H * x.W * 2))
+        colm = self.new_buf(c, x.W, max(nb, 1), A.F32, n["name"] + ".colm")
+        self.ops.append(OpSpec(A.OP_ROWCOL_MEAN, n["name"] + ".means", [x, colm], rowm, cin=c, cout=c, ip=(nb,),
+                               bytes_alg=c * x.H * x.W * 2))
         hg = self.new_buf(c, x.H, 1, A.F32, n["name"] + ".hgate")
         wg = self.new_buf(c, x.W, 1, A.F32, n["name"] + ".wgate")
         cg = self.new_buf(c, 1, 1, A.F32, n["name"] + ".chgate")
         params = torch.cat([n["sp_w"].reshape(-1), n["gn_w"], n["gn_b"], n["ch_w"].reshape(-1)])
         self.ops.append(OpSpec(A.OP_ELA_GATE, n["name"] + ".gate", [rowm, colm, wg, cg], hg, cin=c, cout=c,
                                p_off=(self.blob.add(params.numpy().astype(np.float32)), -1, -1, -1),
-                               ip=(ks, n["groups"], x.H, x.W), fp=(n["gn_eps"],)))
+                               ip=(ks, n["groups"], x.H, x.W, nb), fp=(n["gn_eps"],)))
         co = [float(v) for v in n["coef"]]
         self.ops.append(OpSpec(A.OP_ELA_APPLY, n["name"] + ".apply", [x, hg, wg, cg], dest, cin=c, cout=c, fp=tuple(co),
                                bytes_alg=2 * c * x.H * x.W * 2))

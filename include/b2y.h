@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define B2Y_ABI_VERSION 3
+#define B2Y_ABI_VERSION 4
 #if defined(__GNUC__)
 #define B2Y_API __attribute__((visibility("default")))
 #else
@@ -57,6 +57,15 @@ enum b2y_op_kind {
   B2Y_OP_CONV_PAIR = 14,/* Bottleneck in one kernel: out = x + SiLU(conv3x3(SiLU(conv3x3(x))))  (block.py:3405-3419), the
                            hidden map never leaves the SM.  cin = cout in {16,32,64}; ip[0] = hidden channels (padded
                            to 16/32/64), ip[1] = 1: add the input; w_off/b_off = first conv, p_off[0]/p_off[1] = second */
+  B2Y_OP_PMSFA_DW = 16, /* depthwise tail of a PMSFA block in one kernel (block.py:3046-3051): in = conv1's output [a | b | h]
+                           (c channels: quarters a, b and the half h), out = [SiLU(dw7x7(SiLU(dw5x5([a|b]))_a)) |
+                           SiLU(dw5x5([a|b]))_b | h] = the input of conv4.  cin = cout = c in {16,32,64,128};
+                           w_off/b_off = conv2 fp32 [25][c/2] / [c/2], p_off[0]/p_off[1] = conv3 fp32 [49][c/4] / [c/4] */
+  B2Y_OP_MSCA_BRANCH = 17, /* MSCAAttention up to the branch outputs in one kernel (MSCA.py:52-74): attn = dw5x5(x); branch j =
+                           dw(k_j x 1)(dw(1 x k_j)(attn)) for k = 5, 7, 11, 21 (the shared per-channel `dilconv` folded into
+                           the second strip of branches 0..2); out = the four branch maps as channel slices [jC, (j+1)C) of
+                           one 4C-channel buffer, res = gap (B, 4, C) fp32 = their global average pools.  cin = C,
+                           cout = 4C; w_off = packed fp32 parameters (see plan.msca) */
   B2Y_OP_C3K2 = 15      /* EXPERIMENTAL (never emitted by the default planner; B2Y_FUSE_C3K2=1): a whole C3k2 block with one
                            Bottleneck (block.py:4148-4156, C2f.forward :3306-3310) in one kernel: cv1 1x1 cin -> 2c, Bottleneck
                            c -> chid -> c with shortcut, cv2 1x1 3c -> cout.  ip[0] = c, ip[1] = chid (padded to 16);

@@ -139,6 +139,35 @@ class PlanEmulator:
         y = F.conv2d(x, w, self.f32(op.b_off, c), stride=op.s, padding=op.p, groups=c).permute(0, 2, 3, 1)
         self._epilogue(op, y)
 
+    def op_pmsfa_dw(self, op):
+        """B2Y_OP_PMSFA_DW: in = [a | b | h] -> out = [SiLU(dw7x7(t_a)) | t_b | h], t = SiLU(dw5x5([a | b])) (block.py:3046-3051);
+        t_a is rounded to bf16 on its way into shared memory."""
+        c = op.cin
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        w2 = self.f32(op.w_off, 25 * (c // 2)).view(5, 5, c // 2).permute(2, 0, 1).unsqueeze(1)
+        w3 = self.f32(op.p_off[0], 49 * (c // 4)).view(7, 7, c // 4).permute(2, 0, 1).unsqueeze(1)
+        t = F.silu(F.conv2d(x[:, : c // 2], w2, self.f32(op.b_off, c // 2), padding=2, groups=c // 2))
+        ta = t[:, : c // 4].to(torch.bfloat16).float() if self.round else t[:, : c // 4]
+        o3 = F.silu(F.conv2d(ta, w3, self.f32(op.p_off[1], c // 4), padding=3, groups=c // 4))
+        self.put(op.out, torch.cat([o3, t[:, c // 4:], x[:, c // 2:]], 1).permute(0, 2, 3, 1))
+
+    def op_msca_branch(self, op):
+        """B2Y_OP_MSCA_BRANCH: attn = dw5x5(x); branch_j = dw(k x 1)(dw(1 x k)(attn)), k = 5, 7, 11, 21; gap_j = mean of the
+        (stored, i.e. rounded) branch map (MSCA.py:52-74).  attn and the strip intermediate are rounded to bf16."""
+        c = op.cin
+        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        P = self.f32(op.w_off, 122 * c).view(122, c)
+        rnd = (lambda t: t.to(torch.bfloat16).float()) if self.round else (lambda t: t)
+        attn = rnd(F.conv2d(x, P[:25].view(5, 5, c).permute(2, 0, 1).unsqueeze(1), P[25], padding=2, groups=c))
+        r, outs = 26, []
+        for k in (5, 7, 11, 21):
+            wh, bh, wv, bv = P[r:r + k], P[r + k], P[r + k + 1:r + 2 * k + 1], P[r + 2 * k + 1]
+            r += 2 * k + 2
+            u = rnd(F.conv2d(attn, wh.t().reshape(c, 1, 1, k), bh, padding=(0, k // 2), groups=c))
+            outs.append(F.conv2d(u, wv.t().reshape(c, 1, k, 1), bv, padding=(k // 2, 0), groups=c))
+        self.put(op.out, torch.cat(outs, 1).permute(0, 2, 3, 1))
+        self.bufs[op.res][:, 0, 0, :] = self.get(op.out).mean((1, 2))
+
     def op_sppf_pool(self, op):
         c = op.cin
         x = self.get(op.ins[0]).permute(0, 3, 1, 2)
@@ -167,14 +196,20 @@ class PlanEmulator:
     def op_rowcol_mean(self, op):
         x = self.get(op.ins[0])
         self.bufs[op.out][:, :, 0, :] = x.mean(2)
-        self.bufs[op.ins[1]][:, :, 0, :] = x.mean(1)
+        nb = (tuple(op.ip) + (0,))[0]
+        if nb:  # banded layout: per-band (8 rows) partial column means, summed by ela_gate
+            H = x.shape[1]
+            for k in range(nb):
+                self.bufs[op.ins[1]][:, :, k, :] = x[:, 8 * k:8 * k + 8].sum(1) / H
+        else:
+            self.bufs[op.ins[1]][:, :, 0, :] = x.mean(1)
 
     def op_ela_gate(self, op):
-        ks, groups, H, W = op.ip
+        ks, groups, H, W = op.ip[:4]
         c = op.cin
         p = self.f32(op.p_off[0], 2 * c * ks + 2 * c)
         sp_w, gn_w, gn_b, ch_w = p[:c * ks].view(c, ks), p[c * ks:c * ks + c], p[c * ks + c:c * ks + 2 * c], p[c * ks + 2 * c:].view(c, ks)
-        rowm, colm = self.bufs[op.ins[0]][:, :, 0, :], self.bufs[op.ins[1]][:, :, 0, :]
+        rowm, colm = self.bufs[op.ins[0]][:, :, 0, :], self.bufs[op.ins[1]].sum(2)
 
         def gate(m):  # (B,L,c)
             v = F.conv1d(m.transpose(1, 2), sp_w.unsqueeze(1), padding=ks - 1, dilation=2, groups=c)

@@ -340,6 +340,126 @@ def test_sppf_pool_kernel_vs_torch():
         assert torch.equal(got, ref), (c_, H, W)
 
 
+def _single_op_vs_emulator(plan, B, fill_bufs, out_views, seed=3):
+    """Run a hand-built plan on the GPU and through the PyTorch emulator (bf16 rounding points mirrored) on identical
+    bf16 inputs; returns [(got, ref)] per output view (fp32 CPU tensors)."""
+    from bs_yolo_b200.engine import Engine
+    from plan_emulator import PlanEmulator
+    eng = Engine(None, B, 64, 64, use_graph=False, plan=plan)
+    emu = PlanEmulator(plan, B, round_bf16=True)
+    gen = torch.Generator().manual_seed(seed)
+    for i in fill_bufs:
+        bspec = plan.bufs[i]
+        t = torch.randn(B, bspec.H, bspec.W, bspec.C, generator=gen).to(torch.bfloat16)
+        eng.buffer(i).copy_(t)
+        emu.bufs[i] = t.float()
+    eng.forward()
+    torch.cuda.synchronize()
+    emu.run()
+    res = []
+    for v in out_views:
+        if isinstance(v, int):
+            res.append((eng.buffer(v).float().cpu(), emu.bufs[v]))
+        else:
+            res.append((eng.view_tensor(v).float().cpu(), emu.get(v)))
+    return res, eng, emu
+
+
+@pytest.mark.parametrize("c,H,W,B", [(16, 160, 160, 2), (32, 37, 53, 3), (64, 20, 20, 5), (32, 40, 40, 4), (128, 9, 11, 2)])
+def test_pmsfa_fused_depthwise_kernel(c, H, W, B):
+    """OP_PMSFA_DW (block.py:3046-3051 in one kernel): conv2 5x5 on the first half, conv3 7x7 on its first quarter with
+    the zero-padded halo recomputed per tile, the cat; channel-sliced input and output views; odd maps, every tile shape."""
+    from bs_yolo_b200.plan import Plan, View
+    rng = np.random.default_rng(c * H)
+    pl = Plan.empty(64, 64)
+    tb, cb = pl.new_buf(c + 16, H, W, name="t"), pl.new_buf(c + 24, H, W, name="cat")
+    x = View(pl.new_buf(c, H, W, name="x"), 0, c, H, W)
+
+    def dw(name, ch, k):
+        return dict(type="Conv", name=name, c1=ch, c2=ch, k=(k, k), s=(1, 1), p=(k // 2, k // 2), g=ch, act="silu",
+                    weight=torch.from_numpy((rng.standard_normal((ch, 1, k, k)) / k).astype(np.float32)),
+                    bias=torch.from_numpy(rng.standard_normal(ch).astype(np.float32) * 0.1))
+
+    node = dict(type="PMSFA", name="m", c=c, conv2=dw("m.conv2", c // 2, 5), conv3=dw("m.conv3", c // 4, 7))
+    c2, c3 = node["conv2"], node["conv3"]
+    from bs_yolo_b200.plan import OpSpec
+    w2 = c2["weight"].reshape(c // 2, 25).t().contiguous().numpy()
+    w3 = c3["weight"].reshape(c // 4, 49).t().contiguous().numpy()
+    tin, out = View(tb, 8, c, H, W), View(cb, 16, c, H, W)
+    pl.ops.append(OpSpec(A.OP_PMSFA_DW, "m.dw", [tin], out, cin=c, cout=c, act=1, w_off=pl.blob.add(w2),
+                         b_off=pl.blob.add(c2["bias"].numpy()), p_off=(pl.blob.add(w3), pl.blob.add(c3["bias"].numpy()), -1, -1)))
+    (res,), eng, emu = _single_op_vs_emulator(pl, B, [tb, cb], [cb])
+    got, ref = res
+    sl = slice(16, 16 + c)
+    rel = float((got[..., sl] - ref[..., sl]).norm() / ref[..., sl].norm())
+    assert rel < 4e-3, rel
+    assert torch.equal(got[..., 16 + c // 2:16 + c], ref[..., 16 + c // 2:16 + c])      # the passed-through half: exact
+    assert torch.equal(got[..., :16], ref[..., :16]) and torch.equal(got[..., 16 + c:], ref[..., 16 + c:])  # untouched
+    # independent check of the emulator op itself against plain torch on the same operands
+    import torch.nn.functional as F
+    xin = emu.bufs[tb][..., 8:8 + c].permute(0, 3, 1, 2)
+    t = F.silu(F.conv2d(xin[:, : c // 2], c2["weight"], c2["bias"], padding=2, groups=c // 2))
+    o3 = F.silu(F.conv2d(t[:, : c // 4].bfloat16().float(), c3["weight"], c3["bias"], padding=3, groups=c // 4))
+    want = torch.cat([o3, t[:, c // 4:], xin[:, c // 2:]], 1).permute(0, 2, 3, 1).bfloat16().float()
+    assert float((ref[..., sl] - want).norm() / want.norm()) < 1e-3
+
+
+@pytest.mark.parametrize("c,H,W,B", [(64, 80, 80, 2), (128, 40, 40, 3), (256, 20, 20, 3), (128, 13, 21, 2), (32, 16, 16, 2)])
+def test_ela_kernels(c, H, W, B):
+    """ELA (ELA.py:70-100) = statistics (banded single-pass kernel where the shape allows, per-line kernel otherwise) ->
+    gates (dilated conv1d + GroupNorm + sigmoid) -> apply, against the emulator on the same bf16 input; channel-sliced
+    input view, odd map sizes, a partial last band."""
+    from bs_yolo_b200.plan import Plan, View
+    rng = np.random.default_rng(c + H)
+    ks = 5
+    node = dict(type="ELA", name="ela", c=c, ks=ks, groups=16, gn_eps=1e-5, coef=(0.5, 0.5, 1.0),
+                sp_w=torch.from_numpy(rng.standard_normal((c, ks)).astype(np.float32) * 0.5),
+                gn_w=torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.3 + 1),
+                gn_b=torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.3),
+                ch_w=torch.from_numpy(rng.standard_normal((c, ks)).astype(np.float32)))
+    pl = Plan.empty(64, 64)
+    xb = pl.new_buf(c + 16, H, W, name="x")
+    out = pl.ela(node, View(xb, 8, c, H, W), None)
+    assert pl.ops[0].ip[0] == ((H + 7) // 8 if c >= 64 else 0)
+    res, eng, emu = _single_op_vs_emulator(pl, B, [xb], [out] + [o.out for o in pl.ops[:2]] + [pl.ops[1].ins[2], pl.ops[1].ins[3]])
+    (got, ref), (rowm, rowm_r), (hg, hg_r), (wg, wg_r), (cg, cg_r) = res
+    assert float((rowm - rowm_r).abs().max()) < 1e-5
+    for a, b in ((hg, hg_r), (wg, wg_r), (cg, cg_r)):
+        assert float((a - b).abs().max()) < 2e-4
+    assert float((got - ref).norm() / ref.norm()) < 4e-3
+
+
+@pytest.mark.parametrize("C,H,W,B", [(256, 20, 20, 3), (64, 13, 21, 2), (16, 40, 40, 2), (8, 5, 7, 1)])
+def test_msca_fused_branch_kernel(C, H, W, B):
+    """OP_MSCA_BRANCH (MSCA.py:52-74 in one kernel): conv0 5x5, the four (1 x k)(k x 1) strip pairs with k = 5, 7, 11, 21
+    (21-tap strips reach past both borders of a 20-pixel map), the four global average pools; odd maps."""
+    import torch.nn.functional as F
+    from bs_yolo_b200.plan import OpSpec, Plan, View
+    rng = np.random.default_rng(C + H)
+    pl = Plan.empty(64, 64)
+    xb = pl.new_buf(C + 8, H, W, name="x")
+    ob = pl.new_buf(4 * C, H, W, name="branches")
+    gb = pl.new_buf(4 * C, 1, 1, A.F32, "gap")
+    params = torch.from_numpy((rng.standard_normal((122, C)) * 0.3).astype(np.float32))
+    x = View(xb, 8, C, H, W)
+    pl.ops.append(OpSpec(A.OP_MSCA_BRANCH, "msca.branches", [x], pl.full(ob), res=gb, cin=C, cout=4 * C,
+                         w_off=pl.blob.add(params.numpy())))
+    (br, gap), eng, emu = _single_op_vs_emulator(pl, B, [xb], [ob, gb])
+    rel = float((br[0] - br[1]).norm() / br[1].norm())
+    assert rel < 4e-3, rel
+    assert float((gap[0] - gap[1]).abs().max()) < 5e-3 * float(gap[1].abs().max() + 1e-6) + 1e-4
+    # the emulator op against plain torch convs (fp32, no rounding): loose, it only pins the parameter layout
+    xin = emu.bufs[xb][..., 8:].permute(0, 3, 1, 2)
+    attn = F.conv2d(xin, params[:25].view(5, 5, C).permute(2, 0, 1).unsqueeze(1), params[25], padding=2, groups=C)
+    r = 26
+    for j, k in enumerate((5, 7, 11, 21)):
+        u = F.conv2d(attn, params[r:r + k].t().reshape(C, 1, 1, k), params[r + k], padding=(0, k // 2), groups=C)
+        o = F.conv2d(u, params[r + k + 1:r + 2 * k + 1].t().reshape(C, 1, k, 1), params[r + 2 * k + 1], padding=(k // 2, 0), groups=C)
+        r += 2 * k + 2
+        want = o.permute(0, 2, 3, 1)
+        assert float((br[1][..., j * C:(j + 1) * C] - want).norm() / want.norm()) < 2e-2
+
+
 @pytest.mark.parametrize("nh,N_hw,B", [(2, (20, 20), 3), (6, (40, 40), 2), (6, (13, 21), 1)])
 def test_attention_kernel_vs_torch(nh, N_hw, B):
     """C2PSA attention core (block.py:4277-4286) at kernel level, including yolo11x@1280's size (nh = 6, N = 1600):
