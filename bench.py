@@ -530,10 +530,28 @@ def run_dropin_workload(ctx: Ctx, K: int):
         best = dt if best is None else min(best, dt)
     assert len(res) == n and type(yolo.predictor).__name__ == "B200DetectionPredictor"
     sp = res[0].speed
+    # what the host alone can deliver: the same frames copied into the pinned staging ring (all cores), no GPU work --
+    # pageable ndarrays must cross host memory once more than predict_stream's pinned batches
+    from bs_yolo_b200.predictor import _Staging
+
+    class _Done:
+        def synchronize(self):
+            pass
+
+    ring = _Staging(64, 640, 640)
+    fill = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for buf in ring.chunks(frames):
+            ring.uploaded(buf, _Done())
+        dt = time.perf_counter() - t0
+        fill = dt if fill is None else min(fill, dt)
     return {"metric": metric_name(640), "value": n / best, "unit": UNIT, "frames_per_call": n,
             "api": "YOLO(ckpt).predict(list_of_ndarrays, predictor=B200DetectionPredictor, device=0) incl. Results construction",
             "h2d_bytes_per_call": n * 640 * 640 * 3, "ms_per_image": best * 1e3 / n, "speed_ms_per_image": sp,
-            "detections_first_image": int(res[0].boxes.data.shape[0]), "best_of": 3}
+            "detections_first_image": int(res[0].boxes.data.shape[0]), "best_of": 3,
+            "host_staging_ceiling": {"value": n / fill, "unit": UNIT, "gbps": n * 640 * 640 * 3 / fill / 1e9,
+                                     "what": "pageable frames -> pinned staging ring only (thread pool, no GPU work)"}}
 
 
 def main():

@@ -90,9 +90,38 @@ __global__ void __launch_bounds__(256) resample_kernel(const bf16 *__restrict__ 
   else d[0] = s[0];
 }
 
+// nearest 2x upsample, 16-byte chunks: thread = one INPUT chunk, read once and stored to its 2 x 2 output pixels
+// (the per-output kernel above reads every input pixel four times).
+__global__ void __launch_bounds__(256) upsample2_kernel(const bf16 *__restrict__ in, int in_cs, bf16 *__restrict__ out,
+                                                        int out_cs, int c, long long total, int Hi, int Wi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = c >> 3;
+  const int c0 = (int)(idx % cg) * 8;
+  const long long pix = idx / cg;
+  const int wi = (int)(pix % Wi);
+  const int hi = (int)((pix / Wi) % Hi);
+  const long long b = pix / ((long long)Wi * Hi);
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in + (size_t)pix * in_cs + c0));
+  bf16 *d = out + ((size_t)(b * 2 * Hi + 2 * hi) * (2 * Wi) + 2 * wi) * out_cs + c0;
+  *reinterpret_cast<uint4 *>(d) = v;
+  *reinterpret_cast<uint4 *>(d + out_cs) = v;
+  *reinterpret_cast<uint4 *>(d + (size_t)2 * Wi * out_cs) = v;
+  *reinterpret_cast<uint4 *>(d + (size_t)2 * Wi * out_cs + out_cs) = v;
+}
+
 int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, int scale,
                     cudaStream_t st) {
   // H, W are OUTPUT dims
+  if (scale == 2 && c % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+      H % 2 == 0 && W % 2 == 0) {
+    const long long total = (long long)B * (H / 2) * (W / 2) * (c / 8);
+    b2y_launch(upsample2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, in, in_cs, out, out_cs, c, total, H / 2, W / 2);
+    B2Y_LAUNCH_CHECK();
+    return B2Y_OK;
+  }
   auto ok = [&](int v) {
     const uintptr_t m = (uintptr_t)v * 2 - 1;
     return c % v == 0 && in_cs % v == 0 && out_cs % v == 0 && ((uintptr_t)in & m) == 0 && ((uintptr_t)out & m) == 0;

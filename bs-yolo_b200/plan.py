@@ -642,16 +642,28 @@ class Plan:
                     continue
                 upcat[i] = (src_of(ju, layers[ju]["f"]), skip, srcs[0] == ju)
                 folded.update((ju, jc))
-        # concat destinations: the first Concat consumer of a layer gets a direct write
+        # concat destinations: the first Concat consumer of a layer gets a direct write.  A Concat that is itself an input of
+        # a later Concat (BS-YOLO: layer 13's 384-channel cat is re-used by layer 21, yolo11.yaml:43) lives INSIDE the later
+        # one's buffer, so its producers write there directly and the nested cat is never copied.
         dest: dict[int, View] = {}
         cat_view: dict[int, View] = {}
-        for L in layers:
-            if L["module"]["type"] != "Concat" or L["i"] in folded:
-                continue
+        cats = [L for L in layers if L["module"]["type"] == "Concat" and L["i"] not in folded]
+        for L in reversed(cats):  # outer (later) concats first
             i = L["i"]
             C, Hc, Wc = shape[i]
-            cv = self.full(self.new_buf(C, Hc, Wc, name=f"model.{i}.cat"), C)
-            cat_view[i] = cv
+            if i not in cat_view:
+                cat_view[i] = self.full(self.new_buf(C, Hc, Wc, name=f"model.{i}.cat"), C)
+            off = 0
+            for ff in L["f"]:
+                j = src_of(i, ff)
+                cj = shape[j][0]
+                if (layers[j]["module"]["type"] == "Concat" and j not in folded and j not in cat_view and cj % 8 == 0
+                        and off % 8 == 0 and os.environ.get("B2Y_NEST_CONCAT", "1") != "0"):
+                    cat_view[j] = self.sub(cat_view[i], off, cj)
+                off += cj
+        for L in cats:
+            i = L["i"]
+            cv = cat_view[i]
             off = 0
             for ff in L["f"]:
                 j = src_of(i, ff)

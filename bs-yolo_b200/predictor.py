@@ -25,6 +25,7 @@ The reference package is imported lazily (it is not a dependency of the kernels 
 """
 from __future__ import annotations
 
+import ctypes
 import os
 import queue
 import threading
@@ -98,9 +99,19 @@ class _Staging:
         n, B = len(frames), self.B
         q: queue.Queue = queue.Queue(maxsize=2)
 
-        def fill_one(args):
-            dst, src = args
-            np.copyto(dst, src)
+        nbytes = self.h * self.w * 3
+        workers = self.pool._max_workers
+
+        def fill_range(args):  # one task per worker: a contiguous run of frames, copied without the GIL (ctypes)
+            r, lo, a, b_ = args
+            base = self.bufs[r].data_ptr()
+            view = self.views[r]
+            for j in range(a, b_):
+                f = frames[j]
+                if f.flags.c_contiguous:
+                    ctypes.memmove(base + (j - lo) * nbytes, f.ctypes.data, nbytes)
+                else:
+                    np.copyto(view[j - lo], f)
 
         def produce():
             try:
@@ -111,8 +122,9 @@ class _Staging:
                         self.copied[r].synchronize()
                         self.copied[r] = None
                     self.free[r].clear()
-                    view = self.views[r]
-                    list(self.pool.map(fill_one, [(view[j - lo], frames[j]) for j in range(lo, min(lo + B, n))]))
+                    hi = min(lo + B, n)
+                    per = -(-(hi - lo) // workers)
+                    list(self.pool.map(fill_range, [(r, lo, a, min(a + per, hi)) for a in range(lo, hi, per)]))
                     q.put(self.bufs[r])
                 q.put(None)
             except BaseException as e:  # noqa: BLE001 -- surfaced in the consumer thread

@@ -19,7 +19,7 @@ from bs_yolo_b200 import _cabi as A  # noqa: E402
 from bs_yolo_b200.pipeline import DetectPipeline  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "yolo11n"
-model, batch, imgsz = bench.MODEL_CFG[workload]
+model, batch, imgsz = bench.MODEL_CFG[workload][:3]
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else batch
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 pipe = DetectPipeline(bench.make_ir(model), batch, imgsz, (imgsz, imgsz), use_graph=False)
@@ -36,7 +36,7 @@ rt.cudaProfilerStop()
 table = [{"launch": 0, "name": "preprocess", "kind": "preprocess"}]
 for i, o in enumerate(pipe.engine.plan.ops):
     table.append({"launch": i + 1, "name": o.name, "kind": A.OP_NAMES[o.kind], "impl": pipe.engine.op_impl(i),
-                  "bytes": o.bytes_alg * batch, "flops": o.flops * batch})
+                  "bytes": pipe.engine.plan.op_bytes(o, batch), "flops": o.flops * batch})
 n = len(table)
 table += [{"launch": n, "name": "nms.score", "kind": "nms"}, {"launch": n + 1, "name": "nms.select", "kind": "nms"}]
 out = os.environ.get("B2Y_PROFILE_TABLE")
