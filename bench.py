@@ -449,60 +449,75 @@ def run_detect_workload(ctx: Ctx, name: str, K: int, Wm: int, batch_override=0, 
     return rec
 
 
-def run_sahi_workload(ctx: Ctx, K: int, Wm: int):
+def run_sahi_workload(ctx: Ctx, K: int, Wm: int, frames_per_rank: int = 4):
     """BASELINE.json configs[4]: SAHI-style tiled inference of synthetic 3840x2160 frames, 640 tiles (24 per frame, overlap
     0, SAHI's edge rule), tiles sharded round-robin over the N GPUs, per-frame global class-aware NMS merge at the frame
-    owner.  One step = N frames (each rank owns one): every GPU runs a batch of 24 tiles (24/N of each frame)."""
+    owner.  One step = N x F frames (each rank owns F): every GPU runs a batch of 24 F tiles (24/N of each frame)."""
     from bs_yolo_b200.pipeline import DetectPipeline
     from bs_yolo_b200.shard import SahiSharder
 
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
-    Hf, Wf, tile = 2160, 3840, 640
+    Hf, Wf, tile, F = 2160, 3840, 640, frames_per_rank
     sh = SahiSharder(lambda B: DetectPipeline(make_ir("bsyolo_n"), B, tile, (tile, tile), device=ctx.local),
-                     (Hf, Wf), tile, world=world, rank=rank, group=None)
-    n_rot = 3
-    host = [torch.from_numpy(synth_frames(1, (Hf, Wf), 500 + rank * 8 + j)[0]).pin_memory() for j in range(n_rot)]
+                     (Hf, Wf), tile, world=world, rank=rank, group=None, frames=F)
+    n_rot = 2
+    host = [torch.from_numpy(synth_frames(F, (Hf, Wf), 500 + rank * 8 + j)).pin_memory() for j in range(n_rot)]
     devf = [h.to(dev) for h in host]
 
     def step_res(j):
-        return sh.predict_frame(devf[j % n_rot])
+        return sh.predict_frames(devf[j % n_rot])
 
     for j in range(Wm):
         step_res(j)
     ms, wall = ctx.timed(step_res, K)
-    # end to end: the owner's frame comes from pinned host memory, the merged detections go back to the host
-    out = (torch.empty(sh.max_det, 6).pin_memory(), torch.empty(1, dtype=torch.int32).pin_memory())
-    stage = torch.empty_like(devf[0])
+    # end to end: the owner's frames come from pinned host memory (the upload of step i+1 overlaps step i on a copy
+    # stream), the merged detections go back to the host
+    out = (torch.empty(F, sh.max_det, 6).pin_memory(), torch.empty(F, dtype=torch.int32).pin_memory())
+    stage = [torch.empty_like(devf[0]) for _ in range(2)]
+    cs = torch.cuda.Stream(dev)
+    up, used = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
 
-    def step_e2e(j):
-        stage.copy_(host[j % n_rot], non_blocking=True)
-        d, c = sh.predict_frame(stage)
-        out[0].copy_(d, non_blocking=True)
-        out[1].copy_(c.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def upload(j):
+        with torch.cuda.stream(cs):
+            cs.wait_event(used[j & 1])
+            stage[j & 1].copy_(host[j % n_rot], non_blocking=True)
+            up[j & 1].record(cs)
 
-    for j in range(2):
-        step_e2e(j)
+    def run_e2e(steps):
+        for e in used:
+            e.record(main)
+        upload(0)
+        for j in range(steps):
+            if j + 1 < steps:
+                upload(j + 1)
+            main.wait_event(up[j & 1])
+            d, c = sh.predict_frames(stage[j & 1])
+            used[j & 1].record(main)
+            out[0].copy_(d, non_blocking=True)
+            out[1].copy_(c, non_blocking=True)
+        main.synchronize()
+
+    run_e2e(2)
     ctx.barrier()
     t0 = time.perf_counter()
-    for j in range(K):
-        step_e2e(j)
+    run_e2e(K)
     ctx.barrier()
     wall_e2e = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)[0]
     rec = None
     if rank == 0:
-        fps = world * K / (ms * 1e-3)
+        fps = world * F * K / (ms * 1e-3)
         rec = {"metric": "frames/sec @3840x2160 (SAHI 640 tiles)", "value": fps, "unit": "frames/s", "tiles_per_s": fps * sh.T,
                "n_gpus": world, "steps": K, "ms_per_step": ms / K, "scaling": "weak", "dtype": "bf16",
                "config": {"workload": f"SAHI-style tiled inference, BS-YOLO-n, {Hf}x{Wf} frames -> {sh.T} tiles of {tile}, "
-                                      f"tiles round-robin over {world} GPU(s) ({sh.T // world if sh.T % world == 0 else sh.per} per GPU "
-                                      "per frame), global NMS merge at the frame owner (BASELINE.json configs[4])",
-                          "frames_per_step": world, "tile_batch_per_gpu": sh.B,
+                                      f"tiles round-robin over {world} GPU(s) ({sh.per} per GPU and frame), global NMS merge at the "
+                                      "frame owner (BASELINE.json configs[4])",
+                          "frames_per_step": world * F, "tile_batch_per_gpu": sh.B,
                           "exchange": "none (1 GPU)" if world == 1 else "NCCL all_to_all of tiles out and of padded detections back"},
-               "e2e": {"value": world * K / (wall_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": world * Hf * Wf * 3,
-                       "d2h_bytes_per_step": world * (sh.max_det * 24 + 4), "ms_per_step": wall_e2e / K},
+               "e2e": {"value": world * F * K / (wall_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": world * F * Hf * Wf * 3,
+                       "d2h_bytes_per_step": world * F * (sh.max_det * 24 + 4), "ms_per_step": wall_e2e / K},
                "merged_detections_last_frame": int(out[1][0])}
-    del sh, devf, host
+    del sh, devf, host, stage
     gc.collect()
     torch.cuda.empty_cache()
     return rec

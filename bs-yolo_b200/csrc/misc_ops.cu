@@ -158,95 +158,108 @@ __global__ void rowcol_mean_kernel(const bf16 *__restrict__ x, int cs, int c, in
 }
 
 // Banded single-pass variant (the fast path; C in {64,128,256}, W*C/8 <= 1024): one CTA = 8 rows of one image, read
-// ONCE with fully coalesced 16-byte loads.  Thread t owns the 16-byte chunks t and t + 512 of every row (chunk k = pixel
-// k / (C/8), channel octet k % (C/8); 512 % (C/8) == 0, so a thread's octet and columns are the same in every row):
+// ONCE with fully coalesced 16-byte loads.  Thread t owns the 16-byte chunks t + 256 j of every row (chunk k = pixel
+// k / (C/8), channel octet k % (C/8); 256 % (C/8) == 0, so a thread's octet and columns are the same in every row):
 // column sums accumulate in registers, row sums are reduced by warp shuffles over the lanes that share an octet and then
-// across the 16 warps through shared memory in a fixed order (deterministic).  The column sums of the band are written as
-// partial sums colm[b][w][band][c] (already divided by H); ela_gate adds the bands.
-constexpr int ELA_BAND = 8, ELA_NT = 512, ELA_R = 4;
+// across the 8 warps through shared memory in a fixed order (deterministic).  Rows are fetched two at a time with no
+// barrier in between (one barrier pair per `rs` rows), three CTAs per SM: ~100 KB of loads in flight per SM.  The column
+// sums of the band are written as partial sums colm[b][w][band][c] (already divided by H); ela_gate adds the bands.
+constexpr int ELA_BAND = 8, ELA_NT = 256;
 
-__global__ void __launch_bounds__(ELA_NT) ela_stats_kernel(const bf16 *__restrict__ x, int cs, int c, int H, int W, int nbands,
-                                                           float *__restrict__ rowm, float *__restrict__ colm) {
+template <int NJ>
+__global__ void __launch_bounds__(ELA_NT, 3) ela_stats_kernel(const bf16 *__restrict__ x, int cs, int c, int H, int W, int nbands,
+                                                              int rs_rows, float *__restrict__ rowm, float *__restrict__ colm) {
   pdl_launch_dependents();
-  extern __shared__ float red[];  // [ELA_R][16 warps][c]
+  extern __shared__ float red[];  // [rs_rows][8 warps][c]
   const int b = blockIdx.x / nbands, band = blockIdx.x % nbands;
   const int n_oct = c >> 3, cpr = W * n_oct;  // 16-byte chunks per row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int o = tid % n_oct;
   const int h0 = band * ELA_BAND, h1 = min(h0 + ELA_BAND, H);
-  const bool has[2] = {tid < cpr, tid + ELA_NT < cpr};
-  const int wq[2] = {tid / n_oct, (tid + ELA_NT) / n_oct};
-  float cs_acc[2][8];
+  bool has[NJ];
+  int wq[NJ];
+  float cs_acc[NJ][8];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < NJ; ++j) {
+    has[j] = tid + j * ELA_NT < cpr;
+    wq[j] = (tid + j * ELA_NT) / n_oct;
 #pragma unroll
     for (int i = 0; i < 8; ++i) cs_acc[j][i] = 0.f;
+  }
   const bf16 *img = x + (size_t)b * H * W * cs + o * 8;
   pdl_wait();
-  for (int r0 = h0; r0 < h1; r0 += ELA_R) {
-    uint4 v[ELA_R][2];
+  for (int g0 = h0; g0 < h1; g0 += rs_rows) {
+    for (int r0 = g0; r0 < min(g0 + rs_rows, h1); r0 += 2) {
+      uint4 v[2][NJ];
 #pragma unroll
-    for (int r = 0; r < ELA_R; ++r)
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        v[r][j] = (r0 + r < h1 && has[j]) ? __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(r0 + r) * W + wq[j]) * cs))
-                                           : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < NJ; ++j)
+          v[r][j] = (r0 + r < h1 && has[j]) ? __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(r0 + r) * W + wq[j]) * cs))
+                                             : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int r = 0; r < ELA_R; ++r) {
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < 2; ++r) {
+        float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float f[8];
-        unpack8(v[r][j], f);
+        for (int j = 0; j < NJ; ++j) {
+          float f[8];
+          unpack8(v[r][j], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rs[i] += f[i];
-          cs_acc[j][i] += f[i];
+          for (int i = 0; i < 8; ++i) {
+            rs[i] += f[i];
+            cs_acc[j][i] += f[i];
+          }
         }
-      }
-      for (int st = n_oct; st < 32; st <<= 1)  // lanes l, l ^ st share the octet (n_oct is a power of two <= 32)
+        for (int st = n_oct; st < 32; st <<= 1)  // lanes l, l ^ st share the octet (n_oct is a power of two <= 32)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], st);
-      if (lane < n_oct) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) red[(r * (ELA_NT / 32) + warp) * c + lane * 8 + i] = rs[i];
+          for (int i = 0; i < 8; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], st);
+        if (lane < n_oct) {
+          float *d = red + ((size_t)(r0 + r - g0) * (ELA_NT / 32) + warp) * c + lane * 8;
+          *reinterpret_cast<float4 *>(d) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+          *reinterpret_cast<float4 *>(d + 4) = make_float4(rs[4], rs[5], rs[6], rs[7]);
+        }
       }
     }
     __syncthreads();
-    for (int i = tid; i < ELA_R * c; i += ELA_NT) {
+    const int nr = min(rs_rows, h1 - g0);
+    for (int i = tid; i < nr * c; i += ELA_NT) {
       const int r = i / c, ch = i % c;
-      if (r0 + r < h1) {
-        float s = 0.f;
+      float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < ELA_NT / 32; ++w) s += red[(r * (ELA_NT / 32) + w) * c + ch];
-        rowm[((size_t)b * H + r0 + r) * c + ch] = s / (float)W;
-      }
+      for (int w = 0; w < ELA_NT / 32; ++w) s += red[((size_t)r * (ELA_NT / 32) + w) * c + ch];
+      rowm[((size_t)b * H + g0 + r) * c + ch] = s / (float)W;
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < NJ; ++j)
     if (has[j]) {
       float *d = colm + (((size_t)b * W + wq[j]) * nbands + band) * c + o * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = cs_acc[j][i] / (float)H;
+      const float inv = 1.f / (float)H;
+      *reinterpret_cast<float4 *>(d) = make_float4(cs_acc[j][0] / (float)H, cs_acc[j][1] / (float)H, cs_acc[j][2] / (float)H, cs_acc[j][3] / (float)H);
+      *reinterpret_cast<float4 *>(d + 4) = make_float4(cs_acc[j][4] / (float)H, cs_acc[j][5] / (float)H, cs_acc[j][6] / (float)H, cs_acc[j][7] / (float)H);
+      (void)inv;
     }
 }
 
 bool ela_fast_path(int c, int W, int cs, const void *x) {
-  return (c == 64 || c == 128 || c == 256) && W * (c >> 3) <= 2 * ELA_NT && cs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  return (c == 64 || c == 128 || c == 256) && W * (c >> 3) <= 4 * ELA_NT && cs % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
 
 int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, int nbands, float *rowm, float *colm, cudaStream_t st) {
   if (nbands >= 1) {  // the planner asked for the banded layout of colm (it applies the same shape test)
     B2Y_REQUIRE(ela_fast_path(c, W, cs, x) && nbands == ceil_div(H, ELA_BAND), B2Y_ERR_INVALID,
                 "ELA stats: banded layout requested for an unsupported shape (c %d, W %d, bands %d)", c, W, nbands);
-    const size_t smem = (size_t)ELA_R * (ELA_NT / 32) * c * sizeof(float);
-    if (smem > 48 * 1024)
-      B2Y_CUDA_CHECK(cudaFuncSetAttribute(ela_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    b2y_launch(ela_stats_kernel, dim3(B * nbands), dim3(ELA_NT), smem, st, x, cs, c, H, W, nbands, rowm, colm);
-    B2Y_LAUNCH_CHECK();
-    return B2Y_OK;
+    const int rs_rows = c <= 128 ? ELA_BAND : 4;  // rows between barrier pairs: 16 / 32 / 32 KB of partial row sums
+    const size_t smem = (size_t)rs_rows * (ELA_NT / 32) * c * sizeof(float);
+    const int nj = ceil_div(W * (c >> 3), ELA_NT);
+    auto go = [&](auto kern) -> int {
+      b2y_launch(kern, dim3(B * nbands), dim3(ELA_NT), smem, st, x, cs, c, H, W, nbands, rs_rows, rowm, colm);
+      B2Y_LAUNCH_CHECK();
+      return B2Y_OK;
+    };
+    return nj <= 1 ? go(ela_stats_kernel<1>) : nj == 2 ? go(ela_stats_kernel<2>) : nj == 3 ? go(ela_stats_kernel<3>)
+                                                                                            : go(ela_stats_kernel<4>);
   }
   const int bt = c >= 128 ? 128 : 64;
   dim3 grid(H + W, ceil_div(c, bt), B);
@@ -255,78 +268,71 @@ int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, int nb
   return B2Y_OK;
 }
 
-// One block per (image, GroupNorm group); does both directions.  params: [sp_w (c*ks) | gn_w (c) | gn_b (c) | ch_w (c*ks)].
+// One WARP per (image, GroupNorm group, direction); eight warps per CTA, no block-level barrier.  (The first version used a
+// 256-thread CTA per (image, group) with six barriers and a serial global-memory loop for the channel gate: 50-70 us per
+// call for ~1 MFLOP, every phase waiting out a full memory latency with nothing else to run.)
+// params: [sp_w (c*ks) | gn_w (c) | gn_b (c) | ch_w (c*ks)].
 //   gate_dir[b,l,ch] = sigmoid(GN(conv1d_dil2(mean_dir)[ch]))  (ELA.py:77-86), GroupNorm over (c/groups channels x L)
 //   chgate[b,ch]     = sigmoid(ch_w[ch][centre] * mean(x[b,:,:,ch]))  (ELA.py:49-58: Conv1d on a length-1 sequence)
+// Column means arrive as per-band partial sums (colm[b][w][band][c]) and are added in band order.
 __global__ void __launch_bounds__(256) ela_gate_kernel(const float *__restrict__ rowm, const float *__restrict__ colm,
                                                        const float *__restrict__ params, int c, int H, int W, int ks,
-                                                       int groups, float eps, int nbands, float *__restrict__ hgate,
+                                                       int groups, float eps, int nbands, int total_warps, float *__restrict__ hgate,
                                                        float *__restrict__ wgate, float *__restrict__ chgate) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];  // conv outputs for this group: [cpg][L], then the group's means [L][cpg]
-  __shared__ float red[64];
-  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
-  const int cpg = c / groups;
+  extern __shared__ float sm_all[];  // per warp: means [L][cpg] | conv outputs [cpg*L]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (wid >= total_warps) return;
+  const int dir = wid & 1, g = (wid >> 1) % groups, b = (wid >> 1) / groups;
+  const int cpg = c / groups, Lmax = H > W ? H : W;
+  float *mean_s = sm_all + (size_t)warp * 2 * cpg * Lmax, *sm = mean_s + cpg * Lmax;
   const float *sp_w = params, *gn_w = params + (size_t)c * ks, *gn_b = gn_w + c, *ch_w = gn_b + c;
-  for (int dir = 0; dir < 2; ++dir) {
-    const int L = dir == 0 ? H : W;
-    const int nb = dir == 0 ? 1 : nbands;  // column means arrive as per-band partial sums: add them in band order
-    const float *src = (dir == 0 ? rowm : colm) + (size_t)b * L * nb * c;
-    float *dst = (dir == 0 ? hgate : wgate) + (size_t)b * L * c;
-    const int n = cpg * L;
-    float *mean_s = sm + cpg * (H > W ? H : W);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
-      float m = 0.f;
-      for (int k = 0; k < nb; ++k) m += src[((size_t)l * nb + k) * c + ch];
-      mean_s[i] = m;
-    }
-    __syncthreads();
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
-      float a = 0.f;
-      for (int t = 0; t < ks; ++t) {
-        const int ll = l + 2 * t - (ks - 1);  // dilation 2, padding ks-1
-        if (ll >= 0 && ll < L) a = fmaf(sp_w[ch * ks + t], mean_s[ll * cpg + ci], a);
-      }
-      sm[i] = a;
-      s1 += a;
-      s2 += a * a;
-    }
-    // block reduce (sum, sum of squares)
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-      red[threadIdx.x >> 5] = s1;
-      red[32 + (threadIdx.x >> 5)] = s2;
-    }
-    __syncthreads();
-    float t1 = 0.f, t2 = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-      t1 += red[w];
-      t2 += red[32 + w];
-    }
-    const float mean = t1 / (float)n;
-    const float var = fmaxf(t2 / (float)n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
-      const float v = (sm[i] - mean) * rstd * gn_w[ch] + gn_b[ch];
-      dst[(size_t)l * c + ch] = 1.f / (1.f + expf(-v));
-    }
-    __syncthreads();
+  const int L = dir == 0 ? H : W;
+  const int nb = dir == 0 ? 1 : nbands;
+  const float *src = (dir == 0 ? rowm : colm) + (size_t)b * L * nb * c;
+  float *dst = (dir == 0 ? hgate : wgate) + (size_t)b * L * c;
+  const int n = cpg * L;
+  for (int i = lane; i < n; i += 32) {
+    const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
+    float m = 0.f;
+    for (int k = 0; k < nb; ++k) m += src[((size_t)l * nb + k) * c + ch];
+    mean_s[i] = m;
   }
-  for (int ci = threadIdx.x; ci < cpg; ci += blockDim.x) {
-    const int ch = g * cpg + ci;
-    float s = 0.f;
-    for (int h = 0; h < H; ++h) s += rowm[((size_t)b * H + h) * c + ch];
-    const float gm = s / (float)H;
-    chgate[(size_t)b * c + ch] = 1.f / (1.f + expf(-ch_w[ch * ks + (ks - 1) / 2] * gm));
+  __syncwarp();
+  if (dir == 0) {  // channel gate from the row means
+    for (int ci = lane; ci < cpg; ci += 32) {
+      const int ch = g * cpg + ci;
+      float s = 0.f;
+      for (int h = 0; h < H; ++h) s += mean_s[h * cpg + ci];
+      chgate[(size_t)b * c + ch] = 1.f / (1.f + expf(-ch_w[ch * ks + (ks - 1) / 2] * (s / (float)H)));
+    }
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
+    float a = 0.f;
+    for (int t = 0; t < ks; ++t) {
+      const int ll = l + 2 * t - (ks - 1);  // dilation 2, padding ks-1
+      if (ll >= 0 && ll < L) a = fmaf(sp_w[ch * ks + t], mean_s[ll * cpg + ci], a);
+    }
+    sm[i] = a;
+    s1 += a;
+    s2 += a * a;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float mean = s1 / (float)n;
+  const float var = fmaxf(s2 / (float)n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
+    const float v = (sm[i] - mean) * rstd * gn_w[ch] + gn_b[ch];
+    dst[(size_t)l * c + ch] = 1.f / (1.f + expf(-v));
   }
 }
 
@@ -334,10 +340,11 @@ int launch_ela_gate(const float *rowm, const float *colm, const float *params, i
                     int groups, float eps, int nbands, float *hgate, float *wgate, float *chgate, cudaStream_t st) {
   B2Y_REQUIRE(c % groups == 0, B2Y_ERR_INVALID, "ELA: channels %d not divisible by groups %d", c, groups);
   const int L = H > W ? H : W;
-  const size_t smem = (size_t)(c / groups) * L * sizeof(float) * 2;
+  const size_t smem = (size_t)8 * 2 * (c / groups) * L * sizeof(float);
   B2Y_REQUIRE(smem <= 48 * 1024, B2Y_ERR_UNSUPPORTED, "ELA gate: group tile too large");
-  b2y_launch(ela_gate_kernel, dim3(B * groups), dim3(256), smem, st, rowm, colm, params, c, H, W, ks, groups, eps,
-             nbands < 1 ? 1 : nbands, hgate, wgate, chgate);
+  const int total_warps = B * groups * 2;
+  b2y_launch(ela_gate_kernel, dim3(ceil_div(total_warps, 8)), dim3(256), smem, st, rowm, colm, params, c, H, W, ks, groups, eps,
+             nbands < 1 ? 1 : nbands, total_warps, hgate, wgate, chgate);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -368,24 +375,31 @@ __global__ void __launch_bounds__(256) ela_apply_kernel(const bf16 *__restrict__
   *reinterpret_cast<uint4 *>(out + (size_t)pix * out_cs + c0) = pack8(v);
 }
 
-// Fast path (same shapes as ela_stats_kernel): CTA = 8 rows of one image, thread = the 16-byte chunks t, t + 512 of every
+// Fast path (same shapes as ela_stats_kernel): CTA = 8 rows of one image, thread = the 16-byte chunks t + 256 j of every
 // row.  A thread's column gate and channel gate are loop invariants held in registers; per row it reads one 32-byte row
 // gate (shared by all threads of its octet: L1 hits), so the kernel moves 16 B in + 16 B out per chunk and little else --
-// the per-pixel version above re-read 96 B of gates for every 16 B of x.
-__global__ void __launch_bounds__(ELA_NT) ela_apply_band_kernel(const bf16 *__restrict__ x, int cs, bf16 *__restrict__ out,
-                                                                int out_cs, int c, int H, int W, int nbands,
-                                                                const float *__restrict__ hgate, const float *__restrict__ wgate,
-                                                                const float *__restrict__ chgate, float ch_c, float sp_c,
-                                                                float res_c) {
+// the per-pixel version above re-read 96 B of gates for every 16 B of x.  Four rows of loads are in flight per thread,
+// two CTAs per SM.
+template <int NJ>
+__global__ void __launch_bounds__(ELA_NT, 2) ela_apply_band_kernel(const bf16 *__restrict__ x, int cs, bf16 *__restrict__ out,
+                                                                   int out_cs, int c, int H, int W, int nbands,
+                                                                   const float *__restrict__ hgate, const float *__restrict__ wgate,
+                                                                   const float *__restrict__ chgate, float ch_c, float sp_c,
+                                                                   float res_c) {
   pdl_launch_dependents();
   const int b = blockIdx.x / nbands, band = blockIdx.x % nbands;
   const int n_oct = c >> 3, cpr = W * n_oct;
   const int tid = threadIdx.x, o = tid % n_oct;
   const int h0 = band * ELA_BAND, h1 = min(h0 + ELA_BAND, H);
-  const bool has[2] = {tid < cpr, tid + ELA_NT < cpr};
-  const int wq[2] = {tid / n_oct, (tid + ELA_NT) / n_oct};
+  bool has[NJ];
+  int wq[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    has[j] = tid + j * ELA_NT < cpr;
+    wq[j] = (tid + j * ELA_NT) / n_oct;
+  }
   pdl_wait();
-  float a[8], wg[2][8];
+  float a[8], wg[NJ][8];
   {
     const float4 c0 = __ldg(reinterpret_cast<const float4 *>(chgate + (size_t)b * c + o * 8));
     const float4 c1 = __ldg(reinterpret_cast<const float4 *>(chgate + (size_t)b * c + o * 8) + 1);
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(ELA_NT) ela_apply_band_kernel(const bf16 *__re
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = ch_c * cg[i];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const float *g = wgate + ((size_t)b * W + (has[j] ? wq[j] : 0)) * c + o * 8;
       const float4 g0 = __ldg(reinterpret_cast<const float4 *>(g)), g1 = __ldg(reinterpret_cast<const float4 *>(g) + 1);
       wg[j][0] = g0.x; wg[j][1] = g0.y; wg[j][2] = g0.z; wg[j][3] = g0.w;
@@ -402,27 +416,29 @@ __global__ void __launch_bounds__(ELA_NT) ela_apply_band_kernel(const bf16 *__re
   }
   const bf16 *img = x + (size_t)b * H * W * cs + o * 8;
   bf16 *oimg = out + (size_t)b * H * W * out_cs + o * 8;
-  uint4 v[ELA_BAND][2];
+  for (int r0 = h0; r0 < h1; r0 += 4) {
+    uint4 v[4][NJ];
 #pragma unroll
-  for (int r = 0; r < ELA_BAND; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (h0 + r < h1 && has[j]) v[r][j] = __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(h0 + r) * W + wq[j]) * cs));
+      for (int j = 0; j < NJ; ++j)
+        if (r0 + r < h1 && has[j]) v[r][j] = __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(r0 + r) * W + wq[j]) * cs));
 #pragma unroll
-  for (int r = 0; r < ELA_BAND; ++r) {
-    if (h0 + r >= h1) break;
-    const float *hgp = hgate + ((size_t)b * H + h0 + r) * c + o * 8;
-    const float4 h0v = __ldg(reinterpret_cast<const float4 *>(hgp)), h1v = __ldg(reinterpret_cast<const float4 *>(hgp) + 1);
-    const float hg[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+    for (int r = 0; r < 4; ++r) {
+      if (r0 + r >= h1) break;
+      const float *hgp = hgate + ((size_t)b * H + r0 + r) * c + o * 8;
+      const float4 h0v = __ldg(reinterpret_cast<const float4 *>(hgp)), h1v = __ldg(reinterpret_cast<const float4 *>(hgp) + 1);
+      const float hg[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (has[j]) {
-        float f[8];
-        unpack8(v[r][j], f);
+      for (int j = 0; j < NJ; ++j)
+        if (has[j]) {
+          float f[8];
+          unpack8(v[r][j], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = f[i] * (a[i] + sp_c * (hg[i] * wg[j][i])) + res_c * f[i];
-        *reinterpret_cast<uint4 *>(oimg + ((size_t)(h0 + r) * W + wq[j]) * out_cs) = pack8(f);
-      }
+          for (int i = 0; i < 8; ++i) f[i] = f[i] * (a[i] + sp_c * (hg[i] * wg[j][i])) + res_c * f[i];
+          *reinterpret_cast<uint4 *>(oimg + ((size_t)(r0 + r) * W + wq[j]) * out_cs) = pack8(f);
+        }
+    }
   }
 }
 
@@ -431,10 +447,15 @@ int launch_ela_apply(const bf16 *x, int cs, bf16 *out, int out_cs, int c, int B,
   B2Y_REQUIRE(c % 8 == 0 && cs % 8 == 0 && out_cs % 8 == 0, B2Y_ERR_UNSUPPORTED, "ELA apply: channels must be x8");
   if (ela_fast_path(c, W, cs, x) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     const int nbands = ceil_div(H, ELA_BAND);
-    b2y_launch(ela_apply_band_kernel, dim3(B * nbands), dim3(ELA_NT), 0, st, x, cs, out, out_cs, c, H, W, nbands, hgate, wgate,
-               chgate, ch_c, sp_c, res_c);
-    B2Y_LAUNCH_CHECK();
-    return B2Y_OK;
+    const int nj = ceil_div(W * (c >> 3), ELA_NT);
+    auto go = [&](auto kern) -> int {
+      b2y_launch(kern, dim3(B * nbands), dim3(ELA_NT), 0, st, x, cs, out, out_cs, c, H, W, nbands, hgate, wgate, chgate, ch_c, sp_c,
+                 res_c);
+      B2Y_LAUNCH_CHECK();
+      return B2Y_OK;
+    };
+    return nj <= 1 ? go(ela_apply_band_kernel<1>) : nj == 2 ? go(ela_apply_band_kernel<2>) : nj == 3 ? go(ela_apply_band_kernel<3>)
+                                                                                                      : go(ela_apply_band_kernel<4>);
   }
   const long long total = (long long)B * H * W * (c / 8);
   b2y_launch(ela_apply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, cs, out, out_cs, c, total, H, W, hgate, wgate,
@@ -474,18 +495,31 @@ int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, f
 }
 
 // gate[b,j,ch] = softmax_j(sigmoid(SE_j(gap_j)[ch]))   (MSCA.py:71-77); se_w fp32 [4][c][c], se_b [4][c].
-// block = (image, 32 output channels): one warp per output channel does the 4 dot products.
+// block = (8 output channels, a chunk of images): the 4 x 8 weight rows (32 KB at c = 256) are staged in shared memory ONCE
+// and reused for every image of the chunk; one warp per output channel does the 4 dot products of an image.  (One block per
+// image re-read the whole 1 MB weight set from L2 for every image: 268 MB at batch 256.)
+constexpr int GATE_CH = 8;
 __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict__ gap, const float *__restrict__ se_w,
-                                                        const float *__restrict__ se_b, int c, float *__restrict__ gate) {
+                                                        const float *__restrict__ se_b, int c, int B, int img_per_cta,
+                                                        float *__restrict__ gate) {
   pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.x;
+  extern __shared__ float wsm_gate[];  // [4][GATE_CH][c]
+  const int ch0 = blockIdx.x * GATE_CH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int ch = blockIdx.y * 32 + warp; ch < min(c, (int)blockIdx.y * 32 + 32); ch += 8) {
+  for (int i = threadIdx.x; i < 4 * GATE_CH * c; i += blockDim.x) {
+    const int k = i % c, r = (i / c) % GATE_CH, j = i / (c * GATE_CH);
+    wsm_gate[i] = (ch0 + r < c) ? se_w[((size_t)j * c + ch0 + r) * c + k] : 0.f;
+  }
+  __syncthreads();
+  pdl_wait();
+  const int ch = ch0 + warp;
+  if (ch >= c) return;
+  const int b0 = blockIdx.y * img_per_cta, b1 = min(b0 + img_per_cta, B);
+  for (int b = b0; b < b1; ++b) {
     float z[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float *w = se_w + ((size_t)j * c + ch) * c;
+      const float *w = wsm_gate + ((size_t)j * GATE_CH + warp) * c;
       const float *g = gap + ((size_t)b * 4 + j) * c;
       float s = 0.f;
       for (int k = lane; k < c; k += 32) s = fmaf(w[k], g[k], s);
@@ -508,7 +542,15 @@ __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict_
 
 int launch_msca_gate(const float *gap, const float *se_w, const float *se_b, int c, int B, float *gate,
                      cudaStream_t st) {
-  b2y_launch(msca_gate_kernel, dim3(dim3(B, ceil_div(c, 32))), dim3(256), 0, st, gap, se_w, se_b, c, gate);
+  const size_t smem = (size_t)4 * GATE_CH * c * sizeof(float);
+  B2Y_REQUIRE(smem <= 96 * 1024, B2Y_ERR_UNSUPPORTED, "msca_gate: c = %d too large", c);
+  if (smem > 48 * 1024)
+    B2Y_CUDA_CHECK(cudaFuncSetAttribute(msca_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = ceil_div(c, GATE_CH);
+  int chunks = ceil_div(148 * 2, tiles);  // ~2 CTAs per SM in total
+  if (chunks > B) chunks = B;
+  const int per = ceil_div(B, chunks);
+  b2y_launch(msca_gate_kernel, dim3(dim3(tiles, ceil_div(B, per))), dim3(256), smem, st, gap, se_w, se_b, c, B, per, gate);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -536,9 +578,66 @@ __global__ void __launch_bounds__(256) wsum4_kernel(Ptr4 br, const float *__rest
   *reinterpret_cast<uint4 *>(out + (size_t)pix * out_cs + c0) = pack8(acc);
 }
 
+// Fast path (256 % (c/8) == 0): CTA = (image, a run of pixels), thread = a fixed channel octet whose 4 x 8 gates stay in
+// registers while it walks over pixels (the per-pixel kernel above re-reads 128 B of gates for every 64 B of branch data).
+__global__ void __launch_bounds__(256) wsum4_band_kernel(Ptr4 br, const float *__restrict__ gate, bf16 *__restrict__ out,
+                                                         int out_cs, int c, int HW, int px_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n_oct = c >> 3;
+  const int b = blockIdx.y, o = threadIdx.x % n_oct, pstep = blockDim.x / n_oct;
+  float g[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 *gp = reinterpret_cast<const float4 *>(gate + ((size_t)b * 4 + j) * c + o * 8);
+    const float4 a = __ldg(gp), d = __ldg(gp + 1);
+    g[j][0] = a.x; g[j][1] = a.y; g[j][2] = a.z; g[j][3] = a.w; g[j][4] = d.x; g[j][5] = d.y; g[j][6] = d.z; g[j][7] = d.w;
+  }
+  const int p0 = blockIdx.x * px_per_cta, p1 = min(p0 + px_per_cta, HW);
+  for (int px = p0 + threadIdx.x / n_oct; px < p1; px += 2 * pstep) {
+    uint4 v[2][4];
+    const bool two = px + pstep < p1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[0][j] = __ldg(reinterpret_cast<const uint4 *>(br.p[j] + ((size_t)b * HW + px) * br.cs[j] + o * 8));
+      if (two) v[1][j] = __ldg(reinterpret_cast<const uint4 *>(br.p[j] + ((size_t)b * HW + px + pstep) * br.cs[j] + o * 8));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(v[u][j], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(g[j][k], f[k], acc[k]);
+      }
+      *reinterpret_cast<uint4 *>(out + ((size_t)b * HW + px + u * pstep) * out_cs + o * 8) = pack8(acc);
+    }
+  }
+}
+
 int launch_wsum4(const bf16 *const *br, const int *br_cs, const float *gate, bf16 *out, int out_cs, int c, int B,
                  int HW, cudaStream_t st) {
   B2Y_REQUIRE(c % 8 == 0 && out_cs % 8 == 0, B2Y_ERR_UNSUPPORTED, "wsum4: channels must be x8");
+  if (256 % (c >> 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0) {
+    Ptr4 q;
+    bool ok = true;
+    for (int j = 0; j < 4; ++j) {
+      q.p[j] = br[j];
+      q.cs[j] = br_cs[j];
+      ok = ok && br_cs[j] % 8 == 0 && (reinterpret_cast<uintptr_t>(br[j]) & 15) == 0;
+    }
+    if (ok) {
+      const int per_iter = 2 * (256 / (c >> 3));
+      int px_per_cta = per_iter * 4;  // four iterations per thread
+      if (px_per_cta > HW) px_per_cta = HW;
+      b2y_launch(wsum4_band_kernel, dim3(dim3(ceil_div(HW, px_per_cta), B)), dim3(256), 0, st, q, gate, out, out_cs, c, HW, px_per_cta);
+      B2Y_LAUNCH_CHECK();
+      return B2Y_OK;
+    }
+  }
   Ptr4 q;
   for (int j = 0; j < 4; ++j) {
     q.p[j] = br[j];

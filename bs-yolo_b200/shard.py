@@ -110,19 +110,23 @@ def bind_to_gpu_numa(device_index: int) -> str:
 
 
 def merge_prediction(dets: torch.Tensor, counts: torch.Tensor, origins: torch.Tensor, nc: int) -> torch.Tensor:
-    """Tile detections -> one decoded-prediction tensor (1, 4+nc, T*max_det) in full-frame coordinates, the input of the
-    global class-aware NMS (the same kernel as the per-image NMS).  dets (T, max_det, 6) rows [x1,y1,x2,y2,conf,cls],
-    origins (T, 2) = (x0, y0) of each tile.  Rows past counts[t] get score 0 (never candidates).  All fp32 arithmetic is
-    elementwise IEEE (shift, xyxy -> xywh), so the CPU restatement in the tests reproduces it bit for bit."""
-    T, K, _ = dets.shape
-    d = dets.reshape(T * K, 6)
-    off = origins.to(dets.dtype).repeat_interleave(K, 0)
-    x1, y1, x2, y2 = d[:, 0] + off[:, 0], d[:, 1] + off[:, 1], d[:, 2] + off[:, 0], d[:, 3] + off[:, 1]
-    valid = (torch.arange(K, device=dets.device).repeat(T) < counts.to(torch.int64).repeat_interleave(K))
-    pred = torch.zeros(1, 4 + nc, T * K, dtype=dets.dtype, device=dets.device)
-    pred[0, 0], pred[0, 1], pred[0, 2], pred[0, 3] = (x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1
-    cls = d[:, 5].to(torch.int64).clamp_(0, nc - 1)
-    pred[0, 4:].scatter_(0, cls.unsqueeze(0), torch.where(valid, d[:, 4], torch.zeros_like(d[:, 4])).unsqueeze(0))
+    """Tile detections -> decoded-prediction tensors in full-frame coordinates, the input of the global class-aware NMS
+    (the same kernel as the per-image NMS).  One frame: dets (T, max_det, 6) rows [x1,y1,x2,y2,conf,cls], counts (T,),
+    origins (T, 2) = (x0, y0) of each tile -> (1, 4+nc, T*max_det).  A batch of frames: dets (F, T, max_det, 6), counts
+    (F, T), the same origins -> (F, 4+nc, T*max_det).  Rows past counts[t] get score 0 (never candidates).  All fp32
+    arithmetic is elementwise IEEE (shift, xyxy -> xywh), so the CPU restatement in the tests reproduces it bit for bit."""
+    single = dets.dim() == 3
+    if single:
+        dets, counts = dets.unsqueeze(0), counts.unsqueeze(0)
+    F, T, K, _ = dets.shape
+    d = dets.reshape(F, T * K, 6)
+    off = origins.to(dets.dtype).repeat_interleave(K, 0).unsqueeze(0)            # (1, T*K, 2)
+    x1, y1, x2, y2 = d[..., 0] + off[..., 0], d[..., 1] + off[..., 1], d[..., 2] + off[..., 0], d[..., 3] + off[..., 1]
+    valid = torch.arange(K, device=dets.device).repeat(T).unsqueeze(0) < counts.to(torch.int64).repeat_interleave(K, 1)
+    pred = torch.zeros(F, 4 + nc, T * K, dtype=dets.dtype, device=dets.device)
+    pred[:, 0], pred[:, 1], pred[:, 2], pred[:, 3] = (x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1
+    cls = d[..., 5].to(torch.int64).clamp_(0, nc - 1)
+    pred[:, 4:].scatter_(1, cls.unsqueeze(1), torch.where(valid, d[..., 4], torch.zeros_like(d[..., 4])).unsqueeze(1))
     return pred
 
 
@@ -147,23 +151,24 @@ def sahi_predict(pipe, frame_u8: torch.Tensor, tile: int = 640, overlap: float =
 
 
 class SahiSharder:
-    """BASELINE.json config 5 across the GPUs of one box: every rank owns one frame per step, slices it into SAHI tiles
-    on its GPU, and the tiles are sharded round-robin (tile t -> GPU t mod world) with ONE all_to_all of uint8 tiles;
-    every GPU then runs its tile batch (``per`` tiles of each of the ``world`` frames) through the detect pipeline, the
-    padded per-tile detections return to the frame owners with a second all_to_all, and each owner merges its frame with
-    one global class-aware NMS (`merge_prediction` + the same NMS kernel as the per-image NMS).  These two exchanges are
-    the only cross-GPU traffic (world == 1: none).  Host logic only -- `make_pipe(B)` builds the per-GPU detector (a
-    DetectPipeline on the GPU; any callable ``tiles (B,t,t,3) uint8 -> (dets (B,K,6), counts (B,))`` in the CPU tests)."""
+    """BASELINE.json config 5 across the GPUs of one box: every rank owns ``frames`` frames per step, slices them into SAHI
+    tiles on its GPU, and the tiles are sharded round-robin (tile t -> GPU t mod world) with ONE all_to_all of uint8 tiles;
+    every GPU then runs its tile batch (``per`` tiles of each of the ``world * frames`` frames) through the detect
+    pipeline, the padded per-tile detections return to the frame owners with a second all_to_all, and each owner merges
+    its frames with one batched global class-aware NMS (`merge_prediction` + the same NMS kernel as the per-image NMS).
+    These two exchanges are the only cross-GPU traffic (world == 1: none).  Host logic only -- `make_pipe(B)` builds the
+    per-GPU detector (a DetectPipeline on the GPU; any callable ``tiles (B,t,t,3) uint8 -> (dets (B,K,6), counts (B,))``
+    in the CPU tests)."""
 
     def __init__(self, make_pipe, frame_hw, tile: int = 640, world: int = 1, rank: int = 0, group=None, overlap: float = 0.0,
-                 iou: float | None = None, nms_fn=None):
+                 iou: float | None = None, nms_fn=None, frames: int = 1):
         self.H, self.W = frame_hw
-        self.tile, self.world, self.rank, self.group = tile, world, rank, group
+        self.tile, self.world, self.rank, self.group, self.F = tile, world, rank, group, frames
         self.origins = sahi_tiles(self.H, self.W, tile, overlap)
         self.T = len(self.origins)
         self.per = -(-self.T // world)              # tiles of one frame per GPU (the last GPUs may get a padding tile)
-        self.B = self.per * world                   # tile batch per GPU and step: `per` tiles from each of `world` frames
-        # destination-major send order: block d = this frame's tiles for GPU d (tile_owner), padded with -1
+        self.B = self.per * world * frames          # tile batch per GPU and step
+        # destination-major send order of ONE frame: block d = its tiles for GPU d (tile_owner), padded with -1
         self.send_order = []
         for d in range(world):
             mine = [t for t in range(self.T) if tile_owner(t, world) == d]
@@ -178,28 +183,32 @@ class SahiSharder:
 
     def _consts(self, device):
         if self._dev_cache is None or self._dev_cache[0] != device:
+            slots = self.per * self.world
             valid = torch.tensor([t >= 0 for t in self.send_order], device=device)
-            org = torch.tensor([self.origins[max(t, 0)] for t in self.send_order], dtype=torch.float32, device=device)
-            # permutation that puts the received results back into tile order (ties in the merge NMS break by index, so the
-            # merged result equals the single-GPU one bit for bit); padding slots go last
-            order = sorted(range(self.B), key=lambda i: (self.send_order[i] < 0, self.send_order[i]))
+            # permutation that puts one frame's slots back into tile order (ties in the merge NMS break by index, so the
+            # merged result equals the single-GPU one bit for bit); padding slots go last and are dropped
+            order = sorted(range(slots), key=lambda i: (self.send_order[i] < 0, self.send_order[i]))[: self.T]
+            org = torch.tensor(self.origins, dtype=torch.float32, device=device)
             self._dev_cache = (device, valid, org, torch.tensor(order, device=device))
         return self._dev_cache[1:]
 
-    def slice_tiles(self, frame: torch.Tensor) -> torch.Tensor:
-        t = self.tile
-        return torch.stack([frame[y:y + t, x:x + t] for x, y in (self.origins[max(i, 0)] for i in self.send_order)])
+    def slice_tiles(self, frames: torch.Tensor) -> torch.Tensor:
+        """(F,H,W,3) -> (world, F, per, t, t, 3): destination-major, so all_to_all_single splits it evenly."""
+        t, F = self.tile, frames.shape[0]
+        tiles = torch.stack([frames[:, y:y + t, x:x + t] for x, y in (self.origins[max(i, 0)] for i in self.send_order)], 1)
+        return tiles.view(F, self.world, self.per, t, t, 3).transpose(0, 1).contiguous()
 
-    def predict_frame(self, frame_u8: torch.Tensor):
-        """frame_u8 (H,W,3) uint8 BGR on this rank's device -> (dets (max_det,6) in frame coordinates, count) for THIS
-        rank's frame.  Collective: every rank of the group calls it once per step."""
+    def predict_frames(self, frames_u8: torch.Tensor):
+        """frames_u8 (F,H,W,3) uint8 BGR on this rank's device -> (dets (F,max_det,6) in frame coordinates, counts (F,))
+        for THIS rank's frames.  Collective: every rank of the group calls it once per step."""
         import torch.distributed as dist
 
-        assert tuple(frame_u8.shape) == (self.H, self.W, 3) and frame_u8.dtype == torch.uint8
-        tiles = self.slice_tiles(frame_u8)
+        F = self.F
+        assert tuple(frames_u8.shape) == (F, self.H, self.W, 3) and frames_u8.dtype == torch.uint8
+        tiles = self.slice_tiles(frames_u8).view(self.B, self.tile, self.tile, 3)
         if self.world > 1:
             recv = torch.empty_like(tiles)
-            dist.all_to_all_single(recv, tiles, group=self.group)   # block s of recv: my share of rank s's frame
+            dist.all_to_all_single(recv, tiles, group=self.group)   # block s of recv: my share of rank s's frames
             tiles = recv
         dets, counts = self.pipe(tiles)
         K = dets.shape[1]
@@ -208,15 +217,21 @@ class SahiSharder:
             packed[:, :K * 6] = dets.reshape(self.B, K * 6)
             packed[:, K * 6] = counts.to(torch.int32).view(torch.float32)   # bit-cast: the count rides in the fp32 message
             back = torch.empty_like(packed)
-            dist.all_to_all_single(back, packed, group=self.group)  # block d of back: GPU d's results for my frame's tiles
+            dist.all_to_all_single(back, packed, group=self.group)  # block d of back: GPU d's results for my frames' tiles
             dets = back[:, :K * 6].reshape(self.B, K, 6)
             counts = back[:, K * 6].contiguous().view(torch.int32)
         valid, org, order = self._consts(dets.device)
-        counts = torch.where(valid, counts.to(torch.int32), torch.zeros_like(counts, dtype=torch.int32))
-        dets, counts, org = dets.index_select(0, order), counts.index_select(0, order), org.index_select(0, order)
+        # (world, F, per) -> (F, world*per) slots per frame -> tile order
+        slots = self.world * self.per
+        dets = dets.view(self.world, F, self.per, K, 6).transpose(0, 1).reshape(F, slots, K, 6).index_select(1, order)
+        counts = counts.to(torch.int32).view(self.world, F, self.per).transpose(0, 1).reshape(F, slots).index_select(1, order)
         pred = merge_prediction(dets, counts, org, self.nc)
         nms = self._nms
         if nms is None:
             from .ops import nms_raw as nms
-        md, mc = nms(pred, self.conf, self.iou, self.max_det)
+        return nms(pred, self.conf, self.iou, self.max_det)
+
+    def predict_frame(self, frame_u8: torch.Tensor):
+        """One frame per rank and step (frames == 1): (H,W,3) -> (dets (max_det,6), count)."""
+        md, mc = self.predict_frames(frame_u8.unsqueeze(0))
         return md[0], mc[0]

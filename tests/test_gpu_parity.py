@@ -460,6 +460,37 @@ def test_msca_fused_branch_kernel(C, H, W, B):
         assert float((br[1][..., j * C:(j + 1) * C] - want).norm() / want.norm()) < 2e-2
 
 
+@pytest.mark.parametrize("C,H,W,B", [(256, 20, 20, 5), (64, 13, 21, 3), (24, 10, 10, 2)])
+def test_msca_block_vs_emulator(C, H, W, B):
+    """The whole MSCAAttention block as lowered by plan.msca (MSCA.py:52-88): fused branches -> SE gate (weights staged once per
+    CTA, images in chunks) -> gate-weighted sum (gates in registers / per-pixel fallback at C = 24) -> conv4 * u."""
+    from bs_yolo_b200.plan import Plan, View
+    rng = np.random.default_rng(C * H)
+
+    def cv(name, k, g, scale):
+        kh, kw = k
+        return dict(type="Conv", name=name, c1=C, c2=C, k=k, s=(1, 1), p=(kh // 2, kw // 2), g=g, act="none",
+                    weight=torch.from_numpy((rng.standard_normal((C, C // g, kh, kw)) * scale).astype(np.float32)),
+                    bias=torch.from_numpy(rng.standard_normal(C).astype(np.float32) * 0.1))
+
+    node = dict(type="MSCA", name="msca", c=C, conv0=cv("msca.conv0", (5, 5), C, 0.2), dilconv=cv("msca.dilconv", (1, 1), C, 1.0),
+                conv4=cv("msca.conv4", (1, 1), 1, 1.0 / np.sqrt(C)))
+    for b, k in enumerate((5, 7, 11, 21)):
+        node[f"conv{b}_1"] = cv(f"msca.conv{b}_1", (1, k), C, 1.0 / np.sqrt(k))
+        node[f"conv{b}_2"] = cv(f"msca.conv{b}_2", (k, 1), C, 1.0 / np.sqrt(k))
+    for j in range(1, 5):
+        node[f"SE{j}"] = cv(f"msca.SE{j}", (1, 1), 1, 2.0 / np.sqrt(C))
+    pl = Plan.empty(64, 64)
+    xb = pl.new_buf(C, H, W, name="x")
+    out = pl.msca(node, pl.full(xb), None)
+    kinds = [o.kind for o in pl.ops]
+    assert kinds[:3] == [A.OP_MSCA_BRANCH, A.OP_MSCA_GATE, A.OP_WSUM4] and kinds[3] == A.OP_CONV
+    gate_buf = pl.ops[1].out
+    (got, ref), (gg, gr) = _single_op_vs_emulator(pl, B, [xb], [out, gate_buf])[0]
+    assert float((gg - gr).abs().max()) < 2e-3                      # softmax(sigmoid(SE(gap))) per branch and channel
+    assert float((got - ref).norm() / ref.norm()) < 8e-3, float((got - ref).norm() / ref.norm())
+
+
 @pytest.mark.parametrize("nh,N_hw,B", [(2, (20, 20), 3), (6, (40, 40), 2), (6, (13, 21), 1)])
 def test_attention_kernel_vs_torch(nh, N_hw, B):
     """C2PSA attention core (block.py:4277-4286) at kernel level, including yolo11x@1280's size (nh = 6, N = 1600):

@@ -193,10 +193,11 @@ class _FakeTileDetector:
 
 
 def _oracle_nms(pred, conf, iou, max_det):
-    out = oracle_post.non_max_suppression(pred.numpy().copy(), conf, iou, max_det=max_det)[0]
-    d = torch.zeros(1, max_det, 6)
-    d[0, : len(out)] = torch.from_numpy(out)
-    return d, torch.tensor([len(out)], dtype=torch.int32)
+    outs = oracle_post.non_max_suppression(pred.numpy().copy(), conf, iou, max_det=max_det)
+    d = torch.zeros(len(outs), max_det, 6)
+    for i, out in enumerate(outs):
+        d[i, : len(out)] = torch.from_numpy(out)
+    return d, torch.tensor([len(out) for out in outs], dtype=torch.int32)
 
 
 def _sahi_frames(world):
@@ -248,4 +249,15 @@ def test_sahi_sharder_pads_uneven_tile_counts():
     assert (sh4.per, sh4.B) == (2, 8) and sh4.send_order == [0, 4, 1, 5, 2, -1, 3, -1]
     valid, org, order = sh4._consts(torch.device("cpu"))
     assert valid.tolist() == [True, True, True, True, True, False, True, False]
-    assert [sh4.send_order[i] for i in order.tolist()] == [0, 1, 2, 3, 4, 5, -1, -1]
+    assert [sh4.send_order[i] for i in order.tolist()] == [0, 1, 2, 3, 4, 5]   # tile order, padding slots dropped
+
+
+def test_sahi_sharder_several_frames_per_step_equal_single_frames():
+    frames = torch.stack(_sahi_frames(3))
+    one = shard.SahiSharder(_FakeTileDetector, (150, 230), 64, world=1, rank=0, nms_fn=_oracle_nms)
+    many = shard.SahiSharder(_FakeTileDetector, (150, 230), 64, world=1, rank=0, nms_fn=_oracle_nms, frames=3)
+    assert many.B == 36
+    d, c = many.predict_frames(frames)
+    for f in range(3):
+        d1, c1 = one.predict_frame(frames[f])
+        assert int(c[f]) == int(c1) and torch.equal(d[f], d1)
