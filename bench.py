@@ -211,7 +211,7 @@ def run_reference(args):
                          "sample": f"{n_img} synthetic {imgsz}x{imgsz} frames per step in one batch, torch fp32, {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -569,7 +569,28 @@ def run_dropin_workload(ctx: Ctx, K: int):
                                      "what": "pageable frames -> pinned staging ring only (thread pool, no GPU work)"}}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 while the bench runs (the
+    reference package's logger and settings banner, NCCL, torch warnings) is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -622,7 +643,7 @@ def main():
         line["clocks"] = sampler.stop()
         if subs:
             line["workloads"] = subs
-        print(json.dumps(line))
+        emit(line)
     if ctx.world > 1:
         ctx.dist.destroy_process_group()
     return 0

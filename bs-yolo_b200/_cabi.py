@@ -7,16 +7,16 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2y.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 BF16, F32 = 0, 1
 (OP_CONV, OP_DWCONV, _OP_RESERVED3, OP_SPPF_POOL, OP_RESAMPLE, OP_ATTN, OP_ROWCOL_MEAN, OP_ELA_GATE, OP_ELA_APPLY, OP_GAP4,
- OP_MSCA_GATE, OP_WSUM4, OP_DECODE, OP_CONV_PAIR, OP_C3K2, OP_PMSFA_DW, OP_MSCA_BRANCH) = range(1, 18)
+ OP_MSCA_GATE, OP_WSUM4, OP_DECODE, OP_CONV_PAIR, _OP_RESERVED15, OP_PMSFA_DW, OP_MSCA_BRANCH) = range(1, 18)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 RES_NONE, RES_ADD, RES_MUL, RES_PREADD_UP2 = 0, 1, 2, 3
 OP_NAMES = {1: "conv", 2: "dwconv", 4: "sppf_pool", 5: "resample", 6: "attn", 7: "rowcol_mean", 8: "ela_gate",
-            9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode", 14: "conv_pair", 15: "c3k2", 16: "pmsfa_dw", 17: "msca_branch"}
+            9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode", 14: "conv_pair", 16: "pmsfa_dw", 17: "msca_branch"}
 
 
 class Buf(C.Structure):
@@ -33,7 +33,7 @@ class Op(C.Structure):
 
 
 EXPORTS = ["b2y_abi_version", "b2y_last_error", "b2y_plan_create", "b2y_plan_destroy", "b2y_plan_run",
-           "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_set_mid_op", "b2y_plan_wait_mid", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_conv_pair_fits", "b2y_c3k2_fits", "b2y_preprocess",
+           "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_set_mid_op", "b2y_plan_wait_mid", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_conv_pair_fits", "b2y_preprocess",
            "b2y_decode", "b2y_nms_workspace_bytes", "b2y_nms", "b2y_scale_boxes"]
 
 _lib = None
@@ -66,7 +66,6 @@ def lib():
     L.b2y_plan_num_launches.argtypes = [vp]
     L.b2y_plan_op_impl.argtypes = [vp, i32]
     L.b2y_conv_pair_fits.argtypes = [i32, i32, i32, i32, i32]
-    L.b2y_c3k2_fits.argtypes = [i32, i32, i32, i32, i32, i32, i32]
     L.b2y_preprocess.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.b2y_decode.argtypes = [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(f32), i32, i32, i32, vp, vp]
     L.b2y_nms_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]

@@ -178,20 +178,6 @@ int conv_pair_plan_create(const PairParams &p, int device, ConvPairPlan **out);
 void conv_pair_plan_destroy(ConvPairPlan *p);
 int launch_conv_pair(const ConvPairPlan *p, cudaStream_t st);
 
-// fused C3k2 block (cv1 -> Bottleneck -> cv2) on the tensor cores, c3k2_fused.cu (experimental, opt-in)
-struct C3k2Params {
-  const bf16 *in; int in_cs;
-  void *out; int out_cs;
-  const void *w;              // bf16, packed: W0 [2c][cin] | W1 [chid][9c] | W2 [c][9 chid] | W3 [cout][3c]
-  const float *bias;          // fp32 [2c | chid | c | cout]
-  int B, H, W, cin, c, chid, cout;
-};
-struct C3k2Plan;
-bool c3k2_supported(const C3k2Params &p, char *why, int why_len);
-int c3k2_plan_create(const C3k2Params &p, int device, C3k2Plan **out);
-void c3k2_plan_destroy(C3k2Plan *p);
-int launch_c3k2(const C3k2Plan *p, cudaStream_t st);
-
 // fused depthwise tail of a PMSFA block, pmsfa_dw.cu
 struct PmsfaParams {
   const bf16 *in; int in_cs;

@@ -268,83 +268,116 @@ int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, int nb
   return B2Y_OK;
 }
 
-// One WARP per (image, GroupNorm group, direction); eight warps per CTA, no block-level barrier.  (The first version used a
-// 256-thread CTA per (image, group) with six barriers and a serial global-memory loop for the channel gate: 50-70 us per
-// call for ~1 MFLOP, every phase waiting out a full memory latency with nothing else to run.)
+// One 128-thread block per (image, GroupNorm group); does both directions.
 // params: [sp_w (c*ks) | gn_w (c) | gn_b (c) | ch_w (c*ks)].
 //   gate_dir[b,l,ch] = sigmoid(GN(conv1d_dil2(mean_dir)[ch]))  (ELA.py:77-86), GroupNorm over (c/groups channels x L)
 //   chgate[b,ch]     = sigmoid(ch_w[ch][centre] * mean(x[b,:,:,ch]))  (ELA.py:49-58: Conv1d on a length-1 sequence)
-// Column means arrive as per-band partial sums (colm[b][w][band][c]) and are added in band order.
-__global__ void __launch_bounds__(256) ela_gate_kernel(const float *__restrict__ rowm, const float *__restrict__ colm,
-                                                       const float *__restrict__ params, int c, int H, int W, int ks,
-                                                       int groups, float eps, int nbands, int total_warps, float *__restrict__ hgate,
-                                                       float *__restrict__ wgate, float *__restrict__ chgate) {
+// Column means arrive as per-band partial sums (colm[b][w][band][c]): the band loads of an element are issued together
+// (unrolled, predicated) and added in band order.  The kernel is pure latency: every phase is written so that a thread has
+// all its global loads in flight at once (the first version's serial loops -- channel gate over H rows, bands one by one --
+// cost 25-100 us per call for ~1 MFLOP).
+constexpr int GATE_NT = 128, GATE_MAXNB = 16;
+__global__ void __launch_bounds__(GATE_NT) ela_gate_kernel(const float *__restrict__ rowm, const float *__restrict__ colm,
+                                                           const float *__restrict__ params, int c, int H, int W, int ks,
+                                                           int groups, float eps, int nbands, float *__restrict__ hgate,
+                                                           float *__restrict__ wgate, float *__restrict__ chgate) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm_all[];  // per warp: means [L][cpg] | conv outputs [cpg*L]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (wid >= total_warps) return;
-  const int dir = wid & 1, g = (wid >> 1) % groups, b = (wid >> 1) / groups;
-  const int cpg = c / groups, Lmax = H > W ? H : W;
-  float *mean_s = sm_all + (size_t)warp * 2 * cpg * Lmax, *sm = mean_s + cpg * Lmax;
+  extern __shared__ float sm[];  // conv outputs for this group: [cpg][Lmax], then the group's means [Lmax][cpg]
+  __shared__ float red[2 * (GATE_NT / 32)];
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = c / groups;
+  const int cpg_sh = (cpg & (cpg - 1)) == 0 ? 31 - __clz(cpg) : -1;  // power of two: shifts instead of divisions
   const float *sp_w = params, *gn_w = params + (size_t)c * ks, *gn_b = gn_w + c, *ch_w = gn_b + c;
-  const int L = dir == 0 ? H : W;
-  const int nb = dir == 0 ? 1 : nbands;
-  const float *src = (dir == 0 ? rowm : colm) + (size_t)b * L * nb * c;
-  float *dst = (dir == 0 ? hgate : wgate) + (size_t)b * L * c;
-  const int n = cpg * L;
-  for (int i = lane; i < n; i += 32) {
-    const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
-    float m = 0.f;
-    for (int k = 0; k < nb; ++k) m += src[((size_t)l * nb + k) * c + ch];
-    mean_s[i] = m;
-  }
-  __syncwarp();
-  if (dir == 0) {  // channel gate from the row means
-    for (int ci = lane; ci < cpg; ci += 32) {
+  float *mean_s = sm + cpg * (H > W ? H : W);
+  auto split = [&](int i, int &ci, int &l) {
+    if (cpg_sh >= 0) { ci = i & (cpg - 1); l = i >> cpg_sh; }
+    else { ci = i % cpg; l = i / cpg; }
+  };
+  for (int dir = 0; dir < 2; ++dir) {
+    const int L = dir == 0 ? H : W;
+    const int nb = dir == 0 ? 1 : nbands;
+    const float *src = (dir == 0 ? rowm : colm) + (size_t)b * L * nb * c;
+    float *dst = (dir == 0 ? hgate : wgate) + (size_t)b * L * c;
+    const int n = cpg * L;
+    for (int i = threadIdx.x; i < n; i += GATE_NT) {
+      int ci, l;
+      split(i, ci, l);
       const int ch = g * cpg + ci;
-      float s = 0.f;
-      for (int h = 0; h < H; ++h) s += mean_s[h * cpg + ci];
-      chgate[(size_t)b * c + ch] = 1.f / (1.f + expf(-ch_w[ch * ks + (ks - 1) / 2] * (s / (float)H)));
+      const float *sp = src + (size_t)l * nb * c + ch;
+      float m = 0.f;
+      int k = 0;
+      for (; k + 4 <= nb; k += 4) {  // four band loads in flight, added in band order
+        const float p0 = __ldg(sp + (size_t)k * c), p1 = __ldg(sp + (size_t)(k + 1) * c), p2 = __ldg(sp + (size_t)(k + 2) * c),
+                    p3 = __ldg(sp + (size_t)(k + 3) * c);
+        m += p0; m += p1; m += p2; m += p3;
+      }
+      for (; k < nb; ++k) m += __ldg(sp + (size_t)k * c);
+      mean_s[i] = m;
     }
-  }
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = lane; i < n; i += 32) {
-    const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
-    float a = 0.f;
-    for (int t = 0; t < ks; ++t) {
-      const int ll = l + 2 * t - (ks - 1);  // dilation 2, padding ks-1
-      if (ll >= 0 && ll < L) a = fmaf(sp_w[ch * ks + t], mean_s[ll * cpg + ci], a);
+    __syncthreads();
+    if (dir == 0) {  // channel gate from the row means just staged: one warp-wide strided sum per channel
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int ci = warp; ci < cpg; ci += GATE_NT / 32) {
+        const int ch = g * cpg + ci;
+        float s = 0.f;
+        for (int h = lane; h < H; h += 32) s += mean_s[h * cpg + ci];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) chgate[(size_t)b * c + ch] = 1.f / (1.f + expf(-ch_w[ch * ks + (ks - 1) / 2] * (s / (float)H)));
+      }
     }
-    sm[i] = a;
-    s1 += a;
-    s2 += a * a;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  const float mean = s1 / (float)n;
-  const float var = fmaxf(s2 / (float)n - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) {
-    const int ci = i % cpg, l = i / cpg, ch = g * cpg + ci;
-    const float v = (sm[i] - mean) * rstd * gn_w[ch] + gn_b[ch];
-    dst[(size_t)l * c + ch] = 1.f / (1.f + expf(-v));
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < n; i += GATE_NT) {
+      int ci, l;
+      split(i, ci, l);
+      const int ch = g * cpg + ci;
+      float a = 0.f;
+      for (int t = 0; t < ks; ++t) {
+        const int ll = l + 2 * t - (ks - 1);  // dilation 2, padding ks-1
+        if (ll >= 0 && ll < L) a = fmaf(__ldg(sp_w + ch * ks + t), mean_s[ll * cpg + ci], a);
+      }
+      sm[i] = a;
+      s1 += a;
+      s2 += a * a;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[threadIdx.x >> 5] = s1;
+      red[GATE_NT / 32 + (threadIdx.x >> 5)] = s2;
+    }
+    __syncthreads();
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < GATE_NT / 32; ++w) {
+      t1 += red[w];
+      t2 += red[GATE_NT / 32 + w];
+    }
+    const float mean = t1 / (float)n;
+    const float var = fmaxf(t2 / (float)n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    for (int i = threadIdx.x; i < n; i += GATE_NT) {
+      int ci, l;
+      split(i, ci, l);
+      const int ch = g * cpg + ci;
+      const float v = (sm[i] - mean) * rstd * __ldg(gn_w + ch) + __ldg(gn_b + ch);
+      dst[(size_t)l * c + ch] = __fdividef(1.f, 1.f + __expf(-v));
+    }
+    __syncthreads();
   }
 }
 
 int launch_ela_gate(const float *rowm, const float *colm, const float *params, int c, int B, int H, int W, int ks,
                     int groups, float eps, int nbands, float *hgate, float *wgate, float *chgate, cudaStream_t st) {
   B2Y_REQUIRE(c % groups == 0, B2Y_ERR_INVALID, "ELA: channels %d not divisible by groups %d", c, groups);
+  B2Y_REQUIRE(nbands <= GATE_MAXNB, B2Y_ERR_UNSUPPORTED, "ELA gate: %d column bands (max %d)", nbands, GATE_MAXNB);
   const int L = H > W ? H : W;
-  const size_t smem = (size_t)8 * 2 * (c / groups) * L * sizeof(float);
+  const size_t smem = (size_t)(c / groups) * L * sizeof(float) * 2;
   B2Y_REQUIRE(smem <= 48 * 1024, B2Y_ERR_UNSUPPORTED, "ELA gate: group tile too large");
-  const int total_warps = B * groups * 2;
-  b2y_launch(ela_gate_kernel, dim3(ceil_div(total_warps, 8)), dim3(256), smem, st, rowm, colm, params, c, H, W, ks, groups, eps,
-             nbands < 1 ? 1 : nbands, total_warps, hgate, wgate, chgate);
+  b2y_launch(ela_gate_kernel, dim3(B * groups), dim3(GATE_NT), smem, st, rowm, colm, params, c, H, W, ks, groups, eps,
+             nbands < 1 ? 1 : nbands, hgate, wgate, chgate);
   B2Y_LAUNCH_CHECK();
   return B2Y_OK;
 }
@@ -496,9 +529,11 @@ int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, f
 
 // gate[b,j,ch] = softmax_j(sigmoid(SE_j(gap_j)[ch]))   (MSCA.py:71-77); se_w fp32 [4][c][c], se_b [4][c].
 // block = (8 output channels, a chunk of images): the 4 x 8 weight rows (32 KB at c = 256) are staged in shared memory ONCE
-// and reused for every image of the chunk; one warp per output channel does the 4 dot products of an image.  (One block per
-// image re-read the whole 1 MB weight set from L2 for every image: 268 MB at batch 256.)
-constexpr int GATE_CH = 8;
+// and reused for every image of the chunk; each WARP takes whole images: it loads the image's pooled vectors (4 x c floats,
+// all loads in flight at once) into registers and runs the 32 dot products against shared memory, so eight images are in
+// flight per block.  (v1 re-read the 1 MB weight set per image: 268 MB of L2 traffic at batch 256; v2 walked the images one
+// by one with a memory latency each.)
+constexpr int GATE_CH = 8, GATE_MAXM = 16;  // c <= 32 * GATE_MAXM
 __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict__ gap, const float *__restrict__ se_w,
                                                         const float *__restrict__ se_b, int c, int B, int img_per_cta,
                                                         float *__restrict__ gate) {
@@ -508,34 +543,46 @@ __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 4 * GATE_CH * c; i += blockDim.x) {
     const int k = i % c, r = (i / c) % GATE_CH, j = i / (c * GATE_CH);
-    wsm_gate[i] = (ch0 + r < c) ? se_w[((size_t)j * c + ch0 + r) * c + k] : 0.f;
+    wsm_gate[i] = (ch0 + r < c) ? __ldg(se_w + ((size_t)j * c + ch0 + r) * c + k) : 0.f;
   }
   __syncthreads();
   pdl_wait();
-  const int ch = ch0 + warp;
-  if (ch >= c) return;
   const int b0 = blockIdx.y * img_per_cta, b1 = min(b0 + img_per_cta, B);
-  for (int b = b0; b < b1; ++b) {
-    float z[4];
+  const int nm = (c + 31) / 32;
+  for (int b = b0 + warp; b < b1; b += 8) {
+    float g[4][GATE_MAXM];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float *w = wsm_gate + ((size_t)j * GATE_CH + warp) * c;
-      const float *g = gap + ((size_t)b * 4 + j) * c;
-      float s = 0.f;
-      for (int k = lane; k < c; k += 32) s = fmaf(w[k], g[k], s);
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      z[j] = 1.f / (1.f + expf(-(s + se_b[j * c + ch])));
-    }
-    if (lane == 0) {
-      const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
-      float e[4], t = 0.f;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int m = 0; m < GATE_MAXM; ++m) {
+        const int k = lane + 32 * m;
+        g[j][m] = (m < nm && k < c) ? __ldg(gap + ((size_t)b * 4 + j) * c + k) : 0.f;
+      }
+    for (int r = 0; r < GATE_CH && ch0 + r < c; ++r) {
+      float z[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        e[j] = expf(z[j] - m);
-        t += e[j];
-      }
+        const float *w = wsm_gate + ((size_t)j * GATE_CH + r) * c;
+        float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) gate[((size_t)b * 4 + j) * c + ch] = e[j] / t;
+        for (int m = 0; m < GATE_MAXM; ++m) {
+          const int k = lane + 32 * m;
+          if (m < nm && k < c) s = fmaf(w[k], g[j][m], s);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        z[j] = 1.f / (1.f + expf(-(s + __ldg(se_b + j * c + ch0 + r))));
+      }
+      if (lane == 0) {
+        const float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+        float e[4], t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          e[j] = expf(z[j] - mx);
+          t += e[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gate[((size_t)b * 4 + j) * c + ch0 + r] = e[j] / t;
+      }
     }
   }
 }
@@ -543,12 +590,12 @@ __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict_
 int launch_msca_gate(const float *gap, const float *se_w, const float *se_b, int c, int B, float *gate,
                      cudaStream_t st) {
   const size_t smem = (size_t)4 * GATE_CH * c * sizeof(float);
-  B2Y_REQUIRE(smem <= 96 * 1024, B2Y_ERR_UNSUPPORTED, "msca_gate: c = %d too large", c);
+  B2Y_REQUIRE(smem <= 96 * 1024 && c <= 32 * GATE_MAXM, B2Y_ERR_UNSUPPORTED, "msca_gate: c = %d too large", c);
   if (smem > 48 * 1024)
     B2Y_CUDA_CHECK(cudaFuncSetAttribute(msca_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = ceil_div(c, GATE_CH);
   int chunks = ceil_div(148 * 2, tiles);  // ~2 CTAs per SM in total
-  if (chunks > B) chunks = B;
+  if (chunks > ceil_div(B, 8)) chunks = ceil_div(B, 8);
   const int per = ceil_div(B, chunks);
   b2y_launch(msca_gate_kernel, dim3(dim3(tiles, ceil_div(B, per))), dim3(256), smem, st, gap, se_w, se_b, c, B, per, gate);
   B2Y_LAUNCH_CHECK();

@@ -38,7 +38,6 @@ struct ResolvedOp {
   ConvParams cp;
   ConvTcPlan *tc = nullptr;
   ConvPairPlan *pair = nullptr;
-  C3k2Plan *c3k2 = nullptr;
   int impl = 0;
 };
 
@@ -163,26 +162,6 @@ int resolve_pair(b2y_plan *pl, ResolvedOp &r, int idx, PairParams &q) {
   return B2Y_OK;
 }
 
-int resolve_c3k2(b2y_plan *pl, ResolvedOp &r, int idx, C3k2Params &q) {
-  Resolver R{pl};
-  const b2y_op &o = r.op;
-  const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
-  if (!R.ok) return B2Y_ERR_INVALID;
-  B2Y_REQUIRE(bi->dtype == B2Y_BF16 && bo->dtype == B2Y_BF16 && bi->H == bo->H && bi->W == bo->W &&
-                  o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C,
-              B2Y_ERR_INVALID, "op %d: fused C3k2 views", idx);
-  q.in = reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0]));
-  q.in_cs = bi->C;
-  q.out = R.ptr(o.out, o.out_coff);
-  q.out_cs = bo->C;
-  q.w = R.wptr(o.w_off);
-  q.bias = reinterpret_cast<const float *>(R.wptr(o.b_off));
-  B2Y_REQUIRE(q.w && q.bias, B2Y_ERR_INVALID, "op %d: fused C3k2 needs its packed weights", idx);
-  q.B = pl->B; q.H = bi->H; q.W = bi->W;
-  q.cin = o.cin; q.c = o.ip[0]; q.chid = o.ip[1]; q.cout = o.cout;
-  return B2Y_OK;
-}
-
 int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
   if (idx == pl->mid_op && pl->mid_event) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -196,8 +175,6 @@ int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
   switch (o.kind) {
     case B2Y_OP_CONV_PAIR:
       return launch_conv_pair(r.pair, st);
-    case B2Y_OP_C3K2:
-      return launch_c3k2(r.c3k2, st);
     case B2Y_OP_CONV: {
       if (r.impl == B2Y_IMPL_TCGEN05) {
         static const char *tr = getenv("B2Y_TRACE_OP");  // debug: comma-free single op index, eager launches only
@@ -373,12 +350,6 @@ extern "C" int b2y_plan_create(const b2y_op *ops, int32_t n_ops, const b2y_buf *
       if (rc != B2Y_OK) break;
       rc = conv_pair_plan_create(q, device, &r.pair);
       r.impl = B2Y_IMPL_TCGEN05;
-    } else if (k == B2Y_OP_C3K2) {
-      C3k2Params q;
-      rc = resolve_c3k2(pl, r, i, q);
-      if (rc != B2Y_OK) break;
-      rc = c3k2_plan_create(q, device, &r.c3k2);
-      r.impl = B2Y_IMPL_TCGEN05;
     } else if (k == B2Y_OP_CONV || k == B2Y_OP_DWCONV) {
       rc = resolve_conv(pl, r, i);
       if (rc != B2Y_OK) break;
@@ -419,7 +390,6 @@ extern "C" int b2y_plan_destroy(b2y_plan *pl) {
   for (auto &r : pl->ops) {
     if (r.tc) conv_tc_plan_destroy(r.tc);
     if (r.pair) conv_pair_plan_destroy(r.pair);
-    if (r.c3k2) c3k2_plan_destroy(r.c3k2);
   }
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   if (pl->graph) cudaGraphDestroy(pl->graph);
@@ -470,7 +440,7 @@ void op_regions(const b2y_plan *pl, const ResolvedOp &r, std::vector<Region> &ou
     }
     return;
   }
-  if (o.kind == B2Y_OP_CONV_PAIR || o.kind == B2Y_OP_C3K2) {
+  if (o.kind == B2Y_OP_CONV_PAIR) {
     out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
     out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
     return;

@@ -125,8 +125,6 @@ class Plan:
         # fused Detect decode lives in the tcgen05 conv epilogue only; the SIMT twin keeps raw maps + decode.cu
         self.fuse_decode = bool(fuse_decode) and conv_impl != A.IMPL_SIMT
         self.fuse_pairs = fuse_pairs and os.environ.get("B2Y_FUSE_PAIRS", "1") != "0"  # thin Bottlenecks as one kernel
-        # EXPERIMENTAL, off by default: whole C3k2 blocks (cv1 -> Bottleneck -> cv2) as one kernel (csrc/c3k2_fused.cu)
-        self.fuse_c3k2 = os.environ.get("B2Y_FUSE_C3K2", "0") == "1"
         self.dw_dense = dw_dense  # run small-C depthwise 3x3 convs as block-diagonal tensor-core convs
         # Upsample + Concat + C3k2.cv1 -> half-resolution partial sum + pre-activation add (B2Y_FOLD_UPSAMPLE=0: A/B knob)
         self.fold_upsample = fold_upsample and os.environ.get("B2Y_FOLD_UPSAMPLE", "1") != "0"
@@ -357,10 +355,6 @@ class Plan:
         upsampled on the fly, before the activation of the conv over ``skip`` (RES_PREADD_UP2) -- the upsampled and the
         concatenated tensors are never written."""
         c, nm = n["c"], len(n["m"])
-        if up is None and self.fuse_c3k2 and self.conv_impl != A.IMPL_SIMT:
-            out = self._c3k2_fused(n, x, dest)
-            if out is not None:
-                return out
         if up is not None:
             low, skip, low_first = up
             Hy, Wy = skip.H, skip.W
@@ -380,48 +374,6 @@ class Plan:
         for i, m in enumerate(n["m"]):
             self.inner(m, self.sub(y, (1 + i) * c, c), self.sub(y, (2 + i) * c, c))
         return self.conv(n["cv2"], y, dest)
-
-    def _c3k2_fused(self, n, x, dest):
-        """One OP_C3K2 for a C3k2 block with a single plain Bottleneck (yolo11n layers 2 and 4), or None if the block does
-        not have that shape / no kernel configuration fits.  Weights are packed W0 | W1 | W2 | W3, biases b0 | b1 | b2 | b3."""
-        c = n["c"]
-        if len(n["m"]) != 1 or n["m"][0]["type"] != "Bottleneck":
-            return None
-        m, cv1, cv2 = n["m"][0], n["cv1"], n["cv2"]
-        b1, b2 = m["cv1"], m["cv2"]
-        chid = _r(b1["c2"], 16)
-        cin, cout = x.c, cv2["c2"]
-        conv3 = (("k", (3, 3)), ("s", (1, 1)), ("p", (1, 1)), ("g", 1), ("act", "silu"))
-        conv1 = (("k", (1, 1)), ("s", (1, 1)), ("p", (0, 0)), ("g", 1), ("act", "silu"))
-        if not (m["add"] and x.real == x.c == cv1["c1"] and cv1["c2"] == 2 * c and b1["c1"] == b2["c2"] == c
-                and cv2["c1"] == 3 * c and all(b[k] == v for b in (b1, b2) for k, v in conv3)
-                and all(cv[k] == v for cv in (cv1, cv2) for k, v in conv1)
-                and A.lib().b2y_c3k2_fits(cin, c, chid, cout, 64, x.H, x.W)):
-            return None
-        if dest is None:
-            dest = self.full(self.new_buf(cout, x.H, x.W, name=n["name"]), cout)
-        assert dest.c == cout and (dest.H, dest.W) == (x.H, x.W)
-        w0 = cv1["weight"].reshape(2 * c, cin)
-        w1 = torch.zeros(chid, 9, c)
-        w1[:b1["c2"]] = b1["weight"].permute(0, 2, 3, 1).reshape(b1["c2"], 9, c)
-        bb1 = torch.zeros(chid)
-        bb1[:b1["c2"]] = b1["bias"]
-        w2 = torch.zeros(c, 9, chid)
-        w2[:, :, :b1["c2"]] = b2["weight"].permute(0, 2, 3, 1).reshape(c, 9, b1["c2"])
-        w3 = cv2["weight"].reshape(cout, 3 * c)
-        packed = np.concatenate([_bf16_bits(w0).reshape(-1), _bf16_bits(w1.reshape(chid, -1)).reshape(-1),
-                                 _bf16_bits(w2.reshape(c, -1)).reshape(-1), _bf16_bits(w3).reshape(-1)])
-        bias = torch.cat([cv1["bias"], bb1, b2["bias"], cv2["bias"]]).numpy().astype(np.float32)
-        op = OpSpec(A.OP_C3K2, n["name"], [x], dest, None, A.RES_NONE, cin, cout, cout, (3, 3), (1, 1), (1, 1), 1,
-                    A.IMPL_TCGEN05, self.blob.add(packed), self.blob.add(bias), ip=(c, chid))
-        if self.keep_fp32:
-            op.w_fp32 = (w0.clone(), w1.reshape(chid, -1).clone(), w2.reshape(c, -1).clone(), w3.clone())
-        hw = x.H * x.W
-        op.flops = 2 * hw * (2 * c * cin + 9 * (b1["c2"] * c + c * b1["c2"]) + cout * 3 * c)
-        op.bytes_w = (2 * c * cin + 18 * b1["c2"] * c + cout * 3 * c) * 2
-        op.bytes_alg = (cin + cout) * hw * 2 + op.bytes_w
-        self.ops.append(op)
-        return dest
 
     def sppf(self, n, x, dest):
         c_ = n["cv1"]["c2"]

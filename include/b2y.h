@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define B2Y_ABI_VERSION 4
+#define B2Y_ABI_VERSION 5
 #if defined(__GNUC__)
 #define B2Y_API __attribute__((visibility("default")))
 #else
@@ -66,11 +66,6 @@ enum b2y_op_kind {
                            the second strip of branches 0..2); out = the four branch maps as channel slices [jC, (j+1)C) of
                            one 4C-channel buffer, res = gap (B, 4, C) fp32 = their global average pools.  cin = C,
                            cout = 4C; w_off = packed fp32 parameters (see plan.msca) */
-  B2Y_OP_C3K2 = 15      /* EXPERIMENTAL (never emitted by the default planner; B2Y_FUSE_C3K2=1): a whole C3k2 block with one
-                           Bottleneck (block.py:4148-4156, C2f.forward :3306-3310) in one kernel: cv1 1x1 cin -> 2c, Bottleneck
-                           c -> chid -> c with shortcut, cv2 1x1 3c -> cout.  ip[0] = c, ip[1] = chid (padded to 16);
-                           w_off = packed bf16 W0 [2c][cin] | W1 [chid][9c] | W2 [c][9 chid] | W3 [cout][3c],
-                           b_off = fp32 [2c | chid | c | cout] */
 };
 
 enum b2y_conv_impl { B2Y_IMPL_AUTO = 0, B2Y_IMPL_SIMT = 1, B2Y_IMPL_TCGEN05 = 2 };
@@ -141,8 +136,6 @@ B2Y_API int b2y_plan_num_launches(const b2y_plan *plan);
 B2Y_API int b2y_plan_op_impl(const b2y_plan *plan, int32_t i);
 /* Planner query, no device needed: 1 if B2Y_OP_CONV_PAIR has a kernel configuration for these channels and map size. */
 B2Y_API int b2y_conv_pair_fits(int32_t cin, int32_t chid, int32_t B, int32_t H, int32_t W);
-/* Same query for B2Y_OP_C3K2 (experimental). */
-B2Y_API int b2y_c3k2_fits(int32_t cin, int32_t c, int32_t chid, int32_t cout, int32_t B, int32_t H, int32_t W);
 
 /* ---- preprocess: LetterBox + BGR->RGB + /255 (ultralytics/data/augment.py:1535-1601,
  *      engine/predictor.py:116-134).  src: B x h x w x 3 uint8 (device).  The resized image (uw x uh, OpenCV

@@ -135,59 +135,3 @@ def run_pair_case(name: str, device=0):
     torch.cuda.synchronize()
     emu.run()
     return eng.buffer(out.buf).float().cpu(), emu.bufs[out.buf]
-
-
-# ---- fused C3k2 block (OP_C3K2, experimental / opt-in) cases: name -> (cin, c, cout, H, W, B)
-C3K2_CASES = {
-    "c3k2_32_16_64_160": (32, 16, 64, 160, 160, 3),
-    "c3k2_64_32_128_80": (64, 32, 128, 80, 80, 3),
-    "c3k2_32_16_64_odd": (32, 16, 64, 37, 53, 2),
-    "c3k2_64_16_64_small": (64, 16, 64, 12, 20, 2),
-}
-
-
-def c3k2_node(name: str, cin: int, c: int, cout: int, rng):
-    def cnode(nm, c1, c2, k):
-        return dict(type="Conv", name=nm, c1=c1, c2=c2, k=(k, k), s=(1, 1), p=(k // 2, k // 2), g=1, act="silu",
-                    weight=torch.from_numpy((rng.standard_normal((c2, c1, k, k)) / np.sqrt(c1 * k * k)).astype(np.float32)),
-                    bias=torch.from_numpy(rng.standard_normal(c2).astype(np.float32) * 0.1))
-
-    hid = c // 2
-    m = dict(type="Bottleneck", name=name + ".m.0", cv1=cnode(name + ".m.0.cv1", c, hid, 3), cv2=cnode(name + ".m.0.cv2", hid, c, 3),
-             add=True)
-    return dict(type="C3k2", name=name, c=c, cv1=cnode(name + ".cv1", cin, 2 * c, 1), cv2=cnode(name + ".cv2", 3 * c, cout, 1), m=[m])
-
-
-def build_c3k2_case(name: str, fused: bool):
-    """A single C3k2 block lowered fused (one OP_C3K2) or unfused (cv1, Bottleneck, cv2); returns (plan, x view, out view)."""
-    cin, c, cout, H, W, B = C3K2_CASES[name]
-    rng = np.random.default_rng(sum(map(ord, name)))
-    node = c3k2_node(name, cin, c, cout, rng)
-    plan = Plan.empty(64, 64)
-    plan.fuse_c3k2 = fused
-    xb = plan.new_buf(cin + 16, H, W, name="x")  # channel slices of wider buffers on both sides
-    x = View(xb, 16, cin, H, W)
-    ob = plan.new_buf(cout + 32, H, W, name="out")
-    out = plan.c3k2(node, x, View(ob, 16, cout, H, W))
-    return plan, x, out
-
-
-def run_c3k2_case(name: str, device=0):
-    """Fused C3k2 on the GPU vs the emulator (bf16 storage of the on-chip intermediates emulated); returns (gpu, ref)."""
-    from bs_yolo_b200.engine import Engine
-    from plan_emulator import PlanEmulator
-
-    B = C3K2_CASES[name][5]
-    plan, x, out = build_c3k2_case(name, True)
-    assert len(plan.ops) == 1 and plan.ops[0].kind == A.OP_C3K2, "case must take the fused path"
-    eng = Engine(None, B, 64, 64, device=device, use_graph=False, plan=plan)
-    g = torch.Generator().manual_seed(5)
-    emu = PlanEmulator(plan, B, round_bf16=True)
-    for i, b in enumerate(plan.bufs):
-        v = torch.randn(B, b.H, b.W, b.C, generator=g).to(torch.bfloat16)
-        eng.buffer(i).copy_(v)
-        emu.bufs[i] = v.float()
-    eng.forward()
-    emu.run()
-    torch.cuda.synchronize()
-    return eng.buffer(out.buf).float().cpu(), emu.bufs[out.buf]

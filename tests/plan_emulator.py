@@ -107,30 +107,6 @@ class PlanEmulator:
             y = y + x
         self.put(op.out, y.permute(0, 2, 3, 1), op.cout)
 
-    def op_c3k2(self, op):
-        """B2Y_OP_C3K2: cv1 -> [y0 | y1]; h = conv3x3(y1); y2 = y1 + conv3x3(h); out = cv2([y0 | y1 | y2]), SiLU after
-        every conv (block.py:4148-4156 / :3306-3310 / :3405-3419).  With round_bf16 the three intermediates are rounded
-        where the kernel stores them to shared memory as bf16."""
-        c, chid, cin, cout = op.ip[0], op.ip[1], op.cin, op.cout
-        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
-        n0, n1, n2, n3 = 2 * c * cin, chid * 9 * c, c * 9 * chid, cout * 3 * c
-        if op.w_fp32 is not None and not self.round:
-            w0f, w1f, w2f, w3f = op.w_fp32
-        else:
-            w0f = self.bf16(op.w_off, n0)
-            w1f = self.bf16(op.w_off + 2 * n0, n1)
-            w2f = self.bf16(op.w_off + 2 * (n0 + n1), n2)
-            w3f = self.bf16(op.w_off + 2 * (n0 + n1 + n2), n3)
-        b = self.f32(op.b_off, 2 * c + chid + c + cout)
-        b0, b1, b2, b3 = b[:2 * c], b[2 * c:2 * c + chid], b[2 * c + chid:3 * c + chid], b[3 * c + chid:]
-        rnd = (lambda t: t.to(torch.bfloat16).float()) if self.round else (lambda t: t)
-        y = rnd(F.silu(F.conv2d(x, w0f.reshape(2 * c, cin, 1, 1), b0)))
-        y1 = y[:, c:]
-        h = rnd(F.silu(F.conv2d(y1, w1f.reshape(chid, 3, 3, c).permute(0, 3, 1, 2), b1, padding=1)))
-        y2 = rnd(y1 + F.silu(F.conv2d(h, w2f.reshape(c, 3, 3, chid).permute(0, 3, 1, 2), b2, padding=1)))
-        out = F.silu(F.conv2d(torch.cat([y, y2], 1), w3f.reshape(cout, 3 * c, 1, 1), b3))
-        self.put(op.out, out.permute(0, 2, 3, 1), cout)
-
     def op_dwconv(self, op):
         kh, kw = op.k
         c = op.cout

@@ -41,6 +41,16 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
+        _worker_body(rank, world, q, dist, shard, DetectPipeline, oracle_post)
+    except BaseException as e:  # noqa: BLE001 -- report instead of leaving the parent waiting for the queue
+        q.put((rank, f"{type(e).__name__}: {e}"))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def _worker_body(rank, world, q, dist, shard, DetectPipeline, oracle_post):
+    if True:
         g = _graph()
         frames = _frames(world)
         mk = lambda B: DetectPipeline(g, B, 160, (160, 160), device=rank)  # noqa: E731
@@ -49,7 +59,7 @@ def _worker(rank, world, port, q):
         d, c = sh.predict_frame(frames[rank].cuda())
         torch.cuda.synchronize()
         single = shard.SahiSharder(mk, (300, 400), 160, world=1, rank=0, iou=0.5)
-        tiles = single.slice_tiles(frames[rank].cuda())
+        tiles = single.slice_tiles(frames[rank].cuda().unsqueeze(0)).view(single.B, 160, 160, 3)
         tdets, tcounts = single.pipe(tiles)
         d1, c1 = single.predict_frame(frames[rank].cuda())
         torch.cuda.synchronize()
@@ -78,8 +88,6 @@ def _worker(rank, world, port, q):
             for r in range(world):
                 ok_all = ok_all and all(torch.equal(got[i][0][2 * r:2 * r + 2], allm[r][i].cpu()) for i in range(3))
         q.put((rank, bool(ok_single), bool(ok_oracle), bool(ok_rows), bool(ok_own), bool(ok_all), int(c), sh.B))
-    finally:
-        dist.destroy_process_group()
 
 
 def test_sahi_and_gather_over_nccl_match_single_gpu():
@@ -87,10 +95,21 @@ def test_sahi_and_gather_over_nccl_match_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q), daemon=True) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in procs)
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=300))
+            if len(res[-1]) != 8:   # a worker that raised reports (rank, message): its peer may be stuck in a collective
+                break
+    finally:
+        if len(res) != world or any(len(r) != 8 for r in res):
+            for p in procs:
+                p.terminate()
+    res = sorted(res)
+    assert len(res) == world and all(len(r) == 8 for r in res), res
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

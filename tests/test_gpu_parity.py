@@ -130,18 +130,6 @@ def test_fused_bottleneck_vs_emulator(case):
     assert torch.equal(got[..., :c], ref[..., :c]) and torch.equal(got[..., 2 * c:], ref[..., 2 * c:])
 
 
-@pytest.mark.skipif(os.environ.get("B2Y_FUSE_C3K2") != "1", reason="experimental fused C3k2 kernel: opt-in (B2Y_FUSE_C3K2=1)")
-@pytest.mark.parametrize("case", list(convcase.C3K2_CASES))
-def test_fused_c3k2_vs_emulator(case):
-    """OP_C3K2 (a whole C3k2 block as one kernel, csrc/c3k2_fused.cu): four chained GEMMs with the intermediates in shared
-    memory; zeroed halos at the image border; channel-sliced input/output."""
-    got, ref = convcase.run_c3k2_case(case)
-    cout = convcase.C3K2_CASES[case][2]
-    rel = float((got[..., 16:16 + cout] - ref[..., 16:16 + cout]).norm() / (ref[..., 16:16 + cout].norm() + 1e-12))
-    assert rel < 6e-3, rel
-    assert torch.equal(got[..., :16], ref[..., :16]) and torch.equal(got[..., 16 + cout:], ref[..., 16 + cout:])
-
-
 DW_CASES = {  # name -> (C, k, s, H, W, act, res, in_total, in_off)
     "dw3_64_80": (64, (3, 3), 1, 80, 80, True, None, None, 0),
     "dw3_80_40_res": (80, (3, 3), 1, 40, 40, True, "add", None, 0),
@@ -412,7 +400,7 @@ def test_ela_kernels(c, H, W, B):
     from bs_yolo_b200.plan import Plan, View
     rng = np.random.default_rng(c + H)
     ks = 5
-    node = dict(type="ELA", name="ela", c=c, ks=ks, groups=16, gn_eps=1e-5, coef=(0.5, 0.5, 1.0),
+    node = dict(type="ELA", name="ela", c=c, ks=ks, groups=max(1, c // 16), gn_eps=1e-5, coef=(0.5, 0.5, 1.0),
                 sp_w=torch.from_numpy(rng.standard_normal((c, ks)).astype(np.float32) * 0.5),
                 gn_w=torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.3 + 1),
                 gn_b=torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.3),

@@ -102,41 +102,6 @@ def test_structure_and_alignment():
     assert total > 0 and all(b.offset % 256 == 0 for b in bufs_c)
 
 
-@pytest.mark.parametrize("case", ["c3k2_32_16_64_odd", "c3k2_64_16_64_small"])
-def test_c3k2_fused_lowering_equals_unfused(case):
-    """Experimental OP_C3K2 (opt-in): its op semantics (emulator) and weight packing reproduce the three-op lowering
-    (cv1, Bottleneck, cv2) of the same block on the same input, in fp32 and with bf16 storage emulated."""
-    import convcase
-    from plan_emulator import PlanEmulator
-
-    B = 2
-    outs = []
-    for fused in (False, True):
-        plan, x, out = convcase.build_c3k2_case(case, fused)
-        assert (len(plan.ops) == 1 and plan.ops[0].kind == A.OP_C3K2) if fused else (len(plan.ops) == 3)
-        for rnd in (False, True):
-            emu = PlanEmulator(plan, B, round_bf16=rnd)
-            g = torch.Generator().manual_seed(11)
-            emu.bufs[x.buf] = torch.randn(B, x.H, x.W, plan.bufs[x.buf].C, generator=g).to(torch.bfloat16).float()
-            emu.run()
-            outs.append(emu.bufs[out.buf][..., out.coff:out.coff + out.c].clone())
-    (u32, ubf, f32, fbf) = outs
-    assert float((f32 - u32).norm() / u32.norm()) < 1e-2   # weights are bf16-rounded in the packed blob
-    assert float((fbf - ubf).norm() / ubf.norm()) < 5e-3   # same bf16 operands, same rounding points
-
-
-def test_c3k2_fused_plan_is_opt_in(monkeypatch):
-    plan = Plan(_graph("yolo11n"), 640, 640)
-    assert not any(o.kind == A.OP_C3K2 for o in plan.ops)
-    monkeypatch.setenv("B2Y_FUSE_C3K2", "1")
-    fused = Plan(_graph("yolo11n"), 640, 640)
-    names = [o.name for o in fused.ops if o.kind == A.OP_C3K2]
-    assert names == ["model.2", "model.4"] and len(fused.ops) == len(plan.ops) - 4
-    f0, b0 = plan.work_per_image()
-    f1, b1 = fused.work_per_image()
-    assert abs(f1 - f0) / f0 < 1e-6 and b1 < b0
-
-
 def test_bsyolo_wiring_follows_yaml_literally():
     plan = Plan(_graph("bsyolo_n"), 640, 640)
     assert plan.layer_out[21].c == 448  # 64 + the 384-channel Concat output of layer 13 (SURVEY Appendix B.2)
