@@ -92,7 +92,9 @@ class ClockSampler:
             self.proc.kill()
         num = lambda v: v.replace(".", "").isdigit()  # noqa: E731
         rows = [r for r in self.rows if len(r) >= 7 and num(r[0])]
-        busy = [r for r in rows if num(r[6]) and float(r[6]) >= 50] or rows  # samples taken while the GPU was under load
+        # samples taken while the GPU was under load (nvidia-smi's utilisation is a 1/6-s average: short timed regions between
+        # host-side set-up phases rarely reach 50 %)
+        busy = [r for r in rows if num(r[6]) and float(r[6]) >= 10] or rows
         sm = [float(r[0]) for r in busy]
         mx = [float(r[1]) for r in rows if num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]

@@ -558,32 +558,39 @@ __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict_
         const int k = lane + 32 * m;
         g[j][m] = (m < nm && k < c) ? __ldg(gap + ((size_t)b * 4 + j) * c + k) : 0.f;
       }
-    for (int r = 0; r < GATE_CH && ch0 + r < c; ++r) {
-      float z[4];
+    // 32 dot products (4 branches x 8 channels) per image: every lane accumulates its slice of all 32, then ONE butterfly
+    // transposes and reduces them (31 shuffles instead of 32 x 5): lane l ends up with output l = branch (l >> 3), channel (l & 7)
+    float acc[32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float *w = wsm_gate + ((size_t)j * GATE_CH + r) * c;
-        float s = 0.f;
+    for (int o = 0; o < 32; ++o) {
+      const float *w = wsm_gate + (size_t)o * c;  // [j][r][c] with o = j * GATE_CH + r
+      float s = 0.f;
 #pragma unroll
-        for (int m = 0; m < GATE_MAXM; ++m) {
-          const int k = lane + 32 * m;
-          if (m < nm && k < c) s = fmaf(w[k], g[j][m], s);
-        }
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        z[j] = 1.f / (1.f + expf(-(s + __ldg(se_b + j * c + ch0 + r))));
+      for (int m = 0; m < GATE_MAXM; ++m) {
+        const int k = lane + 32 * m;
+        if (m < nm && k < c) s = fmaf(w[k], g[o >> 3][m], s);
       }
-      if (lane == 0) {
-        const float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
-        float e[4], t = 0.f;
+      acc[o] = s;
+    }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          e[j] = expf(z[j] - mx);
-          t += e[j];
-        }
+    for (int step = 16; step >= 1; step >>= 1) {
+      const bool up = (lane & step) != 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gate[((size_t)b * 4 + j) * c + ch0 + r] = e[j] / t;
+      for (int i = 0; i < step; ++i) {
+        const float send = up ? acc[i] : acc[i + step];
+        const float keep = up ? acc[i + step] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
       }
     }
+    const int j = lane >> 3, r = lane & 7;
+    const bool live = ch0 + r < c;
+    const float z = 1.f / (1.f + expf(-(acc[0] + (live ? __ldg(se_b + j * c + ch0 + r) : 0.f))));
+    float mx = fmaxf(z, __shfl_xor_sync(0xffffffffu, z, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    const float e = expf(z - mx);
+    float t = e + __shfl_xor_sync(0xffffffffu, e, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if (live) gate[((size_t)b * 4 + j) * c + ch0 + r] = e / t;
   }
 }
 
