@@ -187,16 +187,21 @@ __global__ void __launch_bounds__(ELA_NT, 3) ela_stats_kernel(const bf16 *__rest
     for (int i = 0; i < 8; ++i) cs_acc[j][i] = 0.f;
   }
   const bf16 *img = x + (size_t)b * H * W * cs + o * 8;
+  const bf16 *pj[NJ];  // the thread's chunks in row 0 of the image; rows are `rowstride` elements apart (32-bit offsets)
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) pj[j] = img + (has[j] ? wq[j] : 0) * cs;
+  const int rowstride = W * cs;
   pdl_wait();
   for (int g0 = h0; g0 < h1; g0 += rs_rows) {
     for (int r0 = g0; r0 < min(g0 + rs_rows, h1); r0 += 2) {
       uint4 v[2][NJ];
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < 2; ++r) {
+        const int off = (r0 + r) * rowstride;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-          v[r][j] = (r0 + r < h1 && has[j]) ? __ldg(reinterpret_cast<const uint4 *>(img + ((size_t)(r0 + r) * W + wq[j]) * cs))
-                                             : make_uint4(0u, 0u, 0u, 0u);
+          v[r][j] = (r0 + r < h1 && has[j]) ? __ldg(reinterpret_cast<const uint4 *>(pj[j] + off)) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -304,15 +309,15 @@ __global__ void __launch_bounds__(GATE_NT) ela_gate_kernel(const float *__restri
       int ci, l;
       split(i, ci, l);
       const int ch = g * cpg + ci;
-      const float *sp = src + (size_t)l * nb * c + ch;
+      const float *sp = src + l * nb * c + ch;  // (32-bit offsets: an image's slice is < 2^31 elements)
       float m = 0.f;
       int k = 0;
       for (; k + 4 <= nb; k += 4) {  // four band loads in flight, added in band order
-        const float p0 = __ldg(sp + (size_t)k * c), p1 = __ldg(sp + (size_t)(k + 1) * c), p2 = __ldg(sp + (size_t)(k + 2) * c),
-                    p3 = __ldg(sp + (size_t)(k + 3) * c);
+        const float p0 = __ldg(sp), p1 = __ldg(sp + c), p2 = __ldg(sp + 2 * c), p3 = __ldg(sp + 3 * c);
+        sp += 4 * c;
         m += p0; m += p1; m += p2; m += p3;
       }
-      for (; k < nb; ++k) m += __ldg(sp + (size_t)k * c);
+      for (; k < nb; ++k, sp += c) m += __ldg(sp);
       mean_s[i] = m;
     }
     __syncthreads();
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(GATE_NT) ela_gate_kernel(const float *__restri
         float s = 0.f;
         for (int h = lane; h < H; h += 32) s += mean_s[h * cpg + ci];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) chgate[(size_t)b * c + ch] = 1.f / (1.f + expf(-ch_w[ch * ks + (ks - 1) / 2] * (s / (float)H)));
+        if (lane == 0) chgate[(size_t)b * c + ch] = __fdividef(1.f, 1.f + __expf(-ch_w[ch * ks + (ks - 1) / 2] * (s / (float)H)));
       }
     }
     float s1 = 0.f, s2 = 0.f;
@@ -332,9 +337,11 @@ __global__ void __launch_bounds__(GATE_NT) ela_gate_kernel(const float *__restri
       split(i, ci, l);
       const int ch = g * cpg + ci;
       float a = 0.f;
+      const float *wt = sp_w + ch * ks;
+      const float *ms = mean_s + ci + (l - (ks - 1)) * cpg;  // dilation 2, padding ks-1: tap t reads row l + 2t - (ks-1)
       for (int t = 0; t < ks; ++t) {
-        const int ll = l + 2 * t - (ks - 1);  // dilation 2, padding ks-1
-        if (ll >= 0 && ll < L) a = fmaf(__ldg(sp_w + ch * ks + t), mean_s[ll * cpg + ci], a);
+        const int ll = l + 2 * t - (ks - 1);
+        if (ll >= 0 && ll < L) a = fmaf(__ldg(wt + t), ms[2 * t * cpg], a);
       }
       sm[i] = a;
       s1 += a;
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(GATE_NT) ela_gate_kernel(const float *__restri
       split(i, ci, l);
       const int ch = g * cpg + ci;
       const float v = (sm[i] - mean) * rstd * __ldg(gn_w + ch) + __ldg(gn_b + ch);
-      dst[(size_t)l * c + ch] = __fdividef(1.f, 1.f + __expf(-v));
+      dst[l * c + ch] = __fdividef(1.f, 1.f + __expf(-v));
     }
     __syncthreads();
   }
@@ -533,7 +540,9 @@ int launch_gap4(const bf16 *const *br, const int *br_cs, int c, int B, int HW, f
 // all loads in flight at once) into registers and runs the 32 dot products against shared memory, so eight images are in
 // flight per block.  (v1 re-read the 1 MB weight set per image: 268 MB of L2 traffic at batch 256; v2 walked the images one
 // by one with a memory latency each.)
-constexpr int GATE_CH = 8, GATE_MAXM = 16;  // c <= 32 * GATE_MAXM
+constexpr int GATE_CH = 8;
+template <int GATE_MAXM>  // ceil(c / 32): the pooled vectors and the 32 accumulators live in registers (ncu: with a fixed
+                          // bound of 16 the kernel needed 255 registers and issued 6x the instructions at c = 256)
 __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict__ gap, const float *__restrict__ se_w,
                                                         const float *__restrict__ se_b, int c, int B, int img_per_cta,
                                                         float *__restrict__ gate) {
@@ -597,16 +606,20 @@ __global__ void __launch_bounds__(256) msca_gate_kernel(const float *__restrict_
 int launch_msca_gate(const float *gap, const float *se_w, const float *se_b, int c, int B, float *gate,
                      cudaStream_t st) {
   const size_t smem = (size_t)4 * GATE_CH * c * sizeof(float);
-  B2Y_REQUIRE(smem <= 96 * 1024 && c <= 32 * GATE_MAXM, B2Y_ERR_UNSUPPORTED, "msca_gate: c = %d too large", c);
-  if (smem > 48 * 1024)
-    B2Y_CUDA_CHECK(cudaFuncSetAttribute(msca_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2Y_REQUIRE(smem <= 96 * 1024 && c <= 512, B2Y_ERR_UNSUPPORTED, "msca_gate: c = %d too large", c);
   const int tiles = ceil_div(c, GATE_CH);
   int chunks = ceil_div(148 * 2, tiles);  // ~2 CTAs per SM in total
   if (chunks > ceil_div(B, 8)) chunks = ceil_div(B, 8);
   const int per = ceil_div(B, chunks);
-  b2y_launch(msca_gate_kernel, dim3(dim3(tiles, ceil_div(B, per))), dim3(256), smem, st, gap, se_w, se_b, c, B, per, gate);
-  B2Y_LAUNCH_CHECK();
-  return B2Y_OK;
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024) B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    b2y_launch(kern, dim3(dim3(tiles, ceil_div(B, per))), dim3(256), smem, st, gap, se_w, se_b, c, B, per, gate);
+    B2Y_LAUNCH_CHECK();
+    return B2Y_OK;
+  };
+  const int nm = ceil_div(c, 32);
+  return nm <= 1 ? go(msca_gate_kernel<1>) : nm <= 2 ? go(msca_gate_kernel<2>) : nm <= 4 ? go(msca_gate_kernel<4>)
+       : nm <= 8 ? go(msca_gate_kernel<8>) : go(msca_gate_kernel<16>);
 }
 
 // out[b,p,ch] = sum_j gate[b,j,ch] * br_j[b,p,ch]   (MSCA.py:84)
