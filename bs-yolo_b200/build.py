@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb2y.so")
-SOURCES = ["plan.cu", "conv_simt.cu", "conv_tc.cu", "conv_pair.cu", "misc_ops.cu", "pmsfa_dw.cu", "msca.cu", "attention.cu", "preprocess.cu", "decode.cu", "nms.cu"]
+SOURCES = ["plan.cu", "conv_simt.cu", "conv_tc.cu", "conv_pair.cu", "misc_ops.cu", "pmsfa_dw.cu", "msca.cu", "dw3_tile.cu", "attention.cu", "preprocess.cu", "decode.cu", "nms.cu"]
 EXTRA = {"nms.cu": ["-fmad=false"], "preprocess.cu": ["-fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -37,7 +37,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(HERE, "..", "include", "b2y.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "dw_regs.cuh"), os.path.join(HERE, "..", "include", "b2y.h")]
     exe = nvcc()
 
     def compile_one(src: str) -> str:

@@ -152,6 +152,8 @@ struct ConvParams {
 // launchers (one per translation unit); all enqueue on `st` and return a b2y error code
 int launch_conv_simt(const ConvParams &p, cudaStream_t st);
 int launch_dwconv(const ConvParams &p, cudaStream_t st);
+bool dw3_tile_supported(const ConvParams &p);          // dw3_tile.cu: shared-memory tiled depthwise 3x3 (stride 1 | 2)
+int launch_dw3_tile(const ConvParams &p, cudaStream_t st);
 
 struct ConvTcPlan;  // opaque: tensor maps + geometry for one tcgen05 conv
 struct TcConfig {

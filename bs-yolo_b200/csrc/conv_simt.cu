@@ -358,6 +358,10 @@ static int launch_dw_strip(const ConvParams &p, cudaStream_t st) {
 int launch_dwconv(const ConvParams &p, cudaStream_t st) {
   B2Y_REQUIRE(p.cin == p.cout && !p.out_f32, B2Y_ERR_UNSUPPORTED, "depthwise conv needs cin == cout and bf16 output");
   B2Y_REQUIRE(p.res_mode != B2Y_RES_PREADD_UP2, B2Y_ERR_UNSUPPORTED, "depthwise conv: upsampled pre-activation residual");
+  {
+    static const int tile3 = [] { const char *e = getenv("B2Y_DW3_TILE"); return e ? atoi(e) : 1; }();  // A/B knob (default on)
+    if (tile3 && dw3_tile_supported(p)) return launch_dw3_tile(p, st);
+  }
   auto aligned = [&](int v) {
     const uintptr_t m = (uintptr_t)v * 2 - 1;
     bool ok = (p.cout % v == 0) && (p.in_cs % v == 0) && (p.out_cs % v == 0) &&
