@@ -102,16 +102,22 @@ class _Staging:
         nbytes = self.h * self.w * 3
         workers = self.pool._max_workers
 
-        def fill_range(args):  # one task per worker: a contiguous run of frames, copied without the GIL (ctypes)
-            r, lo, a, b_ = args
-            base = self.bufs[r].data_ptr()
+        def fill_range(args):  # one task per worker: a run of frames, copied without the GIL (ctypes.memmove); frames that
+            r, lo, a, b_ = args  # are adjacent in memory (views of one array, a decoder's ring) go in ONE call, so the worker
+            base = self.bufs[r].data_ptr()  # does not have to win the GIL back from the main thread between frames
             view = self.views[r]
-            for j in range(a, b_):
+            j = a
+            while j < b_:
                 f = frames[j]
-                if f.flags.c_contiguous:
-                    ctypes.memmove(base + (j - lo) * nbytes, f.ctypes.data, nbytes)
-                else:
+                if not f.flags.c_contiguous:
                     np.copyto(view[j - lo], f)
+                    j += 1
+                    continue
+                src, k = f.ctypes.data, j + 1
+                while k < b_ and frames[k].flags.c_contiguous and frames[k].ctypes.data == src + (k - j) * nbytes:
+                    k += 1
+                ctypes.memmove(base + (j - lo) * nbytes, src, (k - j) * nbytes)
+                j = k
 
         def produce():
             try:

@@ -1,0 +1,175 @@
+"""Collect the round-2 evidence run (tools/final_evidence.sh r02 -> gpurun_out/) into profiles/: bench lines, per-op tables,
+ncu launch lists (aggregated), the parity audit, and one summary table (profiles/r02_summary.md)."""
+import csv
+import json
+import os
+import shutil
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, PROF, TAG = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles"), "r02"
+HBM, TF_BURST, TF_SUS = 6545.0, 1628.3, 1383.2
+
+
+def last_json(path):
+    for line in reversed(open(path).read().strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise ValueError(path)
+
+
+def launch_list(path):
+    rows = list(csv.DictReader(l for l in open(path) if l.startswith('"')))
+    per = defaultdict(dict)
+    for r in rows:
+        per[int(r["ID"])]["name"] = r["Kernel Name"].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            v = v / 1e3 if u in ("ns", "nsecond") else v if u in ("us", "usecond") else v * 1e3
+        elif r["Metric Name"].startswith("dram__bytes"):
+            v = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        per[int(r["ID"])][r["Metric Name"]] = v
+    return [per[k] for k in sorted(per)]
+
+
+def family_table(launches, title):
+    agg = defaultdict(lambda: [0, 0.0])
+    for L in launches:
+        k = L["name"]
+        agg[k][0] += 1
+        agg[k][1] += L.get("gpu__time_duration.sum", 0.0)
+    tot = sum(a[1] for a in agg.values())
+    lines = [title, f"total {tot:.0f} us over {sum(a[0] for a in agg.values())} launches (cold-cache, serialised: compare shares)", "",
+             "| kernel | launches | us | share |", "|---|---|---|---|"]
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| {k} | {a[0]} | {a[1]:.0f} | {100 * a[1] / tot:.1f}% |")
+    fam = defaultdict(float)
+    for k, a in agg.items():
+        fam[k.split("<")[0]] += a[1]
+    lines += ["", "| kernel family | us | share |", "|---|---|---|"]
+    for k, v in sorted(fam.items(), key=lambda kv: -kv[1]):
+        lines.append(f"| {k} | {v:.0f} | {100 * v / tot:.1f}% |")
+    return lines, fam, tot
+
+
+def main():
+    os.makedirs(PROF, exist_ok=True)
+    b = last_json(f"{OUT}/bench_{TAG}.json")
+    ref = last_json(f"{OUT}/bench_ref_{TAG}.json")
+    bs = last_json(f"{OUT}/bench_bsyolo_{TAG}.json")
+    bx = last_json(f"{OUT}/bench_11x_{TAG}.json")
+    for src, dst in ((f"bench_{TAG}.json", f"{TAG}_bench_final.json"), (f"bench_ref_{TAG}.json", f"{TAG}_bench_reference.json"),
+                     (f"bench_bsyolo_{TAG}.json", f"{TAG}_bench_bsyolo.json"), (f"bench_11x_{TAG}.json", f"{TAG}_bench_yolo11x.json"),
+                     (f"layers_yolo11n_{TAG}.json", f"{TAG}_layers_yolo11n.json"), (f"layers_bsyolo_{TAG}.json", f"{TAG}_layers_bsyolo.json"),
+                     (f"layers_11x_{TAG}.json", f"{TAG}_layers_yolo11x.json"), ("parity_audit.jsonl", f"{TAG}_parity_audit.jsonl")):
+        if os.path.exists(f"{OUT}/{src}"):
+            with open(f"{PROF}/{dst}", "w") as f:
+                f.write(open(f"{OUT}/{src}").read().strip().splitlines()[-1] + "\n" if src.startswith("bench") else open(f"{OUT}/{src}").read())
+    md = [f"# Round-2 evidence summary (`tools/final_evidence.sh {TAG}` on one fresh B200; multi-GPU lines from `tools/gpu_round2_multi.sh`)", "",
+          f"Peaks (MEASURED_PEAKS.json): HBM {HBM:.0f} GB/s copy, bf16 {TF_BURST:.0f} TF/s burst / {TF_SUS:.0f} TF/s sustained.", ""]
+    md += ["## Bench lines", "", "| workload | resident (img/s) | ms/step | end to end (img/s) | network graph ms | conv kernel roofline | network Σfloors ÷ graph | Σfloors ÷ step |",
+           "|---|---|---|---|---|---|---|---|"]
+
+    def row(name, d):
+        r = d["roofline"]
+        return (f"| {name} | {d['value']:,.0f} | {d['ms_per_step']:.3f} | {d['e2e']['value']:,.0f} | {d['stages']['network_graph_ms']:.3f} | "
+                f"{r['frac']:.3f} of {r['peak']:.0f} {r['unit']} ({r['bound']}) | {r['network_roofline_frac']:.3f} | {r.get('step_roofline_frac', 0):.3f} |")
+
+    md.append(row("yolo11n B=64 @640 (configs[1], headline of `bench.py`)", b))
+    w = b.get("workloads", {})
+    if "bsyolo_n" in w and "roofline" in w["bsyolo_n"]:
+        md.append(row("BS-YOLO-n B=256 @640 (configs[2], sub-record)", w["bsyolo_n"]))
+    md.append(row("BS-YOLO-n B=256 @640 (stand-alone run, per-op table)", bs))
+    if "yolo11x" in w and "roofline" in w["yolo11x"]:
+        md.append(row("yolo11x B=32 @1280 (configs[3], sub-record)", w["yolo11x"]))
+    md.append(row("yolo11x B=32 @1280 (stand-alone run)", bx))
+    md += ["", f"Reference arm (`bench.py --impl reference`, unmodified reference on the box's {ref['cpu_baseline']['cores']} host cores, "
+               f"{ref['cpu_baseline']['sample']}): **{ref['value']:.1f} img/s**; in-line `cpu_baseline` of the headline run: "
+               f"{b['cpu_baseline']['value']:.1f} img/s ({b['cpu_baseline']['sample']}).",
+           f"Headline end-to-end ÷ reference arm: {b['e2e']['value'] / ref['value']:.0f}x.", "",
+           f"Clocks during the run: {json.dumps(b['clocks'])}", ""]
+    if "sahi" in w:
+        s = w["sahi"]
+        md.append(f"SAHI config 5, one GPU: {s.get('value', 0):,.0f} frames/s = {s.get('tiles_per_s', 0):,.0f} tiles/s resident, "
+                  f"{(s.get('e2e') or {}).get('value', 0):,.0f} frames/s end to end ({s['config']['frames_per_step']} frames per step).")
+    if "dropin" in w:
+        d = w["dropin"]
+        md.append(f"Drop-in `YOLO.predict(list of {d.get('frames_per_call')} ndarrays, predictor=B200DetectionPredictor)` incl. `Results`: "
+                  f"**{d.get('value', 0):,.0f} img/s** (best of {d.get('best_of')}); host-only staging ceiling of the same frames "
+                  f"(pageable -> pinned ring, all cores, no GPU work): {(d.get('host_staging_ceiling') or {}).get('value', 0):,.0f} img/s "
+                  f"({(d.get('host_staging_ceiling') or {}).get('gbps', 0):.1f} GB/s); `predict_stream` from pinned batches: {b['e2e']['value']:,.0f} img/s.")
+    md.append("")
+    # ---- ncu launch lists of bench.py's timed regions
+    for tag, title in ((TAG, "yolo11n"), (f"{TAG}_bsyolo", "BS-YOLO-n")):
+        p = f"{OUT}/bench_launches_{tag}.csv"
+        if os.path.exists(p):
+            L = launch_list(p)
+            lines, fam, tot = family_table(L, f"## ncu launch list of `bench.py --workload {title.lower().replace('-', '').replace('bsyolon', 'bsyolo_n')} --steps 2 --warmup 3` "
+                                              f"(timed regions only, `--metrics gpu__time_duration.sum --clock-control none`)")
+            md += lines + [""]
+            shutil.copy(p, f"{PROF}/{tag}_bench_launches.csv")
+            if tag == TAG:
+                share = fam.get("conv_tc_kernel", 0) / tot
+                md.append(f"conv_tc_kernel share of the serialised launch list: {share:.3f}; share of the step claimed by the bench line "
+                          f"(`roofline.share_of_step`): {b['roofline']['share_of_step']:.3f}.")
+                md.append("")
+    # ---- eager pass with DRAM bytes and tensor-pipe activity (yolo11n): refresh traffic.json
+    p = f"{OUT}/launches_{TAG}.csv"
+    if os.path.exists(p) and os.path.exists(f"{OUT}/optable_{TAG}.json"):
+        L = launch_list(p)
+        tab = json.load(open(f"{OUT}/optable_{TAG}.json"))
+        ops = tab["ops"]
+        n = tab["launches_per_pass"]
+        L = L[-n:]
+        conv = [(o, l) for o, l in zip(ops, L) if l["name"].startswith("conv_tc_kernel")]
+        dram = sum(l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0) for _, l in conv)
+        alg = sum(o.get("bytes", 0) for o, _ in conv)
+        json.dump({"yolo11n": {"workload": "yolo11n", "batch": tab["batch"], "source": f"ncu launch list {TAG} (tools/ncu_capture.sh)",
+                               "conv_tc_launches_per_step": len(conv), "conv_tc_dram_bytes_per_step": dram,
+                               "conv_tc_alg_bytes_per_step": alg,
+                               "conv_tc_us_per_step_serialised": sum(l["gpu__time_duration.sum"] for _, l in conv),
+                               "all_kernels_us_per_step_serialised": sum(l["gpu__time_duration.sum"] for l in L)}},
+                  open(f"{PROF}/traffic.json", "w"), indent=1)
+        md += ["## One eager pass of yolo11n B=64 under ncu (time, DRAM bytes vs algorithmic bytes, tensor pipe)", "",
+               f"conv_tc_kernel: {len(conv)} launches, DRAM {dram / 1e6:.0f} MB vs algorithmic {alg / 1e6:.0f} MB per pass "
+               f"(ratio {dram / max(alg, 1):.2f}: L2 reuse, no wasted re-reads in aggregate) -> `profiles/traffic.json`.", "",
+               "| launch | layer | kernel | us | DRAM MB | alg MB | tensor pipe % |", "|---|---|---|---|---|---|---|"]
+        for o, l in sorted(zip(ops, L), key=lambda t: -t[1].get("gpu__time_duration.sum", 0))[:25]:
+            md.append(f"| {o['launch']} | {o['name']} | {l['name']} | {l.get('gpu__time_duration.sum', 0):.1f} | "
+                      f"{(l.get('dram__bytes_read.sum', 0) + l.get('dram__bytes_write.sum', 0)) / 1e6:.1f} | {o.get('bytes', 0) / 1e6:.1f} | "
+                      f"{l.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0):.1f} |")
+        md.append("")
+        shutil.copy(p, f"{PROF}/{TAG}_launches_yolo11n.csv")
+    p = f"{OUT}/launches_{TAG}_11x.csv"
+    if os.path.exists(p) and os.path.exists(f"{OUT}/optable_{TAG}_11x.json"):
+        L = launch_list(p)
+        tab = json.load(open(f"{OUT}/optable_{TAG}_11x.json"))
+        ops, n = tab["ops"], tab["launches_per_pass"]
+        L = L[-n:]
+        md += [f"## One eager pass of yolo11x @1280, batch {tab['batch']}, under ncu: the tensor-bound convs", "",
+               "| launch | layer | kernel | us | TFLOP/s | tensor pipe % | DRAM MB |", "|---|---|---|---|---|---|---|"]
+        for o, l in sorted(zip(ops, L), key=lambda t: -t[1].get("gpu__time_duration.sum", 0))[:30]:
+            us = l.get("gpu__time_duration.sum", 0)
+            md.append(f"| {o['launch']} | {o['name']} | {l['name']} | {us:.1f} | {o.get('flops', 0) / max(us, 1e-9) / 1e6:.0f} | "
+                      f"{l.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 0):.1f} | "
+                      f"{(l.get('dram__bytes_read.sum', 0) + l.get('dram__bytes_write.sum', 0)) / 1e6:.0f} |")
+        md.append("")
+        shutil.copy(p, f"{PROF}/{TAG}_launches_yolo11x.csv")
+    # ---- parity audit
+    p = f"{OUT}/parity_audit.jsonl"
+    if os.path.exists(p):
+        md += ["## Final-box parity audit (tests/boxmatch.py; `pytest -m gpu` of this run)", "",
+               "| test | reference boxes | matched | near conf | class flip | IoU tie | cascade | max_det tail | unexplained |", "|---|---|---|---|---|---|---|---|---|"]
+        for line in open(p):
+            a = json.loads(line)
+            md.append(f"| {a['test']} | {a['total']} | {a['matched']} | {a['near_conf']} | {a['class_flip']} | {a['nms_iou_tie']} | "
+                      f"{a['nms_cascade']} | {a['max_det_cut']} | {a['unexplained']} |")
+        md.append("")
+    open(f"{PROF}/{TAG}_summary.md", "w").write("\n".join(md) + "\n")
+    print("\n".join(md[:40]))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
