@@ -190,8 +190,8 @@ class DetectPipeline:
         iterable of pinned host uint8 batches (B,h,w,3) in, one host ``(dets, counts)`` pair per batch out, in order.
         The host->device copy of batch i+1 and the NMS + device->host copy of batch i-1 run on their own streams beside
         the network of batch i, and the result of batch i is handed out after batch i+1 has been enqueued, so neither
-        PCIe nor the host-side wait idles the GPU.  The yielded tensors are pinned buffers that stay valid until two more
-        batches have been requested.
+        PCIe nor the host-side wait idles the GPU (with two network graphs in flight the results run two batches behind).
+        The yielded tensors are pinned buffers that stay valid until two more batches have been requested.
         gather (multi-GPU): False -- every rank yields its own shard; "root" -- rank 0 yields all ranks' detections
         (world*B rows, rank-major; one NCCL gather of the padded detections per batch), the other ranks their own shard;
         True / "all" -- every rank yields all ranks' detections (all-gather: world x the traffic, only if every rank
@@ -207,9 +207,12 @@ class DetectPipeline:
             self._copy_stream2 = torch.cuda.Stream(dev)
         cs, cs2 = self._copy_stream, self._copy_stream2
         split = int(os.environ.get("B2Y_H2D_SPLIT", "1")) >= 2  # A/B knob: the upload as two halves on two copy streams
-        stage, copied, consumed, tickets, outs = [None, None], [None, None], [None, None], [None, None], [None, None]
-        half = [None, None]
-        for k in range(2):
+        # results are handed out `lag` batches behind the submission: 1 keeps one network in flight while the host waits,
+        # 2 (two network graphs in flight, dual_net) lets batch i+1's graph be enqueued while batch i's has barely started
+        lag = 2 if self.dual_net else 1
+        R = lag + 1
+        stage, copied, consumed, tickets, outs, half = ([None] * R for _ in range(6))
+        for k in range(R):
             copied[k], consumed[k], half[k] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
         def upload(frames, k):
@@ -238,30 +241,32 @@ class DetectPipeline:
         nxt = next(it, None)
         if nxt is None:
             return
-        consumed[0].record(main)
-        consumed[1].record(main)
+        for e in consumed:
+            e.record(main)
         upload(nxt, 0)
         rows = self.B
         if gather:
             import torch.distributed as dist
             if gather != "root" or dist.get_rank() == 0:
                 rows = dist.get_world_size() * self.B
-        i, pending = 0, None
+        i = 0
         while nxt is not None:
-            k = i & 1
+            k = i % R
             nxt = next(it, None)
             if nxt is not None:
-                upload(nxt, k ^ 1)  # overlaps the compute of batch i
+                upload(nxt, (i + 1) % R)  # overlaps the compute of batch i
             if outs[k] is None:
                 outs[k] = (None if device_dets else torch.empty(rows, self.max_det, 6, dtype=torch.float32).pin_memory(),
                            torch.empty(rows, dtype=torch.int32).pin_memory())
             tickets[k] = self.submit(stage[k], rescale, consumed=consumed[k], gather=gather, host_out=outs[k],
                                      src_ready=copied[k])
-            if pending is not None:
-                yield self._resolve(tickets[pending], outs[pending], device_dets, main)  # (enqueued by the submit above)
-            pending = k
+            if i >= lag:  # batch i-lag: its post-process was enqueued by an earlier submit
+                j = (i - lag) % R
+                yield self._resolve(tickets[j], outs[j], device_dets, main)
             i += 1
-        yield self._resolve(tickets[pending], outs[pending], device_dets, main)           # (flushes the last batch)
+        for b in range(max(i - lag, 0), i):  # the tail, in order (the last one is flushed here)
+            j = b % R
+            yield self._resolve(tickets[j], outs[j], device_dets, main)
 
     @staticmethod
     def _resolve(ticket, out, device_dets, main):

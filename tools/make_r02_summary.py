@@ -67,7 +67,7 @@ def main():
         if os.path.exists(f"{OUT}/{src}"):
             with open(f"{PROF}/{dst}", "w") as f:
                 f.write(open(f"{OUT}/{src}").read().strip().splitlines()[-1] + "\n" if src.startswith("bench") else open(f"{OUT}/{src}").read())
-    md = [f"# Round-2 evidence summary (`tools/final_evidence.sh {TAG}` on one fresh B200; multi-GPU lines from `tools/gpu_round2_multi.sh`)", "",
+    md = [f"# Round-2 evidence summary (`tools/final_evidence.sh {TAG}` on one fresh B200; multi-GPU lines from `tools/multi_gpu_evidence.sh`)", "",
           f"Peaks (MEASURED_PEAKS.json): HBM {HBM:.0f} GB/s copy, bf16 {TF_BURST:.0f} TF/s burst / {TF_SUS:.0f} TF/s sustained.", ""]
     md += ["## Bench lines", "", "| workload | resident (img/s) | ms/step | end to end (img/s) | network graph ms | conv kernel roofline | network Σfloors ÷ graph | Σfloors ÷ step |",
            "|---|---|---|---|---|---|---|---|"]
