@@ -145,6 +145,8 @@ struct ConvParams {
   int kh, kw, sh, sw, ph, pw, act;
   int asym;                          // 1: padding only before (top/left) -- the 2x2 space-to-depth stem
   int grouped;                       // 1: block-diagonal weights in groups of 16 channels (depthwise on the tensor cores)
+  int dw_chunk, dw_in_stride;        // depthwise only: output channel j reads input channel (j / dw_chunk) * dw_in_stride +
+                                     // j % dw_chunk of the view (0: contiguous) -- Attention.pe over the v slices of qkv
   int epi_mode, a_off, A, nc;        // fused Detect decode (0 none, 1 DFL box, 2 class sigmoid) -> y (B,4+nc,A)
   float det_stride;
 };

@@ -362,6 +362,7 @@ int launch_dwconv(const ConvParams &p, cudaStream_t st) {
     static const int tile3 = [] { const char *e = getenv("B2Y_DW3_TILE"); return e ? atoi(e) : 1; }();  // A/B knob (default on)
     if (tile3 && dw3_tile_supported(p)) return launch_dw3_tile(p, st);
   }
+  B2Y_REQUIRE(p.dw_chunk == 0, B2Y_ERR_UNSUPPORTED, "depthwise conv: a chunked input view needs the tiled 3x3 kernel (C %% 8, 3x3, pad 1)");
   auto aligned = [&](int v) {
     const uintptr_t m = (uintptr_t)v * 2 - 1;
     bool ok = (p.cout % v == 0) && (p.in_cs % v == 0) && (p.out_cs % v == 0) &&

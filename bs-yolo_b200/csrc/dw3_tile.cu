@@ -22,6 +22,7 @@ struct Dw3K {
   const float *w, *bias;  // [9][C], [C]
   int B, H, W, Ho, Wo, C, act;
   int TH, TW, tiles_x, tiles_y, CC, nchunks;  // CC: channels per chunk (multiple of 8)
+  int in_stride;                              // input channels between the chunks (== CC unless the input is a chunked gather)
 };
 
 template <int S>
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(NT, 2) dw3_tile_kernel(Dw3K p) {
   const int cc = min(p.CC, p.C - c0);  // channels of this chunk (multiple of 8)
   const int npairs = cc >> 1, nvec = cc >> 3;
   const int y0 = ty * TH, x0 = tx * TW;
-  const bf16 *img = p.in + (size_t)b * p.H * p.W * p.in_cs + c0;
+  const bf16 *img = p.in + (size_t)b * p.H * p.W * p.in_cs + chunk * p.in_stride;
   pdl_wait();
   {  // stage the input tile: 16-byte vectors, zero outside the map
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(NT, 2) dw3_tile_kernel(Dw3K p) {
 bool dw3_tile_supported(const ConvParams &p) {
   if (!(p.kh == 3 && p.kw == 3 && p.ph == 1 && p.pw == 1 && p.sh == p.sw && (p.sh == 1 || p.sh == 2))) return false;
   if (p.cin != p.cout || p.out_f32 || p.cout % 8 || p.in_cs % 8 || p.out_cs % 2) return false;
+  if (p.dw_chunk && (p.dw_chunk % 8 || p.dw_chunk > 64 || p.dw_in_stride % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(p.in) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 3)) return false;
   if (p.res_mode == B2Y_RES_PREADD_UP2) return false;
   if (p.res_mode && ((p.res_cs % 2) || (reinterpret_cast<uintptr_t>(p.res) & 3))) return false;
@@ -130,6 +132,12 @@ int launch_dw3_tile(const ConvParams &c, cudaStream_t st) {
   p.nchunks = ceil_div(p.C, 64);
   p.CC = (ceil_div(p.C, p.nchunks) + 7) / 8 * 8;
   p.nchunks = ceil_div(p.C, p.CC);
+  p.in_stride = p.CC;
+  if (c.dw_chunk) {  // the input is a gather of equal chunks (Attention.pe: the v slice of every head of qkv)
+    p.CC = c.dw_chunk;
+    p.nchunks = p.C / c.dw_chunk;
+    p.in_stride = c.dw_in_stride;
+  }
   // tile: split the map evenly into tiles of at most 16 x 32 (stride 1) / 8 x 16 (stride 2) outputs, rows in blocks of RO
   const int maxh = S == 1 ? 16 : 8, maxw = S == 1 ? 32 : 16;
   int TH = ceil_div(p.Ho, ceil_div(p.Ho, maxh)), TW = ceil_div(p.Wo, ceil_div(p.Wo, maxw));

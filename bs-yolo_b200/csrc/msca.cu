@@ -15,6 +15,8 @@
 // (dw_regs.cuh): a 20 x 20 map is exactly 160 items per phase = one item per thread.  Lane order runs over (pair, the
 // axis NOT blocked) and the plane pitches are padded to 4 mod 32 words, so every shared-memory access is conflict-free.
 // Intermediates are rounded to bf16 exactly where the unfused path stored them; the means are summed in a fixed order.
+#include <stdlib.h>
+
 #include "dw_regs.cuh"
 
 namespace {
@@ -101,7 +103,8 @@ __device__ __forceinline__ void branch(const MscaK &p, int j, const float *prm, 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT, 3) msca_branch_kernel(MscaK p) {
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) msca_branch_kernel(MscaK p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   const int H = p.H, W = p.W, Hp = p.Hp;
@@ -197,8 +200,12 @@ int launch_msca_branch(const MscaParams &q, cudaStream_t st) {
   const size_t smem = ((size_t)(p.Hp + 4) * p.pitchX + (size_t)q.H * p.pitchA + (size_t)(p.Hp + 2 * HALO) * p.pitchU) * 4 +
                       (size_t)items * 8 + 122 * 2 * CP * 4;
   B2Y_REQUIRE(smem <= 200 * 1024, B2Y_ERR_UNSUPPORTED, "msca_branch: a %dx%d map does not fit shared memory", q.H, q.W);
-  B2Y_CUDA_CHECK(cudaFuncSetAttribute(msca_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  b2y_launch(msca_branch_kernel, dim3((unsigned)(q.B * (q.C / (2 * CP)))), dim3(NT), smem, st, p);
-  B2Y_LAUNCH_CHECK();
-  return B2Y_OK;
+  static const int minb = [] { const char *e = getenv("B2Y_MSCA_MINB"); return e ? atoi(e) : 4; }();  // A/B knob: 3 (128 regs) | 4 (96 regs, measured 7 % faster)
+  auto go = [&](auto kern) -> int {
+    B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    b2y_launch(kern, dim3((unsigned)(q.B * (q.C / (2 * CP)))), dim3(NT), smem, st, p);
+    B2Y_LAUNCH_CHECK();
+    return B2Y_OK;
+  };
+  return minb == 4 ? go(msca_branch_kernel<4>) : go(msca_branch_kernel<3>);
 }

@@ -109,6 +109,14 @@ int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
   c.cin = o.cin; c.cout = o.cout; c.cout_pad = o.cout_pad;
   c.kh = o.kh; c.kw = o.kw; c.sh = o.sh; c.sw = o.sw; c.ph = o.ph; c.pw = o.pw; c.act = o.act;
   c.asym = 0; c.grouped = 0; c.epi_mode = 0; c.a_off = 0; c.A = 0; c.nc = 0; c.det_stride = 0.f;
+  c.dw_chunk = 0; c.dw_in_stride = 0;
+  if (o.kind == B2Y_OP_DWCONV && o.ip[0] > 0) {
+    c.dw_chunk = o.ip[0];
+    c.dw_in_stride = o.ip[1];
+    B2Y_REQUIRE(o.cout % c.dw_chunk == 0 && c.dw_in_stride >= c.dw_chunk &&
+                    o.in_coff[0] + (o.cout / c.dw_chunk - 1) * c.dw_in_stride + c.dw_chunk <= bi->C,
+                B2Y_ERR_INVALID, "op %d: chunked depthwise input view out of range", idx);
+  }
   if (o.kind == B2Y_OP_CONV) {
     c.asym = o.ip[0];
     c.grouped = o.ip[5];
@@ -130,7 +138,7 @@ int resolve_conv(b2y_plan *pl, ResolvedOp &r, int idx) {
   }
   B2Y_REQUIRE(bi->dtype == B2Y_BF16, B2Y_ERR_INVALID, "op %d: conv input must be bf16", idx);
   B2Y_REQUIRE(c.w && c.bias, B2Y_ERR_INVALID, "op %d: conv needs weights and bias", idx);
-  B2Y_REQUIRE(o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C, B2Y_ERR_INVALID,
+  B2Y_REQUIRE((c.dw_chunk || o.in_coff[0] + o.cin <= bi->C) && o.out_coff + o.cout <= bo->C, B2Y_ERR_INVALID,
               "op %d: channel view out of range", idx);
   const int padf = c.asym ? 1 : 2;
   B2Y_REQUIRE(o.sh > 0 && o.sw > 0 && c.Ho == (c.H + padf * c.ph - c.kh) / c.sh + 1 &&
@@ -430,7 +438,8 @@ void op_regions(const b2y_plan *pl, const ResolvedOp &r, std::vector<Region> &ou
     if (b >= 0 && b < (int)pl->bufs.size()) out.push_back(Region{b, 0, 1 << 30, w});
   };
   if (o.kind == B2Y_OP_CONV || o.kind == B2Y_OP_DWCONV) {
-    out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
+    const int span = (o.kind == B2Y_OP_DWCONV && o.ip[0] > 0) ? (o.cout / o.ip[0] - 1) * o.ip[1] + o.ip[0] : o.cin;
+    out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + span, false});
     if (o.res_mode) out.push_back(Region{o.res, o.res_coff, o.res_coff + o.cout, false});
     if (o.kind == B2Y_OP_CONV && o.ip[1]) {
       // fused Detect decode: the six output convs write disjoint rows / anchor ranges of y; nothing in the plan reads y

@@ -16,6 +16,8 @@
 // applied in two row passes (4 + 3 rows) so that at most 56 weight registers are live.
 // The layer is CUDA-core bound (396 MAC per pixel at c = 16 against 64 B of traffic), not HBM bound: the bound quoted
 // in DESIGN.md is the fp32 FMA rate.  t is rounded to bf16 exactly where the unfused path stored it.
+#include <stdlib.h>
+
 #include "dw_regs.cuh"
 
 namespace {
@@ -49,8 +51,8 @@ __device__ __forceinline__ void stage_plane(uint32_t dst_s, const bf16 *img, int
   }
 }
 
-template <int CPQ>  // channel pairs per quarter (c / 8)
-__global__ void __launch_bounds__(NT, 3) pmsfa_dw_kernel(PmsfaK p) {
+template <int CPQ, int MINB>  // channel pairs per quarter (c / 8); CTAs per SM the register budget is sized for
+__global__ void __launch_bounds__(NT, MINB) pmsfa_dw_kernel(PmsfaK p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   constexpr int cpq = CPQ, Q = 2 * CPQ;        // channel pairs / channels per quarter
@@ -229,6 +231,10 @@ int launch_pmsfa_dw(const PmsfaParams &q, cudaStream_t st) {
     B2Y_LAUNCH_CHECK();
     return B2Y_OK;
   };
-  return q.c == 16 ? go(pmsfa_dw_kernel<2>) : q.c == 32 ? go(pmsfa_dw_kernel<4>) : q.c == 64 ? go(pmsfa_dw_kernel<8>)
-                                                                                          : go(pmsfa_dw_kernel<16>);
+  static const int minb = [] { const char *e = getenv("B2Y_PMSFA_MINB"); return e ? atoi(e) : 3; }();  // A/B knob: 3 (159 regs) | 4
+  if (minb == 4)
+    return q.c == 16 ? go(pmsfa_dw_kernel<2, 4>) : q.c == 32 ? go(pmsfa_dw_kernel<4, 4>) : q.c == 64 ? go(pmsfa_dw_kernel<8, 4>)
+                                                                                                  : go(pmsfa_dw_kernel<16, 4>);
+  return q.c == 16 ? go(pmsfa_dw_kernel<2, 3>) : q.c == 32 ? go(pmsfa_dw_kernel<4, 3>) : q.c == 64 ? go(pmsfa_dw_kernel<8, 3>)
+                                                                                                : go(pmsfa_dw_kernel<16, 3>);
 }

@@ -339,8 +339,22 @@ class Plan:
         return {"Bottleneck": self.bottleneck, "PMSFA": self.pmsfa, "C3k": self.c3k}[n["type"]](n, x, dest)
 
     def c3k(self, n, x, dest):
+        """C3k / C3 (block.py:3320-3334): cv3(cat(m(cv1(x)), cv2(x))).  cv1 and cv2 are two 1x1 convs over the same input: with
+        at least two inner blocks they run as ONE conv of 2c_ output channels written straight into the concat buffer (the
+        last inner block then overwrites the cv1 half, which nothing else reads any more) -- one launch less per block on
+        the latency-bound P4/P5 chains."""
         c_ = n["cv1"]["c2"]
         z = self.full(self.new_buf(2 * c_, x.H, x.W, name=n["name"] + ".cat"), 2 * c_)
+        cv1, cv2 = n["cv1"], n["cv2"]
+        if (len(n["m"]) >= 2 and os.environ.get("B2Y_MERGE_C3K", "1") != "0" and c_ % 8 == 0 and cv2["c2"] == c_
+                and all(cv[k] == v for cv in (cv1, cv2) for k, v in (("k", (1, 1)), ("s", (1, 1)), ("g", 1), ("c1", cv1["c1"]),
+                                                                      ("act", cv1["act"])))):
+            both = dict(cv1, c2=2 * c_, name=cv1["name"] + "+cv2")
+            self.conv(both, x, z, wb=(torch.cat([cv1["weight"], cv2["weight"]], 0), torch.cat([cv1["bias"], cv2["bias"]], 0)))
+            t = self.sub(z, 0, c_)
+            for i, m in enumerate(n["m"]):
+                t = self.inner(m, t, self.sub(z, 0, c_) if i == len(n["m"]) - 1 else None)
+            return self.conv(n["cv3"], z, dest)
         t = self.conv(n["cv1"], x)
         for i, m in enumerate(n["m"]):
             t = self.inner(m, t, self.sub(z, 0, c_) if i == len(n["m"]) - 1 else None)
@@ -399,6 +413,24 @@ class Plan:
         self.ops.append(op)
         ao2 = self.full(self.new_buf(c, x.H, x.W, name=a["name"] + ".av_pe"), c)
         pe = a["pe"]
+        vstride = 2 * kd + hd
+        if (self.conv_impl != A.IMPL_SIMT and os.environ.get("B2Y_PE_ONE", "1") != "0" and hd % 8 == 0 and hd <= 64 and vstride % 8 == 0
+                and (qkv.coff + 2 * kd) % 8 == 0 and self.bufs[qkv.buf].C % 8 == 0 and pe["k"] == (3, 3) and pe["s"] == (1, 1)):
+            # pe(v) + attention output (block.py:4286) as ONE depthwise launch: output channel j reads the v slice of head
+            # j // hd of qkv (a chunked input view, dw3_tile.cu) instead of one launch per head
+            wp = pe["weight"].reshape(c, 9).t().contiguous()
+            op = OpSpec(A.OP_DWCONV, pe["name"], [View(qkv.buf, qkv.coff + 2 * kd, hd, x.H, x.W)], ao2, self.full(ao.buf, c), A.RES_ADD,
+                        c, c, c, (3, 3), (1, 1), (1, 1), 1 if pe["act"] == "silu" else 0, A.IMPL_SIMT,
+                        self.blob.add(wp.numpy().astype(np.float32)), self.blob.add(pe["bias"].numpy().astype(np.float32)),
+                        ip=(hd, vstride))
+            op.flops = 2 * c * 9 * x.H * x.W
+            op.bytes_w = c * 9 * 2
+            op.bytes_alg = 3 * c * x.H * x.W * 2 + op.bytes_w
+            self.ops.append(op)
+            add = A.RES_ADD if n["add"] else A.RES_NONE
+            b1 = self.conv(a["proj"], ao2, res=x if n["add"] else None, res_mode=add)
+            f = self.conv(n["ffn"][0], b1)
+            return self.conv(n["ffn"][1], f, dest, res=b1 if n["add"] else None, res_mode=add)
         for h in range(nh):  # pe(v): depthwise 3x3 over the v channels of head h, + attention output (block.py:4286)
             sl = slice(h * hd, (h + 1) * hd)
             sub_node = dict(pe, c1=hd, c2=hd, g=hd, name=f"{pe['name']}[h{h}]")

@@ -110,7 +110,13 @@ class PlanEmulator:
     def op_dwconv(self, op):
         kh, kw = op.k
         c = op.cout
-        x = self.get(op.ins[0]).permute(0, 3, 1, 2)
+        if len(op.ip) >= 2 and op.ip[0] > 0:  # chunked input view: output channel j reads (j // chunk) * stride + j % chunk
+            chunk, stride = op.ip[0], op.ip[1]
+            v = op.ins[0]
+            x = torch.cat([self.bufs[v.buf][..., v.coff + h * stride: v.coff + h * stride + chunk] for h in range(c // chunk)], -1)
+            x = x.permute(0, 3, 1, 2)
+        else:
+            x = self.get(op.ins[0]).permute(0, 3, 1, 2)
         w = self.f32(op.w_off, kh * kw * c).view(kh, kw, c).permute(2, 0, 1).unsqueeze(1)
         y = F.conv2d(x, w, self.f32(op.b_off, c), stride=op.s, padding=op.p, groups=c).permute(0, 2, 3, 1)
         self._epilogue(op, y)
