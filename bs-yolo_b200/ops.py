@@ -150,3 +150,49 @@ def scale_boxes_batched(dets: torch.Tensor, counts: torch.Tensor, img1_shape=Non
     assert geom.shape == (B, 5) and geom.dtype == torch.float32 and geom.device == dets.device
     A.check(A.lib().b2y_scale_boxes(dets.data_ptr(), counts.data_ptr(), geom.data_ptr(), B, max_det, _stream(dets.device)))
     return dets
+
+
+# ---- validator path ------------------------------------------------------------------------------------
+def box_iou(box1: torch.Tensor, box2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """Drop-in for ultralytics.utils.metrics.box_iou (metrics.py:52-71) on CUDA tensors: (N,4) x (M,4) xyxy -> (N,M),
+    bit-identical (one C-ABI call: b2y_box_iou)."""
+    if not (box1.is_cuda and box2.is_cuda):
+        raise A.B2YError("box_iou: CUDA tensors required (no CPU fallback on the B200 path)")
+    box1, box2 = box1.float().contiguous(), box2.float().contiguous()
+    n, m = int(box1.shape[0]), int(box2.shape[0])
+    out = torch.empty(n, m, dtype=torch.float32, device=box1.device)
+    A.check(A.lib().b2y_box_iou(box1.data_ptr(), n, box2.data_ptr(), m, float(eps), out.data_ptr(), _stream(box1.device)))
+    return out
+
+
+def match_predictions_batched(dets: torch.Tensor, counts: torch.Tensor, labels: torch.Tensor, label_counts: torch.Tensor,
+                              iouv) -> torch.Tensor:
+    """DetectionValidator._process_batch (detect/val.py:209-228: box_iou + engine/validator.py:222-258 match_predictions)
+    for a whole batch in one launch.  dets (B, max_det, 6) + counts (B,) as b2y_nms / b2y_scale_boxes leave them; labels
+    (B, max_labels, 5) fp32 rows [cls, x1, y1, x2, y2] in the same coordinates + label_counts (B,) int32; iouv: the
+    thresholds (val.py:41).  Returns tp (B, max_det, niou) bool."""
+    if not (dets.is_cuda and labels.is_cuda):
+        raise A.B2YError("match_predictions: CUDA tensors required (no CPU fallback on the B200 path)")
+    B, max_det, _ = dets.shape
+    assert dets.dtype == torch.float32 and dets.is_contiguous() and counts.dtype == torch.int32
+    assert labels.dtype == torch.float32 and labels.is_contiguous() and labels.shape[0] == B and labels.shape[2] == 5
+    assert label_counts.dtype == torch.int32 and label_counts.shape[0] == B
+    th = [float(t) for t in (iouv.tolist() if hasattr(iouv, "tolist") else iouv)]
+    tp = torch.empty(B, max_det, len(th), dtype=torch.uint8, device=dets.device)
+    A.check(A.lib().b2y_match_predictions(dets.data_ptr(), counts.data_ptr(), labels.data_ptr(), label_counts.data_ptr(),
+                                          (C.c_float * len(th))(*th), len(th), B, max_det, int(labels.shape[1]),
+                                          tp.data_ptr(), _stream(dets.device)))
+    return tp.bool()
+
+
+def preprocess_chw(img_u8: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """DetectionValidator.preprocess (detect/val.py:47-50): the dataloader's letterboxed (B,3,H,W) uint8 RGB batch ->
+    float / 255, written into the network-input buffer `dst` ((B, H/2, W/2, 16) bf16, Engine.input_nhwc)."""
+    if not (img_u8.is_cuda and dst.is_cuda):
+        raise A.B2YError("preprocess_chw: CUDA tensors required (no CPU fallback on the B200 path)")
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[1] == 3
+    img_u8 = img_u8.contiguous()
+    B, _, H, W = (int(v) for v in img_u8.shape)
+    assert dst.dtype == torch.bfloat16 and dst.is_contiguous() and tuple(dst.shape) == (B, H // 2, W // 2, 16), dst.shape
+    A.check(A.lib().b2y_preprocess_chw(img_u8.data_ptr(), B, H, W, dst.data_ptr(), _stream(dst.device)))
+    return dst

@@ -151,6 +151,7 @@ class B200Backend:
     (pt, triton, fp16, stride, names, device, imx, dynamic) and ``warmup`` / ``eval`` / ``__call__``."""
 
     pt, triton, fp16, imx, dynamic, jit, nn_module = True, False, False, False, False, False, True
+    max_engines = 4  # plans kept per backend (one per (batch, H, W)); the validator raises it for rect batches
 
     def __init__(self, det_model, device: torch.device, use_graph: bool = True):
         if device.type != "cuda":
@@ -169,7 +170,7 @@ class B200Backend:
         key = (B, H, W)
         e = self._engines.get(key)
         if e is None:
-            if len(self._engines) >= 4:  # a stream of changing shapes must not accumulate workspaces
+            if len(self._engines) >= self.max_engines:  # a stream of changing shapes must not accumulate workspaces
                 self._engines.pop(next(iter(self._engines)))
             with torch.cuda.device(self.device):
                 e = Engine(self.ir, B, H, W, device=self.device, use_graph=self.use_graph)

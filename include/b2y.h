@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define B2Y_ABI_VERSION 5
+#define B2Y_ABI_VERSION 6
 #if defined(__GNUC__)
 #define B2Y_API __attribute__((visibility("default")))
 #else
@@ -43,7 +43,9 @@ enum b2y_op_kind {
                            decode epilogue 1 = DFL+dist2bbox, 2 = class sigmoid (head.py:100-131) writing y (B,4+nc,A):
                            ip[2] anchor offset, ip[3] A, ip[4] nc, fp[0] stride; ip[5]=1: the weight matrix is diagonal
                            (a depthwise 3x3 lowered to the tensor cores) and may be evaluated in groups of 16 channels   */
-  B2Y_OP_DWCONV = 2,    /* depthwise kh x kw conv + bias (+SiLU) (+residual add); conv.py:224-229, MSCA.py:24-39  */
+  B2Y_OP_DWCONV = 2,    /* depthwise kh x kw conv + bias (+SiLU) (+residual add); conv.py:224-229, MSCA.py:24-39.  ip[0] > 0:
+                           chunked input view -- output channel j reads input channel (j / ip[0]) * ip[1] + j % ip[0] of the view
+                           (Attention.pe over the v slices of qkv, block.py:4286; 3x3 only)                             */
   B2Y_OP_SPPF_POOL = 4, /* three chained MaxPool2d(5,1,2) written to three channel slices; block.py:3145-3149   */
   B2Y_OP_RESAMPLE = 5,  /* channel-slice copy, optionally nearest 2x upsample (nn.Upsample, Concat conv.py:455)  */
   B2Y_OP_ATTN = 6,      /* softmax(q^T k * kd^-0.5) v per head; block.py:4280-4286                               */
@@ -166,6 +168,25 @@ B2Y_API int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float co
 /* ---- scale_boxes + clip_boxes (ultralytics/utils/ops.py:92-127, 319-338) applied in place to dets
  *      (B x max_det x 6); one (gain, padx, pady, w0, h0) record of 5 floats per image (device pointer). */
 B2Y_API int b2y_scale_boxes(void *dets, const void *counts, const void *geom, int32_t B, int32_t max_det, void *stream);
+
+/* ---- validator path: DetectionValidator.preprocess / update_metrics on the device ---------------------
+ *      b2y_preprocess_chw: DetectionValidator.preprocess (ultralytics/models/yolo/detect/val.py:47-50): the dataloader's
+ *      letterboxed (B,3,H,W) uint8 RGB batch -> float / 255, written in the network-input layout of b2y_preprocess
+ *      (dst_format 0).  H even, W % 4 == 0. */
+B2Y_API int b2y_preprocess_chw(const void *src, int32_t B, int32_t H, int32_t W, void *dst, void *stream);
+/*      b2y_box_iou: metrics.box_iou (ultralytics/utils/metrics.py:52-71), bit-exact.  box1 (n,4), box2 (m,4) xyxy fp32,
+ *      iou (n,m) fp32 row-major. */
+B2Y_API int b2y_box_iou(const void *box1, int32_t n, const void *box2, int32_t m, float eps, void *iou, void *stream);
+/*      b2y_match_predictions: DetectionValidator._process_batch (val.py:209-228) = box_iou(gt, det) +
+ *      BaseValidator.match_predictions (ultralytics/engine/validator.py:222-258, use_scipy=False) for a whole batch, bit-exact.
+ *      dets: B x max_det x 6 fp32 [x1,y1,x2,y2,conf,cls] + counts (B int32), as b2y_nms / b2y_scale_boxes leave them;
+ *      labels: B x max_labels x 5 fp32 [cls,x1,y1,x2,y2] in the same coordinate space + label_counts (B int32);
+ *      iouv: niou (<= 16) positive thresholds (host pointer; torch.linspace(0.5, 0.95, 10), val.py:41);
+ *      tp: B x max_det x niou uint8 (rows past counts[b] are zero).  Exact IoU ties between two labels of one detection go
+ *      to the higher label index (numpy's order for the short match lists it insertion-sorts). */
+B2Y_API int b2y_match_predictions(const void *dets, const void *counts, const void *labels, const void *label_counts,
+                          const float *iouv, int32_t niou, int32_t B, int32_t max_det, int32_t max_labels, void *tp,
+                          void *stream);
 
 #ifdef __cplusplus
 }

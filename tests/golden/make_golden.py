@@ -9,6 +9,8 @@ The reference cannot travel to the GPU box, these vectors can.  What each file p
   nms.npz .............. utils/ops.py:167-316 non_max_suppression (+ torchvision.ops.nms) on every tests/kat.py NMS case
   letterbox.npz ........ data/augment.py:1535-1601 LetterBox (cv2.resize / copyMakeBorder)
   predict_<case>.npz ... YOLO(ckpt).predict(list of ndarrays, device="cpu") end to end: Results.boxes.data per image
+  val_match.npz ........ utils/metrics.py:52-71 box_iou and DetectionValidator._process_batch (detect/val.py:209-228 ->
+                         engine/validator.py:222-258 match_predictions) on every tests/kat.py VAL_MATCH case
 """
 import os
 import sys
@@ -83,6 +85,26 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"predict_{case}.npz"), **d)
         print("predict", case, d["n"].tolist())
 
+    val_match()
+
+
+def val_match():
+    """validator: IoU matrix and true-positive matrix of the reference's own validator methods."""
+    ref_import.import_reference()
+    from ultralytics.models.yolo.detect.val import DetectionValidator
+    from ultralytics.utils.metrics import box_iou
+
+    v = object.__new__(DetectionValidator)  # the two methods only read self.iouv (val.py:41)
+    v.iouv = torch.linspace(0.5, 0.95, 10)
+    vm = {"iouv": v.iouv.numpy()}
+    for case in kat.VAL_MATCH_CASES:
+        det, gt, gcls = (torch.from_numpy(a) for a in kat.val_match_case(case))
+        vm[f"{case}__iou"] = box_iou(gt, det[:, :4]).numpy().astype(np.float32)
+        vm[f"{case}__tp"] = v._process_batch(det, gt, gcls).numpy()
+        vm[f"{case}__insum"] = np.float64(det.double().sum() + gt.double().sum() + gcls.double().sum())
+        print("val_match", case, vm[f"{case}__tp"].sum(0).tolist())
+    np.savez_compressed(os.path.join(OUT, "val_match.npz"), **vm)
+
 
 if __name__ == "__main__":
-    main()
+    val_match() if sys.argv[1:] == ["val_match"] else main()  # `make_golden.py val_match` regenerates that file only

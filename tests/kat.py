@@ -128,3 +128,48 @@ def predict_input(name):
 
 def state_dict_checksum(sd) -> float:
     return float(sum(float(v.double().abs().sum()) for v in sd.values()))
+
+
+# ---- validator path: DetectionValidator._process_batch / match_predictions ---------------------------------
+VAL_MATCH_CASES = {  # name -> (detections, labels, classes, seed, kind)
+    "empty_dets": (0, 7, 3, 41, "random"),
+    "empty_labels": (9, 0, 3, 42, "random"),
+    "single_hit": (1, 1, 1, 43, "jitter"),
+    "jitter_40x12": (40, 12, 4, 44, "jitter"),          # detections = jittered copies of the labels: IoU spread over 0.5..1
+    "crowded_300x80": (300, 80, 3, 45, "jitter"),       # max_det detections, several per label, wrong-class look-alikes
+    "random_250x150": (250, 150, 2, 46, "random"),
+    "one_class_200x150": (200, 150, 1, 47, "jitter"),
+    "lowest_index_wins": (6, 2, 1, 48, "quirk"),         # a label's LOWEST-INDEX detection wins, not its best (validator.py:254)
+}
+
+
+def val_match_case(name):
+    """detections (n,6) fp32 [xyxy, conf, cls] sorted by descending conf (as NMS leaves them), gt boxes (m,4), gt classes (m,)."""
+    n, m, nc, seed, kind = VAL_MATCH_CASES[name]
+    rng = np.random.default_rng(seed)
+
+    def boxes(k):
+        c = rng.uniform(40, 600, (k, 2))
+        wh = rng.uniform(16, 160, (k, 2))
+        return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+
+    gt = boxes(m)
+    gcls = rng.integers(0, nc, m).astype(np.float32)
+    if kind == "quirk":
+        gt = np.array([[100, 100, 200, 200], [300, 300, 420, 400]], np.float32)
+        gcls = np.zeros(2, np.float32)
+        d = np.array([[104, 104, 204, 204], [100, 100, 200, 201], [100, 100, 200, 200], [302, 300, 422, 400],
+                      [300, 300, 420, 400], [500, 500, 560, 560]], np.float32)
+        det = np.concatenate([d, np.linspace(0.9, 0.4, 6, dtype=np.float32)[:, None], np.zeros((6, 1), np.float32)], 1)
+        return det, gt, gcls
+    if kind == "jitter" and m:
+        src = rng.integers(0, m, n)
+        wh = (gt[src, 2:] - gt[src, :2])
+        det_b = gt[src] + (rng.normal(0, 0.06, (n, 4)) * np.concatenate([wh, wh], 1)).astype(np.float32)
+        dcls = np.where(rng.random(n) < 0.8, gcls[src], rng.integers(0, nc, n)).astype(np.float32)
+    else:
+        det_b = boxes(n)
+        dcls = rng.integers(0, nc, n).astype(np.float32)
+    conf = np.sort(rng.random(n).astype(np.float32))[::-1]
+    det = np.concatenate([det_b.astype(np.float32), conf[:, None], dcls[:, None]], 1).astype(np.float32)
+    return det, gt, gcls

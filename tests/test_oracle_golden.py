@@ -81,3 +81,37 @@ def test_predict_end_to_end_matches_reference(case, golden_dir):
         assert np.array_equal(d[:, 5], ref[:, 5])
         assert np.abs(d[:, :4] - ref[:, :4]).max() < 2e-2  # pixels (fp32 fold-order noise through the net)
         assert np.abs(d[:, 4] - ref[:, 4]).max() < 1e-4
+
+
+# ---- validator path ------------------------------------------------------------------------------------
+from oracle import oracle_val  # noqa: E402
+
+
+@pytest.mark.parametrize("case", list(kat.VAL_MATCH_CASES))
+def test_val_box_iou_and_match_predictions_bit_exact_vs_reference(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, "val_match.npz"))
+    det, gt, gcls = kat.val_match_case(case)
+    insum = float(det.astype(np.float64).sum() + gt.astype(np.float64).sum() + gcls.astype(np.float64).sum())
+    assert insum == float(g[f"{case}__insum"]), "KAT input drifted"
+    assert np.array_equal(oracle_val.IOUV, g["iouv"])  # == torch.linspace(0.5, 0.95, 10), val.py:41
+    iou = oracle_val.box_iou(gt, det[:, :4])
+    assert iou.shape == g[f"{case}__iou"].shape and iou.tobytes() == g[f"{case}__iou"].tobytes()  # bit-exact
+    tp = oracle_val.process_batch(det, gt, gcls)
+    assert np.array_equal(tp, g[f"{case}__tp"])
+    assert np.array_equal(oracle_val.match_by_definition(det, gt, gcls), g[f"{case}__tp"])  # the kernel's formulation
+
+
+def test_val_match_formulations_agree_on_random_inputs():
+    """match_predictions as the reference runs it (sort + two np.unique) == best label per detection, then the lowest-index
+    detection of every label -- the form the CUDA kernel evaluates -- on many random crowded scenes."""
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        m, n, nc = int(rng.integers(1, 30)), int(rng.integers(1, 120)), int(rng.integers(1, 4))
+        c, wh = rng.uniform(50, 300, (m, 2)), rng.uniform(20, 90, (m, 2))
+        gt = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        gcls = rng.integers(0, nc, m).astype(np.float32)
+        src = rng.integers(0, m, n)
+        box = gt[src] + rng.normal(0, 6, (n, 4)).astype(np.float32)
+        det = np.concatenate([box, np.sort(rng.random((n, 1)).astype(np.float32), 0)[::-1],
+                              np.where(rng.random(n) < 0.85, gcls[src], 0).astype(np.float32)[:, None]], 1).astype(np.float32)
+        assert np.array_equal(oracle_val.process_batch(det, gt, gcls), oracle_val.match_by_definition(det, gt, gcls))

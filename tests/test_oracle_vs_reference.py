@@ -68,3 +68,44 @@ def test_dropin_predictor_plugs_into_predict_and_refuses_cpu(tmp_path):
     with pytest.raises(A.B2YError, match="no CPU fallback"):
         YOLO(path).predict([np.zeros((64, 64, 3), np.uint8)], predictor=B200DetectionPredictor, device="cpu", imgsz=64,
                            verbose=False)
+
+
+def test_validator_label_rows_match_reference_prepare_batch():
+    """Host logic of the drop-in validator (bs_yolo_b200/validator.py:_label_rows) and the oracle's prepare_labels against
+    the reference's own DetectionValidator._prepare_batch (detect/val.py:104-115) on a rect-style batch: bit-exact."""
+    ref_import.import_reference()
+    from ultralytics.models.yolo.detect.val import DetectionValidator
+
+    from bs_yolo_b200.validator import _label_rows
+    from oracle import oracle_val
+
+    rng = np.random.default_rng(11)
+    nb, H, W = 5, 128, 160
+    ori = [(240, 320), (97, 133), (128, 160), (300, 333), (64, 400)]
+    ratio_pad, counts = [], [7, 0, 3, 12, 1]
+    for (h0, w0) in ori:
+        r = min(H / h0, W / w0)
+        nh, nw = int(round(h0 * r)), int(round(w0 * r))
+        ratio_pad.append(((nh / h0, nw / w0), (round((W - nw) / 2 - 0.1), round((H - nh) / 2 - 0.1))))
+    idx = np.concatenate([np.full(c, i) for i, c in enumerate(counts)]).astype(np.float32)
+    n = int(sum(counts))
+    cxy, wh = rng.uniform(0.05, 0.95, (n, 2)), rng.uniform(0.02, 0.6, (n, 2))
+    batch = {"img": torch.zeros(nb, 3, H, W, dtype=torch.uint8), "batch_idx": torch.from_numpy(idx),
+             "cls": torch.from_numpy(rng.integers(0, 12, (n, 1)).astype(np.float32)),
+             "bboxes": torch.from_numpy(np.concatenate([cxy, wh], 1).astype(np.float32)),
+             "ori_shape": ori, "ratio_pad": ratio_pad}
+    v = object.__new__(DetectionValidator)
+    v.device = torch.device("cpu")
+    rows, nl, per_image = _label_rows(batch, nb, (H, W), torch.device("cpu"))
+    assert nl.tolist() == counts and rows.shape == (nb, max(counts), 5)
+    for si in range(nb):
+        ref = v._prepare_batch(si, batch)
+        cls, bbox = per_image[si]
+        assert torch.equal(cls, ref["cls"]) and bbox.shape == ref["bbox"].shape
+        if counts[si]:
+            assert bbox.numpy().tobytes() == ref["bbox"].numpy().tobytes()
+            assert torch.equal(rows[si, : counts[si], 1:], ref["bbox"]) and torch.equal(rows[si, : counts[si], 0], ref["cls"])
+            sel = idx == si
+            mine = oracle_val.prepare_labels(batch["bboxes"].numpy()[sel], (H, W), ori[si], ratio_pad[si])
+            assert mine.tobytes() == ref["bbox"].numpy().tobytes()
+        assert float(rows[si, counts[si]:].abs().sum()) == 0.0
