@@ -62,6 +62,7 @@ class HostFrames:
 
     def __init__(self, frames, src_hw, canvas_hw, device):
         self.frames = frames
+        self.pinned = getattr(frames, "pinned", None)  # ingest.PinnedFrames: the pixels already sit in a pinned block
         self.src_hw, self.canvas_hw = src_hw, canvas_hw
         self.shape = torch.Size((len(frames), 3, *canvas_hw))
         self.device = device
@@ -239,6 +240,19 @@ def _build_class():
             self.device = self.model.device
             self.args.half = False
 
+        def setup_source(self, source):
+            """engine/predictor.py:298-323, then: a source of image FILES gets the prefetching loader (ingest.py) in place of
+            LoadImagesAndVideos -- parallel decode ahead of the GPU, batches handed over in pinned memory."""
+            super().setup_source(source)
+            from ultralytics.data.loaders import LoadImagesAndVideos
+
+            from .ingest import PrefetchImageLoader
+
+            ds = self.dataset
+            if (type(ds) is LoadImagesAndVideos and ds.bs > 1 and not any(ds.video_flag) and os.environ.get("B2Y_INGEST", "1") != "0"
+                    and not any(f.rsplit(".", 1)[-1].lower() == "heic" for f in ds.files)):
+                self.dataset = PrefetchImageLoader(ds)
+
         def preprocess(self, im):
             dev = self.device
             if isinstance(im, torch.Tensor):  # tensor sources skip LetterBox (predictor.py:123-134)
@@ -283,8 +297,13 @@ def _build_class():
             names, paths, origs = self.model.names, self.batch[0], im.frames
             results = []
             with torch.cuda.device(self.device):
-                stream = pipe.predict_stream(staging.chunks(im.frames), rescale=True, device_dets=True,
-                                             uploaded=staging.uploaded)
+                blk = im.pinned
+                if blk is not None and all(lo + B <= blk.shape[0] for lo in range(0, n, B)):
+                    # the loader already put the batch into pinned memory (ingest.py): upload it from there, chunk by chunk
+                    stream = pipe.predict_stream((blk[lo: lo + B] for lo in range(0, n, B)), rescale=True, device_dets=True)
+                else:
+                    stream = pipe.predict_stream(staging.chunks(im.frames), rescale=True, device_dets=True,
+                                                 uploaded=staging.uploaded)
                 for c, (dets, counts) in enumerate(stream):
                     lo = c * B
                     cnt = counts.tolist()

@@ -109,3 +109,46 @@ def test_validator_label_rows_match_reference_prepare_batch():
             mine = oracle_val.prepare_labels(batch["bboxes"].numpy()[sel], (H, W), ori[si], ratio_pad[si])
             assert mine.tobytes() == ref["bbox"].numpy().tobytes()
         assert float(rows[si, counts[si]:].abs().sum()) == 0.0
+
+
+def test_prefetch_image_loader_matches_reference_loader(tmp_path):
+    """ingest.PrefetchImageLoader against the reference's LoadImagesAndVideos (data/loaders.py:284-449) on a
+    directory with an unreadable file and one odd-shaped image: same batches, paths, info strings, pixels and counts; the
+    pinned block of a same-shape batch holds the same pixels in order, a ragged batch has none."""
+    cv2 = pytest.importorskip("cv2")
+    ref_import.import_reference()
+    from ultralytics.data.loaders import LoadImagesAndVideos
+
+    from bs_yolo_b200.ingest import PinnedFrames, PrefetchImageLoader
+
+    rng = np.random.default_rng(2)
+    for i in range(11):
+        shape = (50, 70, 3) if i == 9 else (48, 64, 3)
+        cv2.imwrite(str(tmp_path / f"im{i:02d}.png"), rng.integers(0, 256, shape, dtype=np.uint8))
+    (tmp_path / "im03b.png").write_bytes(b"not a png at all")
+    ref = LoadImagesAndVideos(str(tmp_path), batch=4)
+    ours = PrefetchImageLoader(LoadImagesAndVideos(str(tmp_path), batch=4))
+    assert len(ours) == len(ref) and ours.bs == ref.bs and ours.files == ref.files and ours.mode == "image"
+    for _ in range(2):  # iterable twice, like the reference's
+        it_r, it_o, nb = iter(ref), iter(ours), 0
+        while True:
+            try:
+                pr, ir_, sr = next(it_r)
+            except StopIteration:
+                with pytest.raises(StopIteration):
+                    next(it_o)
+                break
+            po, io, so = next(it_o)
+            nb += 1
+            assert po == pr and so == sr and ours.count == ref.count and isinstance(io, PinnedFrames) and len(io) == len(ir_)
+            assert all(np.array_equal(a, b) for a, b in zip(io, ir_))
+            if len({a.shape for a in ir_}) == 1:
+                assert io.pinned is not None and np.array_equal(io.pinned.numpy()[: len(io)], np.stack(ir_))
+            else:
+                assert io.pinned is None
+        assert nb == 3
+    class VideoLoader:  # a loader over a video file keeps the reference's sequential decoder
+        video_flag, files, nf, ni, bs, vid_stride = [True], ["a.mp4"], 1, 0, 2, 1
+
+    with pytest.raises(ValueError):
+        PrefetchImageLoader(VideoLoader())
