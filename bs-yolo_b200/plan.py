@@ -346,7 +346,7 @@ class Plan:
         c_ = n["cv1"]["c2"]
         z = self.full(self.new_buf(2 * c_, x.H, x.W, name=n["name"] + ".cat"), 2 * c_)
         cv1, cv2 = n["cv1"], n["cv2"]
-        if (len(n["m"]) >= 2 and os.environ.get("B2Y_MERGE_C3K", "1") != "0" and c_ % 8 == 0 and cv2["c2"] == c_
+        if (len(n["m"]) >= 2 and os.environ.get("B2Y_MERGE_C3K", "0") == "1" and c_ % 8 == 0 and cv2["c2"] == c_
                 and all(cv[k] == v for cv in (cv1, cv2) for k, v in (("k", (1, 1)), ("s", (1, 1)), ("g", 1), ("c1", cv1["c1"]),
                                                                       ("act", cv1["act"])))):
             both = dict(cv1, c2=2 * c_, name=cv1["name"] + "+cv2")
@@ -414,7 +414,7 @@ class Plan:
         ao2 = self.full(self.new_buf(c, x.H, x.W, name=a["name"] + ".av_pe"), c)
         pe = a["pe"]
         vstride = 2 * kd + hd
-        if (self.conv_impl != A.IMPL_SIMT and os.environ.get("B2Y_PE_ONE", "1") != "0" and hd % 8 == 0 and hd <= 64 and vstride % 8 == 0
+        if (self.conv_impl != A.IMPL_SIMT and os.environ.get("B2Y_PE_ONE", "0") == "1" and hd % 8 == 0 and hd <= 64 and vstride % 8 == 0
                 and (qkv.coff + 2 * kd) % 8 == 0 and self.bufs[qkv.buf].C % 8 == 0 and pe["k"] == (3, 3) and pe["s"] == (1, 1)):
             # pe(v) + attention output (block.py:4286) as ONE depthwise launch: output channel j reads the v slice of head
             # j // hd of qkv (a chunked input view, dw3_tile.cu) instead of one launch per head

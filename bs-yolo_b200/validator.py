@@ -23,12 +23,35 @@ No CPU fallback: a non-CUDA device, ``half=True``, ``augment``, ``save_hybrid`` 
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _cabi as A
 from .ops import match_predictions_batched, nms_raw, preprocess_chw
 
 _CLS = None
+_BACKENDS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # model -> (device, weights fingerprint, B200Backend)
+
+
+def _fingerprint(model) -> int:
+    """Changes whenever a parameter or buffer is replaced or written in place (optimizer step, load_state_dict, .half())."""
+    return hash(tuple((t.data_ptr(), t._version) for t in list(model.parameters()) + list(model.buffers())))
+
+
+def _backend_for(model, device):
+    """Lowered plans are kept per live model object, so that a second ``model.val()`` does not lower, autotune and
+    capture again; a model whose weights changed since is lowered afresh."""
+    from .predictor import B200Backend
+
+    fp = _fingerprint(model)
+    hit = _BACKENDS.get(model)
+    if hit is not None and hit[0] == device and hit[1] == fp:
+        return hit[2]
+    backend = B200Backend(model, device)
+    backend.max_engines = 8  # rect batches: one plan per (batch, H, W); keep more of them than the predictor does
+    _BACKENDS[model] = (device, fp, backend)
+    return backend
 
 
 def _label_rows(batch, nb: int, imgsz, device):
@@ -79,7 +102,7 @@ def _build_class():
     from ultralytics.utils.ops import Profile
     from ultralytics.utils.torch_utils import select_device
 
-    from .predictor import B200Backend, PreprocessedBatch
+    from .predictor import PreprocessedBatch
 
     class B200DetectionValidator(DetectionValidator):
         """DetectionValidator whose preprocess / inference / NMS / box scaling / TP matching run as sm_100a kernels."""
@@ -106,8 +129,7 @@ def _build_class():
             if isinstance(model, (str, bytes)) or hasattr(model, "__fspath__"):
                 from ultralytics.nn.tasks import attempt_load_weights  # the reference's own loader, unchanged
                 model = attempt_load_weights(str(model), device="cpu", inplace=True, fuse=False)
-            backend = B200Backend(model, torch.device(select_device(a.device, a.batch)))
-            backend.max_engines = 8  # rect batches: one plan per (batch, H, W); keep more of them than the predictor does
+            backend = _backend_for(model, torch.device(select_device(a.device, a.batch)))
             self.backend, self.device = backend, backend.device
             a.half = False
             self.stride = backend.stride

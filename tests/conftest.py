@@ -28,3 +28,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _pin_cuda_device_count():
+    """The reference's select_device("cpu") sets CUDA_VISIBLE_DEVICES=-1 in this process (utils/torch_utils.py:176); the first
+    torch.cuda.device_count() after that would cache 0 for good and a later device=0 call of the SAME reference function
+    would be refused.  Cache the true count while the environment is still intact (tests mix CPU reference runs with ours)."""
+    import torch
+
+    if torch.cuda.is_available():
+        torch.cuda.init()
+        torch.cuda.device_count()
+    yield

@@ -214,6 +214,22 @@ def test_network_heads_vs_reference_golden(case, golden_dir):
         assert rel < 1e-2, (case, i, rel)
 
 
+@pytest.mark.parametrize("case", ["yolo11n_64x96", "yolo11x_64x64"])
+def test_opt_in_launch_merges_vs_reference_golden(case, golden_dir, monkeypatch):
+    """B2Y_MERGE_C3K=1 / B2Y_PE_ONE=1 (opt-in: C3k cv1+cv2 as one conv; Attention.pe as one chunked depthwise launch,
+    dw3_tile.cu's gathered input view) stay parity-green against the reference's head maps."""
+    monkeypatch.setenv("B2Y_MERGE_C3K", "1")
+    monkeypatch.setenv("B2Y_PE_ONE", "1")
+    gld = np.load(os.path.join(golden_dir, f"net_{case}.npz"))
+    g = _graph(kat.NET_CASES[case][0])
+    eng = _run_engine(g, torch.from_numpy(kat.net_input(case)), fuse_decode=False)
+    assert any(o.kind == A.OP_DWCONV and o.ip[0] > 0 for o in eng.plan.ops)
+    for i in range(3):
+        ref = torch.from_numpy(gld[f"raw{i}"])
+        got = eng.raw(i).permute(0, 3, 1, 2).float().cpu()
+        assert float((got - ref).norm() / ref.norm()) < 1e-2, (case, i)
+
+
 @pytest.mark.parametrize("model", ["yolo11n", "bsyolo_n"])
 def test_layerwise_vs_oracle(model):
     """Every top-level layer output, read through its channel-slice view, against the fp32 oracle."""
