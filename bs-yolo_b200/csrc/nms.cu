@@ -21,6 +21,7 @@ constexpr int NT = 1024;
 constexpr int CH = 64;            // candidates per greedy step
 constexpr int MAX_KEPT = 1024;    // upper bound on max_det
 constexpr int SMEM_SORT = 8192;   // keys sorted in shared memory (64 KB); larger sets sort in global memory
+constexpr int PRESEL_K = 6144;    // images with more than SMEM_SORT candidates: the top PRESEL_K (+ score ties) are tried first
 constexpr size_t SMEM_DYN = (size_t)SMEM_SORT * 8;
 
 struct ClassMask {
@@ -33,6 +34,7 @@ struct NmsParams {
   int B, nc, A, S;    // S slots per image
   float conf, iou_f, max_wh;
   int max_det, max_nms, agnostic, multi_label;
+  int preselect;      // 1: top-PRESEL_K preselection for images with more than SMEM_SORT candidates (validator mode)
   float *slot_score;  // B x S
   int *slot_cls;      // B x A (single label)
   unsigned long long *keys;  // B x P2 (P2 = pow2 >= S)
@@ -109,6 +111,70 @@ __device__ void bitonic_sort(unsigned long long *k, int P) {
   __syncthreads();
 }
 
+// Exclusive block scan of one count per thread: returns this thread's offset, `total` = the sum.  `scan` (NT/32 ints)
+// and `s_total` are shared scratch, reusable when the call returns.
+__device__ __forceinline__ int block_scan_excl(int cnt, int *scan, int *s_total, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int v = scan[lane];
+    int iv = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += u;
+    }
+    scan[lane] = iv - v;  // exclusive warp offsets
+    if (lane == 31) *s_total = iv;
+  }
+  __syncthreads();
+  total = *s_total;
+  const int off = scan[warp] + incl - cnt;
+  __syncthreads();
+  return off;
+}
+
+// The K-th smallest 32-bit score key (~score bits: ascending key = descending score) among the candidate slots
+// [s0, s1) of all threads: three radix passes (12 + 12 + 8 bits) with a shared-memory histogram (4096 ints).  Exact.
+// Requires at least K candidates in total.
+__device__ unsigned kth_score_key(const float *score, int s0, int s1, int K, int *hist, int *s_sel) {
+  unsigned prefix = 0, mask = 0;
+  const int shifts[3] = {20, 8, 0}, bits[3] = {12, 12, 8};
+  for (int r = 0; r < 3; ++r) {
+    const int nb = 1 << bits[r], sh = shifts[r];
+    for (int i = threadIdx.x; i < nb; i += NT) hist[i] = 0;
+    __syncthreads();
+    for (int s = s0; s < s1; ++s) {
+      const float v = score[s];
+      if (v >= 0.f) {
+        const unsigned key = ~__float_as_uint(v);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, d = 0;
+      for (; d < nb - 1; ++d) {
+        if (cum + hist[d] >= K) break;
+        cum += hist[d];
+      }
+      s_sel[0] = d;
+      s_sel[1] = K - cum;
+    }
+    __syncthreads();
+    prefix |= (unsigned)s_sel[0] << sh;
+    mask |= (unsigned)(nb - 1) << sh;
+    K = s_sel[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
 __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -122,7 +188,7 @@ __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
   __shared__ int canchor[CH];
   __shared__ int csup[CH];
   __shared__ unsigned long long cmask[CH];
-  __shared__ int s_newkept[CH], s_nnew, s_nk;
+  __shared__ int s_newkept[CH], s_nnew, s_nk, s_sel[2];
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *score = p.slot_score + (size_t)b * p.S;
@@ -133,25 +199,8 @@ __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
   const int s0 = min(tid * per, p.S), s1 = min(s0 + per, p.S);
   int cnt = 0;
   for (int s = s0; s < s1; ++s) cnt += (score[s] >= 0.f);
-  int incl = cnt;
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) scan[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int v = scan[lane];
-    int iv = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, iv, o);
-      if (lane >= o) iv += u;
-    }
-    scan[lane] = iv - v;  // exclusive warp offsets
-    if (lane == 31) s_total = iv;
-  }
-  __syncthreads();
-  const int n = s_total;
+  int n;
+  const int off_all = block_scan_excl(cnt, scan, &s_total, n);
   if (n == 0) {
     if (tid == 0) p.counts[b] = 0;
     for (int i = tid; i < p.max_det * 6; i += NT) p.dets[(size_t)b * p.max_det * 6 + i] = 0.f;  // padded rows are defined
@@ -159,95 +208,114 @@ __global__ void __launch_bounds__(NT) nms_select_kernel(NmsParams p) {
       for (int i = tid; i < p.max_det; i += NT) p.kept_anchor[(size_t)b * p.max_det + i] = 0;
     return;
   }
-  int P = 1;
-  while (P < n) P <<= 1;
-  unsigned long long *keys = (P <= SMEM_SORT) ? skeys : gkeys;
-  {
-    int pos = scan[warp] + incl - cnt;
+  // Images with more candidates than the shared-memory sort holds (validator mode: conf 0.001, multi_label, up to A * nc
+  // slots): attempt 0 sorts only the PRESEL_K best candidates (+ everything tied with the last of them), found by an exact
+  // radix select.  The greedy scan visits candidates in sorted order and never looks ahead, so whenever it reaches max_det
+  // (or max_nms) inside that prefix the result IS the full result; if it runs out of candidates first, attempt 1 redoes
+  // the image with every candidate.
+  const bool can_preselect = p.preselect && n > SMEM_SORT;
+  const float *pb = p.pred + (size_t)b * (4 + p.nc) * p.A;
+  for (int attempt = can_preselect ? 0 : 1; attempt < 2; ++attempt) {
+    unsigned T = 0xffffffffu;  // candidates with key32 <= T take part
+    int n1 = n, pos = off_all;
+    if (attempt == 0) {
+      T = kth_score_key(score, s0, s1, PRESEL_K, reinterpret_cast<int *>(skeys), s_sel);
+      int c1 = 0;
+      for (int s = s0; s < s1; ++s) {
+        const float v = score[s];
+        c1 += (v >= 0.f && ~__float_as_uint(v) <= T);
+      }
+      pos = block_scan_excl(c1, scan, &s_total, n1);
+    }
+    int P = 1;
+    while (P < n1) P <<= 1;
+    unsigned long long *keys = (P <= SMEM_SORT) ? skeys : gkeys;
     for (int s = s0; s < s1; ++s) {
       const float v = score[s];
-      if (v >= 0.f) keys[pos++] = ((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned)s;
+      if (v >= 0.f && ~__float_as_uint(v) <= T) keys[pos++] = ((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned)s;
     }
-  }
-  __syncthreads();
-  for (int i = n + tid; i < P; i += NT) keys[i] = ~0ull;
-  // ---- 2. sort: descending score, ascending slot
-  bitonic_sort(keys, P);
-  const int m = min(n, p.max_nms);
+    __syncthreads();
+    for (int i = n1 + tid; i < P; i += NT) keys[i] = ~0ull;
+    // ---- 2. sort: descending score, ascending slot
+    bitonic_sort(keys, P);
+    const int m = min(n1, p.max_nms);
 
-  if (tid == 0) s_nk = 0;
-  __syncthreads();
-  const float *pb = p.pred + (size_t)b * (4 + p.nc) * p.A;
-  // ---- 3. blocked greedy suppression
-  for (int c0 = 0; c0 < m; c0 += CH) {
-    const int nc_chunk = min(CH, m - c0);
-    const int nk = s_nk;
-    if (nk >= p.max_det) break;
-    if (tid < CH) {
-      csup[tid] = 0;
-      if (tid < nc_chunk) {
-        const unsigned long long key = keys[c0 + tid];
-        const int slot = (int)(key & 0xffffffffu);
-        const float sc = __uint_as_float(~(unsigned)(key >> 32));
-        int a, c;
-        if (p.multi_label) { a = slot / p.nc; c = slot - a * p.nc; }
-        else { a = slot; c = p.slot_cls[(size_t)b * p.A + a]; }
-        const float cx = pb[a], cy = pb[(size_t)p.A + a], w = pb[(size_t)2 * p.A + a], h = pb[(size_t)3 * p.A + a];
-        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
-        Box r;
-        r.x1 = __fsub_rn(cx, hw); r.y1 = __fsub_rn(cy, hh); r.x2 = __fadd_rn(cx, hw); r.y2 = __fadd_rn(cy, hh);
-        const float off = __fmul_rn((float)c, p.agnostic ? 0.f : p.max_wh);
-        Box o;
-        o.x1 = __fadd_rn(r.x1, off); o.y1 = __fadd_rn(r.y1, off); o.x2 = __fadd_rn(r.x2, off); o.y2 = __fadd_rn(r.y2, off);
-        craw[tid] = r; cbox[tid] = o;
-        carea[tid] = __fmul_rn(__fsub_rn(o.x2, o.x1), __fsub_rn(o.y2, o.y1));
-        cscore[tid] = sc; ccls[tid] = (float)c; canchor[tid] = a;
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    // ---- 3. blocked greedy suppression
+    for (int c0 = 0; c0 < m; c0 += CH) {
+      const int nc_chunk = min(CH, m - c0);
+      const int nk = s_nk;
+      if (nk >= p.max_det) break;
+      if (tid < CH) {
+        csup[tid] = 0;
+        if (tid < nc_chunk) {
+          const unsigned long long key = keys[c0 + tid];
+          const int slot = (int)(key & 0xffffffffu);
+          const float sc = __uint_as_float(~(unsigned)(key >> 32));
+          int a, c;
+          if (p.multi_label) { a = slot / p.nc; c = slot - a * p.nc; }
+          else { a = slot; c = p.slot_cls[(size_t)b * p.A + a]; }
+          const float cx = pb[a], cy = pb[(size_t)p.A + a], w = pb[(size_t)2 * p.A + a], h = pb[(size_t)3 * p.A + a];
+          const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+          Box r;
+          r.x1 = __fsub_rn(cx, hw); r.y1 = __fsub_rn(cy, hh); r.x2 = __fadd_rn(cx, hw); r.y2 = __fadd_rn(cy, hh);
+          const float off = __fmul_rn((float)c, p.agnostic ? 0.f : p.max_wh);
+          Box o;
+          o.x1 = __fadd_rn(r.x1, off); o.y1 = __fadd_rn(r.y1, off); o.x2 = __fadd_rn(r.x2, off); o.y2 = __fadd_rn(r.y2, off);
+          craw[tid] = r; cbox[tid] = o;
+          carea[tid] = __fmul_rn(__fsub_rn(o.x2, o.x1), __fsub_rn(o.y2, o.y1));
+          cscore[tid] = sc; ccls[tid] = (float)c; canchor[tid] = a;
+        }
       }
-    }
-    __syncthreads();
-    // (a) against boxes kept in earlier chunks
-    for (int t = tid; t < nc_chunk * nk; t += NT) {
-      const int i = t % nc_chunk, k = t / nc_chunk;
-      if (iou_gt(kbox[k], karea[k], cbox[i], carea[i], p.iou_f)) csup[i] = 1;
-    }
-    // (b) pairwise mask inside the chunk: warp handles rows {warp, warp+32}, lanes are columns
-    for (int i = warp; i < CH; i += 32) {
-      unsigned lo = 0, hi = 0;
-      const bool vi = i < nc_chunk;
-      const int j0 = lane, j1 = lane + 32;
-      const bool t0 = vi && j0 > i && j0 < nc_chunk && iou_gt(cbox[i], carea[i], cbox[j0], carea[j0], p.iou_f);
-      const bool t1 = vi && j1 > i && j1 < nc_chunk && iou_gt(cbox[i], carea[i], cbox[j1], carea[j1], p.iou_f);
-      lo = __ballot_sync(0xffffffffu, t0);
-      hi = __ballot_sync(0xffffffffu, t1);
-      if (lane == 0) cmask[i] = ((unsigned long long)hi << 32) | lo;
-    }
-    __syncthreads();
-    // (c) serial resolve of the chunk
-    if (tid == 0) {
-      unsigned long long dead = 0;
-      for (int i = 0; i < nc_chunk; ++i)
-        if (csup[i]) dead |= (1ull << i);
-      int nn = 0, k = nk;
-      for (int i = 0; i < nc_chunk && k < p.max_det; ++i) {
-        if ((dead >> i) & 1ull) continue;
-        s_newkept[nn++] = i;
-        ++k;
-        dead |= cmask[i];
+      __syncthreads();
+      // (a) against boxes kept in earlier chunks
+      for (int t = tid; t < nc_chunk * nk; t += NT) {
+        const int i = t % nc_chunk, k = t / nc_chunk;
+        if (iou_gt(kbox[k], karea[k], cbox[i], carea[i], p.iou_f)) csup[i] = 1;
       }
-      s_nnew = nn;
-      s_nk = k;
+      // (b) pairwise mask inside the chunk: warp handles rows {warp, warp+32}, lanes are columns
+      for (int i = warp; i < CH; i += 32) {
+        unsigned lo = 0, hi = 0;
+        const bool vi = i < nc_chunk;
+        const int j0 = lane, j1 = lane + 32;
+        const bool t0 = vi && j0 > i && j0 < nc_chunk && iou_gt(cbox[i], carea[i], cbox[j0], carea[j0], p.iou_f);
+        const bool t1 = vi && j1 > i && j1 < nc_chunk && iou_gt(cbox[i], carea[i], cbox[j1], carea[j1], p.iou_f);
+        lo = __ballot_sync(0xffffffffu, t0);
+        hi = __ballot_sync(0xffffffffu, t1);
+        if (lane == 0) cmask[i] = ((unsigned long long)hi << 32) | lo;
+      }
+      __syncthreads();
+      // (c) serial resolve of the chunk
+      if (tid == 0) {
+        unsigned long long dead = 0;
+        for (int i = 0; i < nc_chunk; ++i)
+          if (csup[i]) dead |= (1ull << i);
+        int nn = 0, k = nk;
+        for (int i = 0; i < nc_chunk && k < p.max_det; ++i) {
+          if ((dead >> i) & 1ull) continue;
+          s_newkept[nn++] = i;
+          ++k;
+          dead |= cmask[i];
+        }
+        s_nnew = nn;
+        s_nk = k;
+      }
+      __syncthreads();
+      // (d) publish the newly kept boxes
+      if (tid < s_nnew) {
+        const int i = s_newkept[tid], k = nk + tid;
+        kbox[k] = cbox[i];
+        karea[k] = carea[i];
+        float *d = p.dets + ((size_t)b * p.max_det + k) * 6;
+        d[0] = craw[i].x1; d[1] = craw[i].y1; d[2] = craw[i].x2; d[3] = craw[i].y2; d[4] = cscore[i]; d[5] = ccls[i];
+        if (p.kept_anchor) p.kept_anchor[(size_t)b * p.max_det + k] = canchor[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    // (d) publish the newly kept boxes
-    if (tid < s_nnew) {
-      const int i = s_newkept[tid], k = nk + tid;
-      kbox[k] = cbox[i];
-      karea[k] = carea[i];
-      float *d = p.dets + ((size_t)b * p.max_det + k) * 6;
-      d[0] = craw[i].x1; d[1] = craw[i].y1; d[2] = craw[i].x2; d[3] = craw[i].y2; d[4] = cscore[i]; d[5] = ccls[i];
-      if (p.kept_anchor) p.kept_anchor[(size_t)b * p.max_det + k] = canchor[i];
-    }
-    __syncthreads();
+    const bool exhausted = attempt == 0 && s_nk < p.max_det && n1 < min(n, p.max_nms);
+    __syncthreads();  // every thread has read s_nk before a second attempt resets it
+    if (!exhausted) break;
   }
   const int nk_final = s_nk;
   if (tid == 0) p.counts[b] = nk_final;
@@ -315,6 +383,8 @@ extern "C" int b2y_nms(const void *pred, int32_t B, int32_t nc, int32_t A, float
   p.iou_f = f;
   p.max_wh = max_wh;
   p.max_det = max_det; p.max_nms = max_nms > 0 ? max_nms : 30000; p.agnostic = agnostic;
+  static const int preselect = [] { const char *e = getenv("B2Y_NMS_PRESELECT"); return e ? atoi(e) : 1; }();  // A/B knob
+  p.preselect = preselect;
   char *ws = reinterpret_cast<char *>(workspace);
   p.slot_score = reinterpret_cast<float *>(ws);
   ws += align256((size_t)B * (multi_label ? (size_t)A * nc : (size_t)A) * sizeof(float));

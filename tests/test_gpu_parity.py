@@ -47,6 +47,38 @@ def test_nms_large_candidate_sets_vs_oracle():
             assert a.cpu().numpy().tobytes() == b.tobytes()
 
 
+@pytest.mark.parametrize("regime", ["sparse", "overlap_few_classes", "ties", "small_max_nms"])
+def test_nms_validator_scale_preselection_vs_oracle(regime, monkeypatch):
+    """Validator mode (detect/val.py:92-102: conf 0.001, multi_label): tens to hundreds of thousands of candidate slots per
+    image.  nms_select_kernel first tries the exact top-6144 (+ ties) prefix and falls back to every candidate when the
+    greedy scan runs out before max_det: sparse scenes finish inside the prefix, a few-class pile-up of near-identical
+    boxes forces the fallback, quantised scores put thousands of ties on the cut (prefix > shared-memory sort), and a
+    max_nms below the prefix size takes the max_nms cut inside it.  All bit-exact against the oracle."""
+    rng = np.random.default_rng(17)
+    kw = dict(conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=300)
+    if regime == "sparse":
+        p = kat._rand_pred(rng, 2, 80, 8400, img=4000.0, wh=(5, 30), score_pow=2.0)
+    elif regime == "overlap_few_classes":
+        p = kat._rand_pred(rng, 2, 4, 8400, img=640.0, score_pow=1.0)
+        p[:, 0:2] = 320 + rng.normal(0, 3, p[:, 0:2].shape)
+        p[:, 2:4] = 200 + rng.normal(0, 3, p[:, 2:4].shape)
+    elif regime == "ties":
+        p = kat._rand_pred(rng, 2, 12, 8400, img=2000.0, score_pow=1.0)
+        p[:, 4:] = np.ceil(p[:, 4:] * 8) / 8  # 8 score levels of ~12 600 slots each: the cut lands inside a tie of > 8192
+    else:
+        p = kat._rand_pred(rng, 2, 20, 8400, img=3000.0, wh=(5, 30), score_pow=1.5)
+        kw.update(max_nms=2000, max_det=1000)
+    p = p.astype(np.float32)
+    ref = oracle_post.non_max_suppression(p, **kw)
+    t = torch.from_numpy(p).cuda()
+    out = ops.non_max_suppression(t, **kw)
+    assert [len(o) for o in out] == [len(r) for r in ref]
+    for a, b in zip(out, ref):
+        assert a.cpu().numpy().tobytes() == b.tobytes()
+    if regime == "overlap_few_classes":
+        assert all(len(r) < 300 for r in ref)  # the prefix cannot have been enough: the fallback ran
+
+
 def test_nms_input_not_mutated_and_errors():
     p, kw = kat.nms_case("random_2100")
     t = torch.from_numpy(p).cuda()
