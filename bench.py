@@ -652,6 +652,10 @@ def run_ingest_workload(ctx: Ctx):
     src = os.path.join(tmp, "images", "val")
     kw = dict(device=ctx.local, imgsz=640, conf=0.25, iou=0.7, max_det=300, verbose=False, batch=64)
     out, passes = {}, {"dataset_s": round(t_ds, 2)}
+    trace = os.environ.get("B2Y_TRACE_INGEST") == "1"  # debug: dump every thread's stack every 15 s (where does a slow pass sit?)
+    if trace:
+        import faulthandler
+        faulthandler.dump_traceback_later(15, repeat=True, file=sys.stderr)
     for name, env in (("prefetch", "1"), ("reference_loader", "0")):
         os.environ["B2Y_INGEST"] = env
         try:
@@ -668,6 +672,8 @@ def run_ingest_workload(ctx: Ctx):
             out[name] = n / best
         finally:
             os.environ.pop("B2Y_INGEST", None)
+    if trace:
+        faulthandler.cancel_dump_traceback_later()
     return {"metric": "images/sec @640x640 from image files", "value": out["prefetch"], "unit": UNIT, "files": n, "batch": 64,
             "api": "YOLO(ckpt).predict('dir', batch=64, predictor=B200DetectionPredictor) incl. PNG decode and Results",
             "with_reference_loader": out["reference_loader"], "best_of": 2, "wall": passes,
@@ -705,7 +711,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch of the headline workload (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no `workloads` sub-records)")
-    ap.add_argument("--extras", default="bsyolo_n,yolo11x,sahi,dropin,val,ingest", help="comma list of sub-records to run")
+    ap.add_argument("--extras", default="bsyolo_n,yolo11x,sahi,dropin,ingest,val", help="comma list of sub-records to run")
     ap.add_argument("--layers-out", default="", help="write the per-op timing table of the headline workload to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -100,6 +100,17 @@ def main():
                   f"**{d.get('value', 0):,.0f} img/s** (best of {d.get('best_of')}); host-only staging ceiling of the same frames "
                   f"(pageable -> pinned ring, all cores, no GPU work): {(d.get('host_staging_ceiling') or {}).get('value', 0):,.0f} img/s "
                   f"({(d.get('host_staging_ceiling') or {}).get('gbps', 0):.1f} GB/s); `predict_stream` from pinned batches: {b['e2e']['value']:,.0f} img/s.")
+    if "ingest" in w and "value" in w["ingest"]:
+        g = w["ingest"]
+        md.append(f"Ingest (SURVEY §8 f2) `YOLO.predict('dir of {g['files']} PNG files', batch=64, predictor=B200DetectionPredictor)` incl. decode "
+                  f"and `Results`: **{g['value']:,.0f} img/s** with `ingest.PrefetchImageLoader`, {g['with_reference_loader']:,.0f} img/s "
+                  f"with the reference's sequential loader (same predictor).")
+    if "val" in w and "value" in w["val"]:
+        v = w["val"]
+        md.append(f"Validator (SURVEY §8 f1) `YOLO.val(data, validator=B200DetectionValidator, batch=64)` on {v['images']} synthetic 640x640 files incl. "
+                  f"dataloader and metrics: **{v['value']:,.0f} img/s**; per-image stage times (ms): {json.dumps(v['speed_ms_per_image'])}; "
+                  f"the reference's CPU validator: {v['cpu_baseline']['value']:.1f} img/s ({v['cpu_baseline']['sample']}; its NMS hits the "
+                  f"reference's own wall-clock abort, ops.py:312-314).")
     md.append("")
     # ---- ncu launch lists of bench.py's timed regions
     for tag, title in ((TAG, "yolo11n"), (f"{TAG}_bsyolo", "BS-YOLO-n")):
