@@ -18,7 +18,9 @@ Headline workload: BASELINE.json configs[1] (stock yolo11n, batch 64 per GPU, bf
 `workloads`: the other BASELINE.json configs as sub-records of the same line, each with its own value / e2e / roofline:
             configs[2] BS-YOLO-n ("best.pt" architecture) batch 256 sharded 256/N (strong scaling), configs[3] yolo11x
             @1280 batch 32 (N=1), configs[4] SAHI-style tiled inference of 3840x2160 frames (tiles sharded over the N
-            GPUs, global NMS merge), and the drop-in `YOLO.predict(list, predictor=B200DetectionPredictor)` (N=1).
+            GPUs, global NMS merge), the drop-in `YOLO.predict(list, predictor=B200DetectionPredictor)` (N=1), `ingest`
+            (`predict("dir of image files", batch=64)`: prefetching loader vs the reference's) and `val`
+            (`YOLO.val(validator=B200DetectionValidator)` beside the reference's CPU validator) -- SURVEY §8 f2 / f1, N=1.
             `--workload X` makes X the headline instead; `--no-extras` prints the headline only.
 """
 from __future__ import annotations

@@ -46,6 +46,7 @@ class DetectPipeline:
     def __init__(self, ir, batch: int, imgsz=(640, 640), src_shape=(640, 640), device: int = 0, conf=0.25, iou=0.7,
                  max_det=300, classes=None, agnostic=False, auto=True, use_graph=True, conv_impl=A.IMPL_AUTO, slots: int = 2):
         imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        slots = int(os.environ.get("B2Y_SLOTS", slots))  # A/B knob: engines (= network graphs that may be in flight at once)
         self.src_shape = tuple(src_shape)
         H, W, *_ = letterbox_geometry(self.src_shape, imgsz, auto)
         self.auto = auto
