@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb2y.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 BF16, F32 = 0, 1
@@ -35,7 +35,7 @@ class Op(C.Structure):
 EXPORTS = ["b2y_abi_version", "b2y_last_error", "b2y_plan_create", "b2y_plan_destroy", "b2y_plan_run",
            "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_set_mid_op", "b2y_plan_wait_mid", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_conv_pair_fits", "b2y_preprocess",
            "b2y_decode", "b2y_nms_workspace_bytes", "b2y_nms", "b2y_scale_boxes", "b2y_preprocess_chw", "b2y_box_iou",
-           "b2y_match_predictions"]
+           "b2y_match_predictions", "b2y_gather_extras"]
 
 _lib = None
 
@@ -76,6 +76,8 @@ def lib():
     L.b2y_preprocess_chw.argtypes = [vp, i32, i32, i32, vp, vp]
     L.b2y_box_iou.argtypes = [vp, i32, vp, i32, f32, vp, vp]
     L.b2y_match_predictions.argtypes = [vp, vp, vp, vp, C.POINTER(f32), i32, i32, i32, i32, vp, vp]
+    L.b2y_gather_extras.argtypes = [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(f32), i32, i32, i32, i32, i32, vp, vp,
+                                    vp, i32, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("b2y_abi_version",):

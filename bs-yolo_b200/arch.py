@@ -19,6 +19,7 @@ Reference anchors:
   SPPF / C2PSA / PSABlock / Attention / SCDown ... block.py:3114-3149, 4235-4288, 4348-4383, 4429-4468, 4503-4535
   MSCAAttention / ELA .......... ultralytics/nn/Addmodules/MSCA.py:19-88, ELA.py:33-100
   Detect / DFL ................. ultralytics/nn/modules/head.py:21-74, block.py:58-76
+  Pose .......... ultralytics/nn/modules/head.py:230-250, cfg/models/11/yolo11-pose.yaml:15-47
 """
 from __future__ import annotations
 
@@ -157,6 +158,19 @@ def detect(name, nc, ch) -> Node:
                 stride=[8.0, 16.0, 32.0][: len(ch)])
 
 
+def pose(name, nc, ch, kpt_shape=(17, 3)) -> Node:
+    """`Pose(Detect)` (head.py:230-250): the Detect branches plus one keypoint branch per level, cv4[i] =
+    Conv(x, c4, 3) -> Conv(c4, c4, 3) -> Conv2d(c4, nk, 1) with c4 = max(ch[0] // 4, nk).  Kept as a Detect node with
+    ``head="pose"`` so that everything that only needs the Detect part treats it as one."""
+    n = detect(name, nc, ch)
+    nk = int(kpt_shape[0]) * int(kpt_shape[1])
+    c4 = max(ch[0] // 4, nk)
+    n.update(head="pose", kpt_shape=(int(kpt_shape[0]), int(kpt_shape[1])), ne=nk,
+             cv4=[[conv_bn(f"{name}.cv4.{i}.0", x, c4, 3), conv_bn(f"{name}.cv4.{i}.1", c4, c4, 3),
+                   conv_plain(f"{name}.cv4.{i}.2", c4, nk, 1)] for i, x in enumerate(ch)])
+    return n
+
+
 # ----------------------------------------------------------------------------- whole graphs
 _STOCK = [  # (from, repeats, module, args)  -- yolo11-seg.yaml:15-46 with Detect as the last layer
     (-1, 1, "Conv", [64, 3, 2]), (-1, 1, "Conv", [128, 3, 2]), (-1, 2, "C3k2", [256, False, 0.25]),
@@ -182,11 +196,14 @@ _BSYOLO = [  # yolo11.yaml:15-52 of the fork; absolute `from` indices kept verba
     ([19, 23, 27], 1, "Detect", []),
 ]
 
+_STOCK_POSE = _STOCK[:-1] + [([16, 19, 22], 1, "Pose", [(17, 3)])]  # yolo11-pose.yaml:15-47 (same backbone / neck)
+
 HEAD_GAIN = 8.0
 SYNTH_CLS_BIAS = {  # model -> per-level bias shift of the final class conv (seed 0 calibration, see synth_state_dict)
     "yolo11n": (-3.678, -4.087, -3.846),
     "bsyolo_n": (-2.583, -3.309, -3.207),
     "yolo11x": (-3.446, -3.569, -3.91),
+    "yolo11n-pose": (-3.678, -4.087, -3.846),  # cv4 is drawn after every Detect parameter: the Detect part equals yolo11n's
 }
 
 MODELS = {  # name -> (table, scale, nc)
@@ -196,6 +213,7 @@ MODELS = {  # name -> (table, scale, nc)
     "yolo11l": (_STOCK, "l", 80),
     "yolo11x": (_STOCK, "x", 80),
     "bsyolo_n": (_BSYOLO, "n", 12),
+    "yolo11n-pose": (_STOCK_POSE, "n", 80),  # nc: 80 and kpt_shape: [17, 3] are the yaml's own defaults
 }
 
 
@@ -237,6 +255,8 @@ def build_spec(model: str, nc: int | None = None) -> Node:
             c2, node = sum(ch[x] if x != -1 else c_prev for x in f), dict(type="Concat", name=name)
         elif kind == "Detect":
             c2, node = None, detect(name, nc, [ch[x] for x in f])
+        elif kind == "Pose":
+            c2, node = None, pose(name, nc, [ch[x] for x in f], args[0])
         else:
             raise ValueError(kind)
         fl = [f] if isinstance(f, int) else list(f)

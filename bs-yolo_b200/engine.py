@@ -108,6 +108,24 @@ class Engine:
             raise A.B2YError("raw head maps are not materialised when Detect decode is fused (use fuse_decode=False)")
         return self.buffer(self.plan.head_bufs[level])
 
+    def extra(self, level: int) -> torch.Tensor:
+        """(B, H_l, W_l, pitch) fp32 NHWC raw map of the head's extra branch (Pose.cv4, head.py:245); channels [0, plan.ne)
+        are the reference's ``cv4[level](x[level])`` (permute(0,3,1,2)), the rest is pitch padding."""
+        if not self.plan.extra_bufs:
+            raise A.B2YError("this plan has no extra head branch (not a Pose model)")
+        return self.buffer(self.plan.extra_bufs[level])
+
+    def keypoints(self, kept: torch.Tensor, counts: torch.Tensor, geom: torch.Tensor | None = None,
+                  round_dets: torch.Tensor | None = None) -> torch.Tensor:
+        """Decoded keypoints (B, max_det, nkpt, ndim) of the rows NMS kept (``nms(return_anchors=True)``): Pose.kpts_decode +
+        the gather non_max_suppression does + (with ``geom`` = ops.coords_geometry) ops.scale_coords, one launch."""
+        from .ops import gather_extras
+        if self.plan.extra_kind != "pose":
+            raise A.B2YError("keypoints: not a Pose model")
+        out = gather_extras([self.extra(l) for l in range(len(self.plan.extra_bufs))], self.plan.extra_strides, self.plan.ne,
+                            kept, counts, mode=1, ndim=self.plan.kpt_shape[1], geom=geom, round_dets=round_dets)
+        return out.view(out.shape[0], out.shape[1], *self.plan.kpt_shape)
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 

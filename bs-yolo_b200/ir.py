@@ -150,7 +150,7 @@ def _module_node(m, name: str) -> Node:
     if tn == "Concat":
         assert m.d == 1
         return dict(type="Concat", name=name)
-    if tn == "Detect":
+    if tn in ("Detect", "Pose"):
         if getattr(m, "end2end", False) or m.reg_max != 16:
             raise NotImplementedError("end2end / non-DFL16 Detect is not on the B200 path")
         cv2 = [[C(s[j], f"{name}.cv2.{i}.{j}") for j in range(3)] for i, s in enumerate(m.cv2)]
@@ -161,8 +161,12 @@ def _module_node(m, name: str) -> Node:
             cv3.append([[C(s[0][0], f"{name}.cv3.{i}.0.0"), C(s[0][1], f"{name}.cv3.{i}.0.1")],
                         [C(s[1][0], f"{name}.cv3.{i}.1.0"), C(s[1][1], f"{name}.cv3.{i}.1.1")],
                         C(s[2], f"{name}.cv3.{i}.2")])
-        return dict(type="Detect", name=name, nc=int(m.nc), reg_max=16, no=int(m.no), nl=int(m.nl),
+        node = dict(type="Detect", name=name, nc=int(m.nc), reg_max=16, no=int(m.no), nl=int(m.nl),
                     ch=[s[0].conv.in_channels for s in m.cv2], cv2=cv2, cv3=cv3, stride=[float(v) for v in m.stride])
+        if tn == "Pose":  # head.py:230-250: Detect + one keypoint branch per level
+            node.update(head="pose", kpt_shape=(int(m.kpt_shape[0]), int(m.kpt_shape[1])), ne=int(m.nk),
+                        cv4=[[C(s[j], f"{name}.cv4.{i}.{j}") for j in range(3)] for i, s in enumerate(m.cv4)])
+        return node
     raise NotImplementedError(f"module {tn} ({name}) is not on the B200 hot path (no CPU fallback by design)")
 
 

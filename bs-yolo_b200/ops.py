@@ -152,6 +152,45 @@ def scale_boxes_batched(dets: torch.Tensor, counts: torch.Tensor, img1_shape=Non
     return dets
 
 
+# ---- Detect-derived heads --------------------------------------------------------------------------------
+def coords_geometry(img1_shape, img0_shapes, device) -> torch.Tensor:
+    """Per-image (gain, padx, pady, w0, h0) rows of scale_coords + clip_coords (ops.py:756-758, 341-358) as one fp32 device
+    tensor.  Same as scale_geometry except that scale_coords does NOT round the pad (scale_boxes does, ops.py:113-116)."""
+    geom = []
+    for (h0, w0) in img0_shapes:
+        gain = min(img1_shape[0] / h0, img1_shape[1] / w0)
+        geom.append([gain, (img1_shape[1] - w0 * gain) / 2, (img1_shape[0] - h0 * gain) / 2, w0, h0])
+    return torch.tensor(geom, dtype=torch.float32).to(device)
+
+
+def gather_extras(raws, strides, ne: int, kept: torch.Tensor, counts: torch.Tensor, mode: int = 0, ndim: int = 3,
+                  geom: torch.Tensor | None = None, round_dets: torch.Tensor | None = None) -> torch.Tensor:
+    """The extra columns of the rows NMS kept (one C-ABI call: b2y_gather_extras).  raws: per-level (B, H_l, W_l, pitch)
+    fp32 NHWC maps of a Detect-derived head's cv4 branch; kept (B, max_det) int32 anchors + counts (B,) int32 from
+    ``nms_raw(return_anchors=True)``.  mode 1 = Pose.kpts_decode (head.py:252-279) on those rows, then -- with ``geom``
+    (coords_geometry) -- ops.scale_coords to the original image; ``round_dets``: detections whose boxes get the
+    `.round()` of pose/predict.py:52.  Returns (B, max_det, ne) fp32, zero past counts."""
+    if not all(r.is_cuda for r in raws) or not kept.is_cuda:
+        raise A.B2YError("gather_extras: CUDA tensors required (no CPU fallback on the B200 path)")
+    nl = len(raws)
+    B, max_det = int(kept.shape[0]), int(kept.shape[1])
+    pitch = int(raws[0].shape[3])
+    assert all(r.dtype == torch.float32 and r.is_contiguous() and r.shape[0] == B and r.shape[3] == pitch for r in raws)
+    assert kept.dtype == torch.int32 and kept.is_contiguous() and counts.dtype == torch.int32 and counts.shape[0] == B
+    assert geom is None or (geom.dtype == torch.float32 and tuple(geom.shape) == (B, 5) and geom.is_cuda)
+    assert round_dets is None or (round_dets.dtype == torch.float32 and round_dets.is_contiguous()
+                                  and tuple(round_dets.shape) == (B, max_det, 6))
+    out = torch.empty(B, max_det, ne, dtype=torch.float32, device=kept.device)
+    A.check(A.lib().b2y_gather_extras((C.c_void_p * nl)(*[r.data_ptr() for r in raws]),
+                                      (C.c_int32 * nl)(*[int(r.shape[1]) for r in raws]),
+                                      (C.c_int32 * nl)(*[int(r.shape[2]) for r in raws]),
+                                      (C.c_float * nl)(*[float(v) for v in strides]), nl, pitch, int(ne), int(ndim), int(mode),
+                                      kept.data_ptr(), counts.data_ptr(), geom.data_ptr() if geom is not None else None, B,
+                                      max_det, out.data_ptr(), round_dets.data_ptr() if round_dets is not None else None,
+                                      _stream(kept.device)))
+    return out
+
+
 # ---- validator path (SURVEY §8 f1) ------------------------------------------------------------------------------------
 def box_iou(box1: torch.Tensor, box2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
     """Drop-in for ultralytics.utils.metrics.box_iou (metrics.py:52-71) on CUDA tensors: (N,4) x (M,4) xyxy -> (N,M),

@@ -137,6 +137,10 @@ class Plan:
         # network input, space-to-depth: channel ((y&1)*2 + (x&1))*4 + {R,G,B,0} of super-pixel (y/2, x/2)
         self.input_buf = self.new_buf(16, H // 2, W // 2, name="input_s2d", exact=True)
         self.head_bufs: list[int] = []
+        self.extra_bufs: list[int] = []  # Pose: per-level raw keypoint maps (B, H_l, W_l, ne) fp32
+        self.ne = 0                      # logical channels of the extra maps (nk); the buffers are pitched to a multiple of 4
+        self.extra_strides: list[float] = []
+        self.extra_kind, self.kpt_shape = "", ()
         self.y_buf = -1
         self.A = 0
         if ir.get("layers"):
@@ -564,6 +568,24 @@ class Plan:
                         ip=(nc, len(xs)), fp=tuple(float(s) for s in n["stride"]))
             op.bytes_alg = self.A * (no * 4 + (4 + nc) * 4)
             self.ops.append(op)
+        if n.get("cv4"):
+            self.extras(n, xs)
+
+    def extras(self, n, xs):
+        """The extra branch of a Detect-derived head -- Pose.cv4 (head.py:239-246): Conv(x, c4, 3) -> Conv(c4, c4, 3) ->
+        Conv2d(c4, ne, 1) per level.  The reference concatenates the decoded (B, ne, A) rows under y and drags them through
+        NMS (ops.py:245-246 `box, cls, mask = x.split((4, nc, nm), 1)`); here the branch stops at its raw fp32 NHWC maps:
+        NMS runs on (B, 4+nc, A) as for Detect and b2y_gather_extras decodes only the <= max_det rows NMS kept.
+        c4 = max(ch0 // 4, nk) is 51 on the n scale: both hidden maps are zero-padded to 64 channels (pad16)."""
+        self.ne = int(n["ne"])
+        self.extra_strides = [float(v) for v in n["stride"]]
+        self.extra_kind, self.kpt_shape = n["head"], tuple(n.get("kpt_shape", ()))
+        for i, x in enumerate(xs):
+            c4 = n["cv4"][i]
+            t = self.conv(c4[1], self.conv(c4[0], x, pad16=True), pad16=True)
+            eb = self.new_buf(_r(self.ne, 4), x.H, x.W, A.F32, f"{n['name']}.extra{i}")
+            self.extra_bufs.append(eb)
+            self.conv(c4[2], t, View(eb, 0, self.ne, x.H, x.W), out_dtype=A.F32)
 
     # ------------------------------------------------------------------ whole graph
     def _lower(self):

@@ -163,6 +163,9 @@ class B200Backend:
         self.names = dict(getattr(det_model, "names", None) or self.ir["names"])
         self.stride = max(int(max(float(s) for s in det_model.stride)), 32)
         self.nc = self.ir["nc"]
+        head = _ir.detect_node(self.ir)
+        if head.get("head") == "pose":  # AutoBackend forwards the checkpoint's kpt_shape (autobackend.py:149-150)
+            self.kpt_shape = list(head["kpt_shape"])
         self.use_graph = use_graph
         self._engines: dict[tuple[int, int, int], Engine] = {}
         self._pipes: dict[tuple, tuple] = {}
@@ -227,6 +230,7 @@ def _build_class():
         """DetectionPredictor whose preprocess / inference / postprocess run as hand-written sm_100a kernels."""
 
         max_chunk = int(os.environ.get("B2Y_PREDICT_BATCH", "64"))  # frames per pipelined chunk of a same-shape list
+        pipelined = True  # same-shape uint8 lists stream through DetectPipeline (boxes only); False: single-engine route
 
         def setup_model(self, model, verbose=True):
             if self.args.half:
@@ -266,12 +270,20 @@ def _build_class():
             H, W = geo[0][0], geo[0][1]
             if any((g[0], g[1]) != (H, W) for g in geo):
                 raise ValueError("letterboxed images of one batch must share one canvas size")
-            if same and self.model.stride == 32 and all(x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 3 for x in im):
+            hot = same and self.model.stride == 32 and all(x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 3 for x in im)
+            if hot and self.pipelined:
                 # the hot case: nothing is copied here; `inference` streams the frames through the pipelined path
                 return HostFrames(im, shapes[0][:2], (H, W), dev)
             eng = self.model.engine(len(im), H, W)
             lib, st = A.lib(), torch.cuda.current_stream(dev).cuda_stream
             dst = eng.input_nhwc
+            if hot:  # same-shape batch on the single-engine route (heads whose extras the chunked pipeline does not carry)
+                src = torch.from_numpy(np.ascontiguousarray(np.stack(im))).pin_memory().to(dev, non_blocking=True)
+                _, _, top, left, uh, uw = geo[0]
+                A.check(lib.b2y_preprocess(src.data_ptr(), len(im), shapes[0][0], shapes[0][1], dst.data_ptr(), H, W, top, left,
+                                           uh, uw, 0, st))
+                self._keep = [src]
+                return PreprocessedBatch(eng)
             keep = []  # ragged batch: LetterBox(auto=False) per image into that image's slot of the input buffer
             for i, x in enumerate(im):
                 src = torch.from_numpy(np.ascontiguousarray(x)).pin_memory().to(dev, non_blocking=True)
@@ -327,13 +339,47 @@ def _build_class():
             return [Results(o, path=p, names=self.model.names, boxes=dets[i, : n[i]])
                     for i, (o, p) in enumerate(zip(orig_imgs, self.batch[0]))]
 
-    return B200DetectionPredictor
+    class B200PosePredictor(B200DetectionPredictor):
+        """PosePredictor (models/yolo/pose/predict.py:8-59) on the B200 path: backbone, neck, the Detect
+        branches and the keypoint branch (Pose.cv4, head.py:239-246) run in the same CUDA-graphed plan; NMS is the Detect
+        NMS (the reference drags the 51 decoded keypoint rows of every anchor through it, ops.py:245-273); Pose.kpts_decode
+        (head.py:252-279), the gather of the kept rows, ops.scale_coords (ops.py:740-772) and the `.round()` of the boxes
+        (predict.py:52) are ONE launch over the <= max_det kept rows (b2y_gather_extras).  ``Results.keypoints`` stay on
+        the GPU.  Batches take the single-engine route (the chunked pipeline carries boxes only)."""
+
+        pipelined = False
+
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            self.args.task = "pose"
+
+        def postprocess(self, preds, img, orig_imgs):
+            from .ops import coords_geometry
+
+            if isinstance(preds, (list, tuple)):
+                preds = preds[0]
+            a = self.args
+            dets, counts, kept = nms_raw(preds, a.conf, a.iou, a.max_det, a.classes, bool(a.agnostic_nms), return_anchors=True)
+            if not isinstance(orig_imgs, list):
+                from ultralytics.utils import ops as ref_ops
+                orig_imgs = ref_ops.convert_torch2numpy_batch(orig_imgs)
+            shapes = [o.shape[:2] for o in orig_imgs]
+            scale_boxes_batched(dets, counts, tuple(img.shape[2:]), shapes)
+            kpts = img.engine.keypoints(kept, counts, geom=coords_geometry(tuple(img.shape[2:]), shapes, dets.device),
+                                        round_dets=dets)
+            n = counts.tolist()  # the one device->host sync of the batch
+            nk = kpts.shape[2] * kpts.shape[3]
+            return [Results(o, path=p, names=self.model.names, boxes=dets[i, : n[i]],
+                            keypoints=kpts[i, : n[i]] if n[i] else kpts[i, :0].reshape(0, nk))  # predict.py:51: (0, nk) when empty
+                    for i, (o, p) in enumerate(zip(orig_imgs, self.batch[0]))]
+
+    return {"B200DetectionPredictor": B200DetectionPredictor, "B200PosePredictor": B200PosePredictor}
 
 
-def __getattr__(name):  # PEP 562: resolve the class on first use so importing this module never imports ultralytics
+def __getattr__(name):  # PEP 562: resolve the classes on first use so importing this module never imports ultralytics
     global _CLS
-    if name == "B200DetectionPredictor":
+    if name in ("B200DetectionPredictor", "B200PosePredictor"):
         if _CLS is None:
             _CLS = _build_class()
-        return _CLS
+        return _CLS[name]
     raise AttributeError(name)

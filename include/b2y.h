@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define B2Y_ABI_VERSION 6
+#define B2Y_ABI_VERSION 7
 #if defined(__GNUC__)
 #define B2Y_API __attribute__((visibility("default")))
 #else
@@ -187,6 +187,23 @@ B2Y_API int b2y_box_iou(const void *box1, int32_t n, const void *box2, int32_t m
 B2Y_API int b2y_match_predictions(const void *dets, const void *counts, const void *labels, const void *label_counts,
                           const float *iouv, int32_t niou, int32_t B, int32_t max_det, int32_t max_labels, void *tp,
                           void *stream);
+
+/* ---- Detect-derived heads: the extra per-anchor columns of a Pose head --------------------------------
+ *      b2y_gather_extras replaces, for the rows NMS kept, Pose.kpts_decode (ultralytics/nn/modules/head.py:252-279), the
+ *      "mask" columns non_max_suppression carries along (ultralytics/utils/ops.py:245-246, 268-273) and
+ *      PosePredictor.postprocess's ops.scale_coords + clip_coords (ultralytics/models/yolo/pose/predict.py:52-56,
+ *      utils/ops.py:740-772, 341-358).
+ *      raw[l]: B x H_l x W_l x pitch fp32 NHWC maps of the cv4 branch (head.py:245; the plan's extra buffers), levels in
+ *      anchor order (P3 | P4 | P5, row-major); kept_anchor / counts: as b2y_nms wrote them.
+ *      mode 0: copy the ne channels; mode 1: keypoints in groups of ndim (2 | 3): x, y = (v * 2 + cell) * stride (bit-exact
+ *      fp32), visibility = sigmoid(v).  geom (optional device pointer): one (gain, padx, pady, w0, h0) record of 5 floats
+ *      per image -- x, y are then mapped to the original image and clipped like ops.scale_coords (pad NOT rounded, unlike
+ *      scale_boxes).  round_dets (optional): the (B, max_det, 6) detections whose box corners are rounded half-to-even in
+ *      place (pose/predict.py:52 `.round()`).  out: B x max_det x ne fp32, rows past counts[b] are zero. */
+B2Y_API int b2y_gather_extras(const void *const *raw, const int32_t *hs, const int32_t *ws, const float *strides,
+                      int32_t n_levels, int32_t pitch, int32_t ne, int32_t ndim, int32_t mode, const void *kept_anchor,
+                      const void *counts, const void *geom, int32_t B, int32_t max_det, void *out, void *round_dets,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -178,6 +178,30 @@ def decode(raws, strides, nc):
     return torch.cat((dbox, cls.sigmoid()), 1)
 
 
+def pose_kpt_raw(n, xs):
+    """nn/modules/head.py:245: cat over levels of cv4[i](x[i]).view(bs, nk, -1) -> (B, nk, A) raw keypoint maps."""
+    out = []
+    for i, x in enumerate(xs):
+        t = x
+        for c in n["cv4"][i]:
+            t = conv(c, t)
+        out.append(t.reshape(t.shape[0], n["ne"], -1))
+    return torch.cat(out, -1)
+
+
+def kpts_decode(kpts, shapes, strides, ndim):
+    """nn/modules/head.py:274-279 (Pose.kpts_decode, non-export branch).  kpts (B, nk, A) raw -> decoded, model-input pixels:
+    x, y = (v * 2 + (anchor - 0.5)) * stride, visibility = sigmoid(v) when ndim == 3."""
+    anchors, st = make_anchors(shapes, strides)
+    anchors, st = anchors.t(), st.t()  # (2, A), (1, A): self.anchors / self.strides (head.py:108)
+    y = kpts.clone()
+    if ndim == 3:
+        y[:, 2::3] = y[:, 2::3].sigmoid()
+    y[:, 0::ndim] = (y[:, 0::ndim] * 2.0 + (anchors[0] - 0.5)) * st
+    y[:, 1::ndim] = (y[:, 1::ndim] * 2.0 + (anchors[1] - 0.5)) * st
+    return y
+
+
 _TOP = {"Conv": conv, "C3k2": c3k2, "SPPF": sppf, "C2PSA": c2psa, "SCDown": scdown, "MSCA": msca, "ELA": ela}
 
 
@@ -185,7 +209,8 @@ _TOP = {"Conv": conv, "C3k2": c3k2, "SPPF": sppf, "C2PSA": c2psa, "SCDown": scdo
 def forward(ir, x, capture=None):
     """nn/tasks.py:138-165 (_predict_once) + head.py:64-74. x: (B,3,H,W) fp32 in [0,1] RGB.
 
-    Returns (y, raws): y (B,4+nc,A) decoded, raws the three (B,64+nc,H,W) head maps.
+    Returns (y, raws): y (B,4+nc,A) decoded, raws the three (B,64+nc,H,W) head maps.  A Pose head (head.py:242-250)
+    returns (cat(y, decoded keypoints) (B,4+nc+nk,A), (raws, raw keypoints (B,nk,A))).
     ``capture``: optional dict filled with {layer index: output} for every top-level layer."""
     ys = []
     save = set(ir["save"])
@@ -204,7 +229,12 @@ def forward(ir, x, capture=None):
             raws = detect_raw(m, xin)
             if capture is not None:
                 capture[L["i"]] = raws
-            return decode(raws, m["stride"], m["nc"]), raws
+            y = decode(raws, m["stride"], m["nc"])
+            if m.get("head") == "pose":
+                kpt = pose_kpt_raw(m, xin)
+                pk = kpts_decode(kpt, [r.shape[2:] for r in raws], m["stride"], m["kpt_shape"][1])
+                return torch.cat((y, pk), 1), (raws, kpt)
+            return y, raws
         else:
             x = _TOP[ty](m, xin)
         if capture is not None:

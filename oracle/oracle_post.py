@@ -8,6 +8,8 @@ numpy restatement of the reference's pre- and post-processing for the detect pat
   non_max_suppression ..... ultralytics/utils/ops.py:167-316 (+ xywh2xyxy :416-433)
   torchvision.ops.nms ..... third party; restated in oracle/nms_ref.c (C) and ``nms_numpy`` below
   scale_boxes/clip_boxes .. ultralytics/utils/ops.py:92-127, 319-338
+  scale_coords/clip_coords  ultralytics/utils/ops.py:740-772, 341-358 (Pose keypoints)
+  pose_postprocess ........ ultralytics/models/yolo/pose/predict.py:39-59
 
 Deviations from the reference that are documented, not reproduced: the wall-clock abort of NMS
 (ops.py:238,312-314) and the in-place mutation of the caller's tensor (ops.py:244).
@@ -218,3 +220,50 @@ def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape) -> np.ndarray:
     boxes[..., 0] = boxes[..., 0].clip(0, img0_shape[1]); boxes[..., 2] = boxes[..., 2].clip(0, img0_shape[1])
     boxes[..., 1] = boxes[..., 1].clip(0, img0_shape[0]); boxes[..., 3] = boxes[..., 3].clip(0, img0_shape[0])
     return boxes
+
+
+# ----------------------------------------------------------------------------- Pose head post-process
+def scale_coords(img1_shape, coords: np.ndarray, img0_shape) -> np.ndarray:
+    """utils/ops.py:740-772 + clip_coords :341-358 (ratio_pad=None, normalize=False, padding=True).  coords (..., >=2) fp32,
+    returns a copy.  Unlike scale_boxes the pad is NOT rounded; the Python doubles act on the fp32 tensor as fp32 scalars."""
+    coords = np.array(coords, np.float32, copy=True)
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    coords[..., 0] -= np.float32(pad[0])
+    coords[..., 1] -= np.float32(pad[1])
+    coords[..., 0] /= np.float32(gain)
+    coords[..., 1] /= np.float32(gain)
+    coords[..., 0] = coords[..., 0].clip(0, img0_shape[1])
+    coords[..., 1] = coords[..., 1].clip(0, img0_shape[0])
+    return coords
+
+
+def nms_with_extras(prediction, nc, **kw):
+    """utils/ops.py:167-316 with nm = rows - 4 - nc extra ("mask") columns: they take no part in any decision and ride
+    along with the kept rows (:245-246, 268-273).  prediction (B, 4+nc+nm, A) -> list of (n_i, 6+nm)."""
+    pred = np.asarray(prediction, np.float32)
+    out, idx = non_max_suppression(pred[:, :4 + nc], nc=nc, return_indices=True, **kw)
+    return [np.concatenate((o, pred[b][4 + nc:][:, i].T), 1) for b, (o, i) in enumerate(zip(out, idx))]
+
+
+def pose_postprocess(prediction, nc, kpt_shape, img1_shape, img0_shapes, conf=0.25, iou=0.7, max_det=300, classes=None,
+                     agnostic=False):
+    """models/yolo/pose/predict.py:39-59: NMS, boxes scaled to the original image and ROUNDED (:52), keypoints reshaped to
+    kpt_shape and mapped with scale_coords (:53-54).  Returns per image (boxes (n,6), keypoints (n, *kpt_shape))."""
+    res = []
+    rows = nms_with_extras(prediction, nc, conf_thres=conf, iou_thres=iou, max_det=max_det, classes=classes, agnostic=agnostic)
+    for r, s0 in zip(rows, img0_shapes):
+        boxes = r[:, :6].copy()
+        boxes[:, :4] = np.round(scale_boxes(img1_shape, boxes[:, :4], s0))  # np.round == torch.round: half to even
+        k = r[:, 6:].reshape(len(r), *kpt_shape)
+        res.append((boxes, scale_coords(img1_shape, k, s0)))
+    return res
+
+
+def keypoints_result(kpts: np.ndarray) -> np.ndarray:
+    """engine/results.py:1305-1309 (Keypoints.__init__): what ``Results.keypoints.data`` holds -- x, y of points whose
+    visibility is < 0.5 are zeroed.  Returns a copy."""
+    k = np.array(kpts, np.float32, copy=True)
+    if k.ndim == 3 and k.shape[2] == 3:
+        k[..., :2][k[..., 2] < 0.5] = 0
+    return k

@@ -58,6 +58,10 @@ def reference_cfg(model: str) -> dict:
         d = yaml_load(os.path.join(cfg_dir, "yolo11.yaml"))
         d["scale"] = "n"
         return d
+    if model.endswith("-pose"):  # the fork ships the stock pose graph unchanged (cfg/models/11/yolo11-pose.yaml; nc 80, kpt_shape [17, 3])
+        d = yaml_load(os.path.join(cfg_dir, "yolo11-pose.yaml"))
+        d["scale"] = model[len("yolo11")]
+        return d
     assert model.startswith("yolo11")
     d = yaml_load(os.path.join(cfg_dir, "yolo11-seg.yaml"))
     d["scale"] = model[-1]
@@ -67,9 +71,9 @@ def reference_cfg(model: str) -> dict:
 
 def reference_model(model: str, state_dict=None):
     import_reference()
-    from ultralytics.nn.tasks import DetectionModel
+    from ultralytics.nn.tasks import DetectionModel, PoseModel
 
-    m = DetectionModel(reference_cfg(model), verbose=False)
+    m = (PoseModel if model.endswith("-pose") else DetectionModel)(reference_cfg(model), verbose=False)
     if state_dict is not None:
         m.load_state_dict(state_dict, strict=True)
     return m.eval()

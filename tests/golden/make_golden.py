@@ -9,6 +9,9 @@ The reference cannot travel to the GPU box, these vectors can.  What each file p
   nms.npz .............. utils/ops.py:167-316 non_max_suppression (+ torchvision.ops.nms) on every tests/kat.py NMS case
   letterbox.npz ........ data/augment.py:1535-1601 LetterBox (cv2.resize / copyMakeBorder)
   predict_<case>.npz ... YOLO(ckpt).predict(list of ndarrays, device="cpu") end to end: Results.boxes.data per image
+  net_<pose case>.npz / predict_<pose case>.npz ... the same two for the stock pose graph: PoseModel forward
+                         (head.py:242-279: y incl. the decoded keypoint rows, raw keypoint maps) and
+                         YOLO(pose ckpt).predict() -> Results.boxes.data + Results.keypoints.data (pose/predict.py:39-59)
   val_match.npz ........ utils/metrics.py:52-71 box_iou and DetectionValidator._process_batch (detect/val.py:209-228 ->
                          engine/validator.py:222-258 match_predictions) on every tests/kat.py VAL_MATCH case
 """
@@ -86,6 +89,43 @@ def main():
         print("predict", case, d["n"].tolist())
 
     val_match()
+    pose()
+
+
+def pose_checkpoint(model, imgsz, path):
+    """A pose checkpoint the way the reference's trainer writes it (pose/train.py:49 sets model.kpt_shape)."""
+    spec = arch.build_spec(model)
+    m = ref_import.reference_model(model, arch.synth_state_dict(spec, 0))
+    m.names = {k: f"class{k}" for k in range(spec["nc"])}
+    m.kpt_shape = list(m.model[-1].kpt_shape)
+    m.args = {"task": "pose", "imgsz": imgsz}
+    torch.save({"model": m, "ema": None, "train_args": {"task": "pose", "imgsz": imgsz}}, path)
+    return path
+
+
+def pose():
+    """the Pose head through the reference's own PoseModel / PosePredictor."""
+    ref_import.import_reference()
+    from ultralytics import YOLO
+
+    for case, (model, *_rest) in kat.POSE_NET_CASES.items():
+        spec = arch.build_spec(model)
+        sd = arch.synth_state_dict(spec, 0)
+        m = ref_import.reference_model(model, sd)
+        with torch.no_grad():
+            y, (raws, kpt) = m(torch.from_numpy(kat.net_input(case)))
+        np.savez_compressed(os.path.join(OUT, f"net_{case}.npz"), y=y.numpy(), kpt=kpt.numpy(), raw0=raws[0].numpy(),
+                            raw1=raws[1].numpy(), raw2=raws[2].numpy(), sd_checksum=np.float64(kat.state_dict_checksum(sd)))
+        print("net", case, tuple(y.shape), tuple(kpt.shape))
+    for case, (model, n, h, w, imgsz, seed) in kat.POSE_PREDICT_CASES.items():
+        yolo = YOLO(pose_checkpoint(model, imgsz, f"/tmp/b2y_golden_{case}.pt"))
+        res = yolo.predict(kat.predict_input(case), device="cpu", imgsz=imgsz, conf=0.25, iou=0.7, max_det=300, verbose=False)
+        assert type(yolo.predictor).__name__ == "PosePredictor"
+        d = {f"boxes{i}": r.boxes.data.numpy().astype(np.float32) for i, r in enumerate(res)}
+        d.update({f"kpts{i}": r.keypoints.data.numpy().astype(np.float32) for i, r in enumerate(res)})
+        d["n"] = np.array([r.boxes.data.shape[0] for r in res], np.int64)
+        np.savez_compressed(os.path.join(OUT, f"predict_{case}.npz"), **d)
+        print("predict", case, d["n"].tolist(), [d[f"kpts{i}"].shape for i in range(n)])
 
 
 def val_match():
@@ -107,4 +147,5 @@ def val_match():
 
 
 if __name__ == "__main__":
-    val_match() if sys.argv[1:] == ["val_match"] else main()  # `make_golden.py val_match` regenerates that file only
+    # `make_golden.py val_match` / `make_golden.py pose` regenerate those files only
+    {"val_match": val_match, "pose": pose}.get((sys.argv[1:] or [""])[0], main)()

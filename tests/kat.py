@@ -12,8 +12,13 @@ NET_CASES = {  # name -> (model, batch, H, W, seed)
 }
 
 
+POSE_NET_CASES = {  # the stock pose graph (yolo11-pose.yaml), same tuple layout
+    "yolo11n-pose_64x96": ("yolo11n-pose", 2, 64, 96, 14),
+}
+
+
 def net_input(name):
-    _, b, h, w, seed = NET_CASES[name]
+    _, b, h, w, seed = (NET_CASES.get(name) or POSE_NET_CASES[name])
     return np.random.default_rng(seed).random((b, 3, h, w), dtype=np.float32)
 
 
@@ -120,8 +125,14 @@ PREDICT_CASES = {  # name -> (model, n images, src h, src w, imgsz, seed)
 }
 
 
+POSE_PREDICT_CASES = {  # YOLO(pose ckpt).predict(): boxes + keypoints, letterboxed (240x320 -> 128x160 canvas, pad 4 rows)
+    "yolo11n-pose_240x320": ("yolo11n-pose", 2, 240, 320, 160, 23),
+    "yolo11n-pose_200x150": ("yolo11n-pose", 2, 200, 150, 160, 24),  # unrounded pad 20.0 px left/right
+}
+
+
 def predict_input(name):
-    _, n, h, w, _, seed = PREDICT_CASES[name]
+    _, n, h, w, _, seed = (PREDICT_CASES.get(name) or POSE_PREDICT_CASES[name])
     rng = np.random.default_rng(seed)
     return [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(n)]
 

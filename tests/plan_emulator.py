@@ -238,5 +238,10 @@ class PlanEmulator:
     def y(self):
         return self.bufs[self.plan.y_buf][:, :, 0, :]
 
+    def extras(self):
+        """(B, ne, A): the head's extra branch (Pose.cv4) in the reference's layout (head.py:245), pitch padding dropped."""
+        ne = self.plan.ne
+        return torch.cat([self.bufs[i][..., :ne].reshape(self.B, -1, ne).transpose(1, 2) for i in self.plan.extra_bufs], 2)
+
     def raws(self):
         return [self.bufs[i].permute(0, 3, 1, 2) for i in self.plan.head_bufs]
