@@ -61,7 +61,7 @@ def test_gather_extras_vs_oracle(ndim, with_geom, pitch):
         got = out[b, :n].reshape(n, nkpt, ndim)
         assert got[..., :2].tobytes() == ref[..., :2].tobytes()  # bit-exact x, y
         if ndim == 3:
-            assert np.abs(got[..., 2] - ref[..., 2]).max() < 1e-6
+            assert np.abs(got[..., 2] - ref[..., 2]).max(initial=0) < 1e-6
         exp = dets[b].copy()
         exp[:n, :4] = np.round(exp[:n, :4])
         assert np.array_equal(d_dev[b].cpu().numpy(), exp)
@@ -122,7 +122,7 @@ def test_engine_keypoints_equal_oracle_postprocess_on_own_tensors():
         assert np.array_equal(dets[i, : n[i]].cpu().numpy(), rb)
         got = kp[i, : n[i]].cpu().numpy()
         assert got.shape == rk.shape and got[..., :2].tobytes() == rk[..., :2].tobytes()
-        assert np.abs(got[..., 2] - rk[..., 2]).max() < 1e-6
+        assert np.abs(got[..., 2] - rk[..., 2]).max(initial=0) < 1e-6
 
 
 def _pose_checkpoint(model, imgsz, tmp_path):
@@ -175,7 +175,7 @@ def test_pose_dropin_vs_reference_golden(case, golden_dir, tmp_path):
             used.add(best)
             matched += 1
             ok, rk = ours_k[best], ref_k[j]
-            assert np.abs(ok[:, 2] - rk[:, 2]).max() <= 2e-2
+            assert np.abs(ok[:, 2] - rk[:, 2]).max(initial=0) <= 2e-2
             sure = np.abs(rk[:, 2] - 0.5) > 2e-2
             vis = sure & (rk[:, 2] >= 0.5)
             assert np.abs(ok[vis, :2] - rk[vis, :2]).max(initial=0) <= 0.5
