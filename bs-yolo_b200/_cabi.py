@@ -12,11 +12,11 @@ ABI_VERSION = 7
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 BF16, F32 = 0, 1
 (OP_CONV, OP_DWCONV, _OP_RESERVED3, OP_SPPF_POOL, OP_RESAMPLE, OP_ATTN, OP_ROWCOL_MEAN, OP_ELA_GATE, OP_ELA_APPLY, OP_GAP4,
- OP_MSCA_GATE, OP_WSUM4, OP_DECODE, OP_CONV_PAIR, _OP_RESERVED15, OP_PMSFA_DW, OP_MSCA_BRANCH) = range(1, 18)
+ OP_MSCA_GATE, OP_WSUM4, OP_DECODE, OP_CONV_PAIR, _OP_RESERVED15, OP_PMSFA_DW, OP_MSCA_BRANCH, OP_D2S) = range(1, 19)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 RES_NONE, RES_ADD, RES_MUL, RES_PREADD_UP2 = 0, 1, 2, 3
 OP_NAMES = {1: "conv", 2: "dwconv", 4: "sppf_pool", 5: "resample", 6: "attn", 7: "rowcol_mean", 8: "ela_gate",
-            9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode", 14: "conv_pair", 16: "pmsfa_dw", 17: "msca_branch"}
+            9: "ela_apply", 10: "gap4", 11: "msca_gate", 12: "wsum4", 13: "decode", 14: "conv_pair", 16: "pmsfa_dw", 17: "msca_branch", 18: "d2s"}
 
 
 class Buf(C.Structure):
@@ -35,7 +35,7 @@ class Op(C.Structure):
 EXPORTS = ["b2y_abi_version", "b2y_last_error", "b2y_plan_create", "b2y_plan_destroy", "b2y_plan_run",
            "b2y_plan_graph_build", "b2y_plan_graph_launch", "b2y_plan_set_mid_op", "b2y_plan_wait_mid", "b2y_plan_autotune", "b2y_plan_num_launches", "b2y_plan_op_impl", "b2y_conv_pair_fits", "b2y_preprocess",
            "b2y_decode", "b2y_nms_workspace_bytes", "b2y_nms", "b2y_scale_boxes", "b2y_preprocess_chw", "b2y_box_iou",
-           "b2y_match_predictions", "b2y_gather_extras"]
+           "b2y_match_predictions", "b2y_gather_extras", "b2y_process_mask"]
 
 _lib = None
 
@@ -78,6 +78,7 @@ def lib():
     L.b2y_match_predictions.argtypes = [vp, vp, vp, vp, C.POINTER(f32), i32, i32, i32, i32, vp, vp]
     L.b2y_gather_extras.argtypes = [C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(f32), i32, i32, i32, i32, i32, vp, vp,
                                     vp, i32, i32, vp, vp, vp]
+    L.b2y_process_mask.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, i32, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("b2y_abi_version",):

@@ -20,6 +20,7 @@ Reference anchors:
   MSCAAttention / ELA .......... ultralytics/nn/Addmodules/MSCA.py:19-88, ELA.py:33-100
   Detect / DFL ................. ultralytics/nn/modules/head.py:21-74, block.py:58-76
   Pose .......... ultralytics/nn/modules/head.py:230-250, cfg/models/11/yolo11-pose.yaml:15-47
+  Segment / Proto (§8 f4) ...... ultralytics/nn/modules/head.py:175-197, block.py:80-97, cfg/models/11/yolo11-seg.yaml:15-47
 """
 from __future__ import annotations
 
@@ -60,6 +61,11 @@ def conv_plain(name, c1, c2, k=1, p=0, g=1) -> Node:
     """Bare `nn.Conv2d` with bias, no norm, no activation."""
     return dict(type="Conv", name=name, c1=c1, c2=c2, k=_pair(k), s=(1, 1), p=_pair(p), g=g,
                 act="none", w=f"{name}.weight", b=f"{name}.bias", bn=None, bn_eps=0.0)
+
+
+def conv_t2(name, c1, c2) -> Node:
+    """`nn.ConvTranspose2d(c1, c2, 2, 2, 0, bias=True)` (Proto.upsample, block.py:91): weight (c1, c2, 2, 2)."""
+    return dict(type="ConvT", name=name, c1=c1, c2=c2, k=(2, 2), s=(2, 2), w=f"{name}.weight", b=f"{name}.bias")
 
 
 # ----------------------------------------------------------------------------- blocks
@@ -171,6 +177,21 @@ def pose(name, nc, ch, kpt_shape=(17, 3)) -> Node:
     return n
 
 
+def segment(name, nc, ch, nm=32, npr=256) -> Node:
+    """`Segment(Detect)` (head.py:175-197): the Detect branches, Proto(ch[0], npr, nm) on the P3 map (block.py:80-97:
+    Conv 3x3 -> ConvTranspose2d 2x2 s2 -> Conv 3x3 -> Conv 1x1) and one mask-coefficient branch per level, cv4[i] =
+    Conv(x, c4, 3) -> Conv(c4, c4, 3) -> Conv2d(c4, nm, 1) with c4 = max(ch[0] // 4, nm)."""
+    n = detect(name, nc, ch)
+    c4 = max(ch[0] // 4, nm)
+    n.update(head="segment", nm=nm, npr=npr, ne=nm,
+             proto=dict(type="Proto", name=f"{name}.proto", cv1=conv_bn(f"{name}.proto.cv1", ch[0], npr, 3),
+                        upsample=conv_t2(f"{name}.proto.upsample", npr, npr), cv2=conv_bn(f"{name}.proto.cv2", npr, npr, 3),
+                        cv3=conv_bn(f"{name}.proto.cv3", npr, nm, 1)),
+             cv4=[[conv_bn(f"{name}.cv4.{i}.0", x, c4, 3), conv_bn(f"{name}.cv4.{i}.1", c4, c4, 3),
+                   conv_plain(f"{name}.cv4.{i}.2", c4, nm, 1)] for i, x in enumerate(ch)])
+    return n
+
+
 # ----------------------------------------------------------------------------- whole graphs
 _STOCK = [  # (from, repeats, module, args)  -- yolo11-seg.yaml:15-46 with Detect as the last layer
     (-1, 1, "Conv", [64, 3, 2]), (-1, 1, "Conv", [128, 3, 2]), (-1, 2, "C3k2", [256, False, 0.25]),
@@ -198,12 +219,15 @@ _BSYOLO = [  # yolo11.yaml:15-52 of the fork; absolute `from` indices kept verba
 
 _STOCK_POSE = _STOCK[:-1] + [([16, 19, 22], 1, "Pose", [(17, 3)])]  # yolo11-pose.yaml:15-47 (same backbone / neck)
 
+_STOCK_SEG = _STOCK[:-1] + [([16, 19, 22], 1, "Segment", [32, 256])]  # yolo11-seg.yaml:47 as shipped
+
 HEAD_GAIN = 8.0
 SYNTH_CLS_BIAS = {  # model -> per-level bias shift of the final class conv (seed 0 calibration, see synth_state_dict)
     "yolo11n": (-3.678, -4.087, -3.846),
     "bsyolo_n": (-2.583, -3.309, -3.207),
     "yolo11x": (-3.446, -3.569, -3.91),
     "yolo11n-pose": (-3.678, -4.087, -3.846),  # cv4 is drawn after every Detect parameter: the Detect part equals yolo11n's
+    "yolo11n-seg": (-3.678, -4.087, -3.846),   # likewise (proto and cv4 come last)
 }
 
 MODELS = {  # name -> (table, scale, nc)
@@ -214,6 +238,7 @@ MODELS = {  # name -> (table, scale, nc)
     "yolo11x": (_STOCK, "x", 80),
     "bsyolo_n": (_BSYOLO, "n", 12),
     "yolo11n-pose": (_STOCK_POSE, "n", 80),  # nc: 80 and kpt_shape: [17, 3] are the yaml's own defaults
+    "yolo11n-seg": (_STOCK_SEG, "n", 80),
 }
 
 
@@ -257,6 +282,8 @@ def build_spec(model: str, nc: int | None = None) -> Node:
             c2, node = None, detect(name, nc, [ch[x] for x in f])
         elif kind == "Pose":
             c2, node = None, pose(name, nc, [ch[x] for x in f], args[0])
+        elif kind == "Segment":  # tasks.py:1079-1080: npr is width-scaled like a channel count
+            c2, node = None, segment(name, nc, [ch[x] for x in f], args[0], _div8(min(args[1], max_ch) * width))
         else:
             raise ValueError(kind)
         fl = [f] if isinstance(f, int) else list(f)
@@ -320,6 +347,10 @@ def synth_state_dict(spec: Node, seed: int = 0) -> dict[str, torch.Tensor]:
                 sd[n["bn"] + ".running_mean"] = t(rng.standard_normal(c2) * 0.1)
                 sd[n["bn"] + ".running_var"] = t(rng.uniform(0.8, 1.2, c2))
                 sd[n["bn"] + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+        elif ty == "ConvT":
+            c1, c2 = n["c1"], n["c2"]
+            sd[n["w"]] = t(rng.standard_normal((c1, c2, 2, 2)) * (1.0 / math.sqrt(c1)))
+            sd[n["b"]] = t(rng.standard_normal(c2) * 0.1)
         elif ty == "ELA":
             c, ks, name = n["c"], n["ks"], n["name"]
             sd[f"{name}.ch_att.2.weight"] = t(rng.standard_normal((c, 1, ks)) / math.sqrt(ks))

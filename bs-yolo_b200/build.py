@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb2y.so")
-SOURCES = ["plan.cu", "conv_simt.cu", "conv_tc.cu", "conv_pair.cu", "misc_ops.cu", "pmsfa_dw.cu", "msca.cu", "dw3_tile.cu", "attention.cu", "preprocess.cu", "decode.cu", "nms.cu", "val_match.cu", "extras.cu"]
+SOURCES = ["plan.cu", "conv_simt.cu", "conv_tc.cu", "conv_pair.cu", "misc_ops.cu", "pmsfa_dw.cu", "msca.cu", "dw3_tile.cu", "attention.cu", "preprocess.cu", "decode.cu", "nms.cu", "val_match.cu", "extras.cu", "seg.cu"]
 EXTRA = {"nms.cu": ["-fmad=false"], "preprocess.cu": ["-fmad=false"], "val_match.cu": ["-fmad=false"], "extras.cu": ["-fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -204,6 +204,7 @@ int launch_msca_branch(const MscaParams &p, cudaStream_t st);
 int launch_sppf_pool(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, cudaStream_t st);
 int launch_resample(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int H, int W, int scale,
                     cudaStream_t st);
+int launch_d2s(const bf16 *in, int in_cs, bf16 *out, int out_cs, int c, int B, int Hi, int Wi, cudaStream_t st);  // seg.cu
 int launch_attention(const bf16 *qkv, int qkv_cs, bf16 *out, int out_cs, int B, int N, int nh, int kd, int hd,
                      cudaStream_t st);
 int launch_rowcol_mean(const bf16 *x, int cs, int c, int B, int H, int W, int nbands, float *rowm, float *colm, cudaStream_t st);

@@ -296,6 +296,15 @@ int run_op(b2y_plan *pl, ResolvedOp &r, int idx, cudaStream_t st) {
       q.B = pl->B; q.H = bi->H; q.W = bi->W; q.C = o.cin;
       return launch_msca_branch(q, st);
     }
+    case B2Y_OP_D2S: {
+      const b2y_buf *bi = R.buf(o.in[0]), *bo = R.buf(o.out);
+      if (!R.ok) return B2Y_ERR_INVALID;
+      B2Y_REQUIRE(bi->dtype == B2Y_BF16 && bo->dtype == B2Y_BF16 && bo->H == 2 * bi->H && bo->W == 2 * bi->W &&
+                      o.cin == 4 * o.cout && o.in_coff[0] + o.cin <= bi->C && o.out_coff + o.cout <= bo->C,
+                  B2Y_ERR_INVALID, "op %d: depth-to-space views", idx);
+      return launch_d2s(reinterpret_cast<const bf16 *>(R.ptr(o.in[0], o.in_coff[0])), bi->C,
+                        reinterpret_cast<bf16 *>(R.ptr(o.out, o.out_coff)), bo->C, o.cout, pl->B, bi->H, bi->W, st);
+    }
     case B2Y_OP_DECODE: {
       const void *raw[4];
       int32_t hs[4], wsz[4];
@@ -470,7 +479,7 @@ void op_regions(const b2y_plan *pl, const ResolvedOp &r, std::vector<Region> &ou
     out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
     return;
   }
-  if (o.kind == B2Y_OP_RESAMPLE || o.kind == B2Y_OP_ATTN) {
+  if (o.kind == B2Y_OP_RESAMPLE || o.kind == B2Y_OP_ATTN || o.kind == B2Y_OP_D2S) {
     out.push_back(Region{o.in[0], o.in_coff[0], o.in_coff[0] + o.cin, false});
     out.push_back(Region{o.out, o.out_coff, o.out_coff + o.cout, true});
     return;

@@ -112,8 +112,25 @@ class Engine:
         """(B, H_l, W_l, pitch) fp32 NHWC raw map of the head's extra branch (Pose.cv4, head.py:245); channels [0, plan.ne)
         are the reference's ``cv4[level](x[level])`` (permute(0,3,1,2)), the rest is pitch padding."""
         if not self.plan.extra_bufs:
-            raise A.B2YError("this plan has no extra head branch (not a Pose model)")
+            raise A.B2YError("this plan has no extra head branch (not a Pose / Segment model)")
         return self.buffer(self.plan.extra_bufs[level])
+
+    @property
+    def protos(self) -> torch.Tensor:
+        """(B, H/4, W/4, nm) bf16 NHWC mask prototypes of a Segment head (Proto, block.py:95-97; permute(0,3,1,2) gives the
+        reference's ``p``, head.py:190)."""
+        if self.plan.proto_buf < 0:
+            raise A.B2YError("this plan has no mask prototypes (not a Segment model)")
+        return self.buffer(self.plan.proto_buf)
+
+    def mask_coeffs(self, kept: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+        """(B, max_det, nm) fp32 mask coefficients of the rows NMS kept -- the `mask` columns non_max_suppression carries
+        along in the reference (ops.py:245-246, 268-273)."""
+        from .ops import gather_extras
+        if self.plan.extra_kind != "segment":
+            raise A.B2YError("mask_coeffs: not a Segment model")
+        return gather_extras([self.extra(l) for l in range(len(self.plan.extra_bufs))], self.plan.extra_strides, self.plan.ne,
+                             kept, counts, mode=0)
 
     def keypoints(self, kept: torch.Tensor, counts: torch.Tensor, geom: torch.Tensor | None = None,
                   round_dets: torch.Tensor | None = None) -> torch.Tensor:

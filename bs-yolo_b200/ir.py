@@ -40,6 +40,10 @@ def build_ir(spec: Node, sd: dict[str, torch.Tensor]) -> Node:
                 b = beta - mu * scale + b * scale
             assert tuple(w.shape) == (n["c2"], n["c1"] // n["g"], *n["k"]), (n["name"], w.shape)
             n["weight"], n["bias"] = w.contiguous(), b.contiguous()
+        elif ty == "ConvT":
+            n["weight"] = sd[n["w"]].detach().float().cpu().contiguous()  # (c1, c2, 2, 2)
+            n["bias"] = sd[n["b"]].detach().float().cpu().contiguous()
+            assert tuple(n["weight"].shape) == (n["c1"], n["c2"], 2, 2), (n["name"], n["weight"].shape)
         elif ty == "ELA":
             p = n["name"]
             n["ch_w"] = sd[f"{p}.ch_att.2.weight"].detach().float().cpu().reshape(n["c"], n["ks"]).contiguous()
@@ -150,7 +154,7 @@ def _module_node(m, name: str) -> Node:
     if tn == "Concat":
         assert m.d == 1
         return dict(type="Concat", name=name)
-    if tn in ("Detect", "Pose"):
+    if tn in ("Detect", "Pose", "Segment"):
         if getattr(m, "end2end", False) or m.reg_max != 16:
             raise NotImplementedError("end2end / non-DFL16 Detect is not on the B200 path")
         cv2 = [[C(s[j], f"{name}.cv2.{i}.{j}") for j in range(3)] for i, s in enumerate(m.cv2)]
@@ -165,6 +169,18 @@ def _module_node(m, name: str) -> Node:
                     ch=[s[0].conv.in_channels for s in m.cv2], cv2=cv2, cv3=cv3, stride=[float(v) for v in m.stride])
         if tn == "Pose":  # head.py:230-250: Detect + one keypoint branch per level
             node.update(head="pose", kpt_shape=(int(m.kpt_shape[0]), int(m.kpt_shape[1])), ne=int(m.nk),
+                        cv4=[[C(s[j], f"{name}.cv4.{i}.{j}") for j in range(3)] for i, s in enumerate(m.cv4)])
+        if tn == "Segment":  # head.py:175-197: Detect + Proto on P3 + one mask-coefficient branch per level
+            p, up = m.proto, m.proto.upsample
+            if (type(up).__name__ != "ConvTranspose2d" or tuple(up.kernel_size) != (2, 2) or tuple(up.stride) != (2, 2)
+                    or tuple(up.padding) != (0, 0) or up.groups != 1 or up.bias is None):
+                raise NotImplementedError(f"{name}.proto.upsample: only ConvTranspose2d(c, c, 2, 2, 0, bias=True) is on the B200 path")
+            node.update(head="segment", nm=int(m.nm), npr=int(m.npr), ne=int(m.nm),
+                        proto=dict(type="Proto", name=f"{name}.proto", cv1=C(p.cv1, f"{name}.proto.cv1"),
+                                   upsample=dict(type="ConvT", name=f"{name}.proto.upsample", c1=up.in_channels,
+                                                 c2=up.out_channels, k=(2, 2), s=(2, 2), w=f"{name}.proto.upsample.weight",
+                                                 b=f"{name}.proto.upsample.bias"),
+                                   cv2=C(p.cv2, f"{name}.proto.cv2"), cv3=C(p.cv3, f"{name}.proto.cv3")),
                         cv4=[[C(s[j], f"{name}.cv4.{i}.{j}") for j in range(3)] for i, s in enumerate(m.cv4)])
         return node
     raise NotImplementedError(f"module {tn} ({name}) is not on the B200 hot path (no CPU fallback by design)")

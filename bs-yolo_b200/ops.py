@@ -191,6 +191,35 @@ def gather_extras(raws, strides, ne: int, kept: torch.Tensor, counts: torch.Tens
     return out
 
 
+def process_mask_batched(protos: torch.Tensor, coeffs: torch.Tensor, dets: torch.Tensor, counts, shape) -> list:
+    """ops.process_mask(protos[i], pred[:, 6:], pred[:, :4], shape, upsample=True) (ops.py:663-693) for every image of a batch
+    in ONE launch (b2y_process_mask).  protos: (B, mh, mw, pitch) bf16 NHWC (Engine.protos); coeffs (B, max_det, nm) fp32
+    (gather_extras mode 0); dets (B, max_det, 6) with boxes in network-input pixels (before scale_boxes); counts: the
+    per-image row counts as a host list.  Returns one (n_i, H, W) fp32 0/1 tensor per image (views of one allocation),
+    None where n_i == 0 (segment/predict.py:49-50)."""
+    if not (protos.is_cuda and coeffs.is_cuda and dets.is_cuda):
+        raise A.B2YError("process_mask: CUDA tensors required (no CPU fallback on the B200 path)")
+    B, mh, mw, pitch = (int(v) for v in protos.shape)
+    H, W = int(shape[0]), int(shape[1])
+    max_det, nm = int(coeffs.shape[1]), int(coeffs.shape[2])
+    assert protos.dtype == torch.bfloat16 and protos.is_contiguous() and coeffs.dtype == torch.float32 and coeffs.is_contiguous()
+    assert dets.dtype == torch.float32 and dets.is_contiguous() and tuple(dets.shape) == (B, max_det, 6) and len(counts) == B
+    rows = int(sum(counts))
+    if rows == 0:
+        return [None] * B
+    img = np.repeat(np.arange(B, dtype=np.int32), counts)
+    det = np.concatenate([np.arange(n, dtype=np.int32) for n in counts])
+    idx = torch.from_numpy(np.stack([img, det])).to(dets.device, non_blocking=True)
+    masks = torch.empty(rows, H, W, dtype=torch.float32, device=dets.device)
+    A.check(A.lib().b2y_process_mask(protos.data_ptr(), pitch, nm, mh, mw, coeffs.data_ptr(), dets.data_ptr(), max_det,
+                                     idx[0].data_ptr(), idx[1].data_ptr(), rows, H, W, masks.data_ptr(), _stream(dets.device)))
+    out, lo = [], 0
+    for n in counts:
+        out.append(masks[lo: lo + n] if n else None)
+        lo += n
+    return out
+
+
 # ---- validator path (SURVEY §8 f1) ------------------------------------------------------------------------------------
 def box_iou(box1: torch.Tensor, box2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
     """Drop-in for ultralytics.utils.metrics.box_iou (metrics.py:52-71) on CUDA tensors: (N,4) x (M,4) xyxy -> (N,M),

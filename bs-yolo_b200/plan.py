@@ -137,8 +137,9 @@ class Plan:
         # network input, space-to-depth: channel ((y&1)*2 + (x&1))*4 + {R,G,B,0} of super-pixel (y/2, x/2)
         self.input_buf = self.new_buf(16, H // 2, W // 2, name="input_s2d", exact=True)
         self.head_bufs: list[int] = []
-        self.extra_bufs: list[int] = []  # Pose: per-level raw keypoint maps (B, H_l, W_l, ne) fp32
-        self.ne = 0                      # logical channels of the extra maps (nk); the buffers are pitched to a multiple of 4
+        self.extra_bufs: list[int] = []  # Pose / Segment: per-level raw cv4 maps (B, H_l, W_l, ne) fp32
+        self.ne = 0                      # logical channels of the extra maps (nk | nm); buffers are pitched to a multiple of 4
+        self.proto_buf = -1              # Segment: mask prototypes (B, H/4, W/4, nm) bf16 NHWC
         self.extra_strides: list[float] = []
         self.extra_kind, self.kpt_shape = "", ()
         self.y_buf = -1
@@ -571,9 +572,32 @@ class Plan:
         if n.get("cv4"):
             self.extras(n, xs)
 
+    def conv_t2(self, n, x: View) -> View:
+        """nn.ConvTranspose2d(c1, c2, 2, 2, 0, bias=True) (Proto.upsample, block.py:91).  Kernel = stride = 2: every output
+        pixel (2y+dy, 2x+dx) is ONE tap of input pixel (y, x) -- four 1x1 convs.  They run as one tensor-core 1x1 conv
+        with 4*c2 output channels ordered (dy, dx, co), followed by a depth-to-space shuffle (OP_D2S)."""
+        c1, c2 = n["c1"], n["c2"]
+        assert x.real == x.c == c1 and c2 % 8 == 0
+        w = n["weight"].permute(2, 3, 1, 0).reshape(4 * c2, c1, 1, 1).contiguous()  # [(dy, dx, co)][ci]
+        node = dict(type="Conv", name=n["name"], c1=c1, c2=4 * c2, k=(1, 1), s=(1, 1), p=(0, 0), g=1, act="none")
+        t = self.conv(node, x, wb=(w, n["bias"].repeat(4)))
+        out = self.full(self.new_buf(c2, 2 * x.H, 2 * x.W, name=n["name"] + ".d2s"), c2)
+        op = OpSpec(A.OP_D2S, n["name"] + ".d2s", [t], out, cin=4 * c2, cout=c2)
+        op.bytes_alg = 2 * 4 * c2 * x.H * x.W * 2
+        self.ops.append(op)
+        return out
+
+    def proto(self, n, x: View):
+        """Proto (block.py:80-97): cv3(cv2(upsample(cv1(x)))) on the P3 map -> (B, H/4, W/4, nm) mask prototypes, kept bf16
+        NHWC: one pixel = nm contiguous values, the layout b2y_process_mask's dot products want."""
+        t = self.conv_t2(n["upsample"], self.conv(n["cv1"], x))
+        nm = n["cv3"]["c2"]
+        self.proto_buf = self.new_buf(nm, t.H, t.W, name=n["name"])
+        self.conv(n["cv3"], self.conv(n["cv2"], t), self.full(self.proto_buf, nm))
+
     def extras(self, n, xs):
-        """The extra branch of a Detect-derived head -- Pose.cv4 (head.py:239-246): Conv(x, c4, 3) -> Conv(c4, c4, 3) ->
-        Conv2d(c4, ne, 1) per level.  The reference concatenates the decoded (B, ne, A) rows under y and drags them through
+        """The extra branch of a Detect-derived head -- Pose.cv4 (head.py:239-246) / Segment.cv4 (head.py:186,193): Conv(x, c4, 3)
+        -> Conv(c4, c4, 3) -> Conv2d(c4, ne, 1) per level; a Segment head also runs Proto on the P3 map.  The reference concatenates the decoded (B, ne, A) rows under y and drags them through
         NMS (ops.py:245-246 `box, cls, mask = x.split((4, nc, nm), 1)`); here the branch stops at its raw fp32 NHWC maps:
         NMS runs on (B, 4+nc, A) as for Detect and b2y_gather_extras decodes only the <= max_det rows NMS kept.
         c4 = max(ch0 // 4, nk) is 51 on the n scale: both hidden maps are zero-padded to 64 channels (pad16)."""
@@ -586,6 +610,8 @@ class Plan:
             eb = self.new_buf(_r(self.ne, 4), x.H, x.W, A.F32, f"{n['name']}.extra{i}")
             self.extra_bufs.append(eb)
             self.conv(c4[2], t, View(eb, 0, self.ne, x.H, x.W), out_dtype=A.F32)
+        if n["head"] == "segment":
+            self.proto(n["proto"], xs[0])
 
     # ------------------------------------------------------------------ whole graph
     def _lower(self):

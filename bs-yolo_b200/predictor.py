@@ -373,12 +373,47 @@ def _build_class():
                             keypoints=kpts[i, : n[i]] if n[i] else kpts[i, :0].reshape(0, nk))  # predict.py:51: (0, nk) when empty
                     for i, (o, p) in enumerate(zip(orig_imgs, self.batch[0]))]
 
-    return {"B200DetectionPredictor": B200DetectionPredictor, "B200PosePredictor": B200PosePredictor}
+    class B200SegmentationPredictor(B200DetectionPredictor):
+        """SegmentationPredictor (models/yolo/segment/predict.py:8-57) on the B200 path (SURVEY §8 f4): Proto (block.py:80-97;
+        its ConvTranspose2d as one tensor-core 1x1 conv + a depth-to-space shuffle) and the mask-coefficient branch
+        (Segment.cv4, head.py:186,193) run inside the CUDA-graphed plan; NMS is the Detect NMS; the 32 coefficients of the
+        kept rows are gathered afterwards (b2y_gather_extras) and ops.process_mask (ops.py:663-693: coefficients @
+        prototypes, crop to the box, bilinear x4, > 0) runs as ONE launch for the whole batch (b2y_process_mask) instead
+        of a per-image loop.  ``Results.masks`` stay on the GPU.  retina_masks=True (process_mask_native) is not built."""
+
+        pipelined = False
+
+        def __init__(self, *args, **kwargs):
+            super().__init__(*args, **kwargs)
+            self.args.task = "segment"
+
+        def postprocess(self, preds, img, orig_imgs):
+            from .ops import process_mask_batched
+
+            if self.args.retina_masks:
+                raise NotImplementedError("retina_masks=True (ops.process_mask_native) is not on the B200 segment path")
+            if isinstance(preds, (list, tuple)):
+                preds = preds[0]
+            a = self.args
+            dets, counts, kept = nms_raw(preds, a.conf, a.iou, a.max_det, a.classes, bool(a.agnostic_nms), return_anchors=True)
+            eng = img.engine
+            coeffs = eng.mask_coeffs(kept, counts)
+            if not isinstance(orig_imgs, list):
+                from ultralytics.utils import ops as ref_ops
+                orig_imgs = ref_ops.convert_torch2numpy_batch(orig_imgs)
+            n = counts.tolist()  # the one device->host sync of the batch
+            masks = process_mask_batched(eng.protos, coeffs, dets, n, tuple(img.shape[2:]))  # from the UNSCALED boxes (predict.py:54)
+            scale_boxes_batched(dets, counts, tuple(img.shape[2:]), [o.shape[:2] for o in orig_imgs])
+            return [Results(o, path=p, names=self.model.names, boxes=dets[i, : n[i]], masks=masks[i])
+                    for i, (o, p) in enumerate(zip(orig_imgs, self.batch[0]))]
+
+    return {"B200DetectionPredictor": B200DetectionPredictor, "B200PosePredictor": B200PosePredictor,
+            "B200SegmentationPredictor": B200SegmentationPredictor}
 
 
 def __getattr__(name):  # PEP 562: resolve the classes on first use so importing this module never imports ultralytics
     global _CLS
-    if name in ("B200DetectionPredictor", "B200PosePredictor"):
+    if name in ("B200DetectionPredictor", "B200PosePredictor", "B200SegmentationPredictor"):
         if _CLS is None:
             _CLS = _build_class()
         return _CLS[name]

@@ -68,6 +68,9 @@ enum b2y_op_kind {
                            the second strip of branches 0..2); out = the four branch maps as channel slices [jC, (j+1)C) of
                            one 4C-channel buffer, res = gap (B, 4, C) fp32 = their global average pools.  cin = C,
                            cout = 4C; w_off = packed fp32 parameters (see plan.msca) */
+  B2Y_OP_D2S = 18       /* depth-to-space: out[b, 2y+dy, 2x+dx, c] = in[b, y, x, (dy*2+dx)*cout + c], cin = 4*cout, cout % 8 == 0.
+                           With the preceding 1x1 conv of 4*cout channels it is nn.ConvTranspose2d(c, c, 2, 2, 0) --
+                           Proto.upsample of a Segment head (block.py:91) */
 };
 
 enum b2y_conv_impl { B2Y_IMPL_AUTO = 0, B2Y_IMPL_SIMT = 1, B2Y_IMPL_TCGEN05 = 2 };
@@ -188,7 +191,7 @@ B2Y_API int b2y_match_predictions(const void *dets, const void *counts, const vo
                           const float *iouv, int32_t niou, int32_t B, int32_t max_det, int32_t max_labels, void *tp,
                           void *stream);
 
-/* ---- Detect-derived heads: the extra per-anchor columns of a Pose head --------------------------------
+/* ---- Detect-derived heads: the extra per-anchor columns of a Pose / Segment head --------------------------------
  *      b2y_gather_extras replaces, for the rows NMS kept, Pose.kpts_decode (ultralytics/nn/modules/head.py:252-279), the
  *      "mask" columns non_max_suppression carries along (ultralytics/utils/ops.py:245-246, 268-273) and
  *      PosePredictor.postprocess's ops.scale_coords + clip_coords (ultralytics/models/yolo/pose/predict.py:52-56,
@@ -204,6 +207,18 @@ B2Y_API int b2y_gather_extras(const void *const *raw, const int32_t *hs, const i
                       int32_t n_levels, int32_t pitch, int32_t ne, int32_t ndim, int32_t mode, const void *kept_anchor,
                       const void *counts, const void *geom, int32_t B, int32_t max_det, void *out, void *round_dets,
                       void *stream);
+
+/*      b2y_process_mask: ops.process_mask(protos, masks_in, bboxes, shape, upsample=True) (ultralytics/utils/ops.py:663-693,
+ *      crop_mask :644-660) for all kept rows of a batch in one launch -- the per-image loop of
+ *      SegmentationPredictor.postprocess (ultralytics/models/yolo/segment/predict.py:48-56, retina_masks=False).
+ *      protos: B x mh x mw x proto_cs bf16 NHWC mask prototypes (nm channels used; the plan's proto buffer), mh = H / 4,
+ *      mw = W / 4; coeffs: B x max_det x nm fp32 (b2y_gather_extras mode 0); dets: B x max_det x 6 fp32 with boxes in
+ *      network-input pixels (BEFORE b2y_scale_boxes).  row_img / row_det (device int32, `rows` entries): image and
+ *      detection index of every output row (the ragged concatenation of the images' kept rows).
+ *      masks: rows x H x W fp32, 1.0 where the upsampled cropped mask is > 0 else 0.0 (the reference's `masks.gt_(0.0)`). */
+B2Y_API int b2y_process_mask(const void *protos, int32_t proto_cs, int32_t nm, int32_t mh, int32_t mw, const void *coeffs,
+                     const void *dets, int32_t max_det, const void *row_img, const void *row_det, int32_t rows, int32_t H,
+                     int32_t W, void *masks, void *stream);
 
 #ifdef __cplusplus
 }

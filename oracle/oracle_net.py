@@ -179,7 +179,8 @@ def decode(raws, strides, nc):
 
 
 def pose_kpt_raw(n, xs):
-    """nn/modules/head.py:245: cat over levels of cv4[i](x[i]).view(bs, nk, -1) -> (B, nk, A) raw keypoint maps."""
+    """nn/modules/head.py:245 (Pose) / :193 (Segment): cat over levels of cv4[i](x[i]).view(bs, ne, -1) -> (B, ne, A) raw
+    keypoint maps / mask coefficients."""
     out = []
     for i, x in enumerate(xs):
         t = x
@@ -187,6 +188,12 @@ def pose_kpt_raw(n, xs):
             t = conv(c, t)
         out.append(t.reshape(t.shape[0], n["ne"], -1))
     return torch.cat(out, -1)
+
+
+def proto(n, x):
+    """nn/modules/block.py:95-97 (Proto.forward): cv3(cv2(upsample(cv1(x)))), upsample = ConvTranspose2d(c_, c_, 2, 2, 0)."""
+    t = F.conv_transpose2d(conv(n["cv1"], x), n["upsample"]["weight"], n["upsample"]["bias"], stride=2)
+    return conv(n["cv3"], conv(n["cv2"], t))
 
 
 def kpts_decode(kpts, shapes, strides, ndim):
@@ -210,7 +217,8 @@ def forward(ir, x, capture=None):
     """nn/tasks.py:138-165 (_predict_once) + head.py:64-74. x: (B,3,H,W) fp32 in [0,1] RGB.
 
     Returns (y, raws): y (B,4+nc,A) decoded, raws the three (B,64+nc,H,W) head maps.  A Pose head (head.py:242-250)
-    returns (cat(y, decoded keypoints) (B,4+nc+nk,A), (raws, raw keypoints (B,nk,A))).
+    returns (cat(y, decoded keypoints) (B,4+nc+nk,A), (raws, raw keypoints (B,nk,A))); a Segment head (head.py:188-197)
+    (cat(y, mask coefficients) (B,4+nc+nm,A), (raws, mask coefficients (B,nm,A), prototypes (B,nm,H/4,W/4))).
     ``capture``: optional dict filled with {layer index: output} for every top-level layer."""
     ys = []
     save = set(ir["save"])
@@ -234,6 +242,9 @@ def forward(ir, x, capture=None):
                 kpt = pose_kpt_raw(m, xin)
                 pk = kpts_decode(kpt, [r.shape[2:] for r in raws], m["stride"], m["kpt_shape"][1])
                 return torch.cat((y, pk), 1), (raws, kpt)
+            if m.get("head") == "segment":  # head.py:188-197: (cat(y, mc), (x, mc, p))
+                mc = pose_kpt_raw(m, xin)
+                return torch.cat((y, mc), 1), (raws, mc, proto(m["proto"], xin[0]))
             return y, raws
         else:
             x = _TOP[ty](m, xin)

@@ -10,6 +10,9 @@ numpy restatement of the reference's pre- and post-processing for the detect pat
   scale_boxes/clip_boxes .. ultralytics/utils/ops.py:92-127, 319-338
   scale_coords/clip_coords  ultralytics/utils/ops.py:740-772, 341-358 (Pose keypoints)
   pose_postprocess ........ ultralytics/models/yolo/pose/predict.py:39-59
+  process_mask/crop_mask .. ultralytics/utils/ops.py:663-693, 644-660 (Segment masks; torch fp32 because the
+                            reference's own bilinear F.interpolate is the definition)
+  segment_postprocess ..... ultralytics/models/yolo/segment/predict.py:29-57 (retina_masks=False)
 
 Deviations from the reference that are documented, not reproduced: the wall-clock abort of NMS
 (ops.py:238,312-314) and the in-place mutation of the caller's tensor (ops.py:244).
@@ -267,3 +270,54 @@ def keypoints_result(kpts: np.ndarray) -> np.ndarray:
     if k.ndim == 3 and k.shape[2] == 3:
         k[..., :2][k[..., 2] < 0.5] = 0
     return k
+
+
+# ----------------------------------------------------------------------------- Segment head post-process
+def crop_mask(masks, boxes):
+    """utils/ops.py:644-660.  masks (n, h, w), boxes (n, 4) torch tensors."""
+    import torch
+
+    _, h, w = masks.shape
+    x1, y1, x2, y2 = torch.chunk(boxes[:, :, None], 4, 1)
+    r = torch.arange(w, dtype=x1.dtype)[None, None, :]
+    c = torch.arange(h, dtype=x1.dtype)[None, :, None]
+    return masks * ((r >= x1) * (r < x2) * (c >= y1) * (c < y2))
+
+
+def process_mask(protos, masks_in, bboxes, shape) -> np.ndarray:
+    """utils/ops.py:663-693 with upsample=True.  protos (c, mh, mw), masks_in (n, c), bboxes (n, 4) in network-input pixels,
+    shape = (H, W) of the network input.  Returns (n, H, W) fp32 of 0 / 1."""
+    import torch
+    import torch.nn.functional as F
+
+    protos, masks_in = torch.as_tensor(np.asarray(protos, np.float32)), torch.as_tensor(np.asarray(masks_in, np.float32))
+    bboxes = torch.as_tensor(np.array(bboxes, np.float32, copy=True))
+    c, mh, mw = protos.shape
+    ih, iw = shape
+    masks = (masks_in @ protos.view(c, -1)).view(-1, mh, mw)
+    width_ratio, height_ratio = mw / iw, mh / ih
+    bboxes[:, 0] *= width_ratio
+    bboxes[:, 2] *= width_ratio
+    bboxes[:, 3] *= height_ratio
+    bboxes[:, 1] *= height_ratio
+    masks = crop_mask(masks, bboxes)
+    masks = F.interpolate(masks[None], tuple(shape), mode="bilinear", align_corners=False)[0]
+    return masks.gt_(0.0).numpy()
+
+
+def segment_postprocess(prediction, protos, nc, img1_shape, img0_shapes, conf=0.25, iou=0.7, max_det=300, classes=None,
+                        agnostic=False):
+    """models/yolo/segment/predict.py:29-57 (retina_masks=False): NMS carrying the nm coefficient rows, masks from the
+    UNSCALED boxes (:54), then boxes scaled to the original image (:55; not rounded).  Returns per image (boxes (n,6),
+    masks (n, H, W) or None when nothing was kept (:49-50))."""
+    res = []
+    rows = nms_with_extras(prediction, nc, conf_thres=conf, iou_thres=iou, max_det=max_det, classes=classes, agnostic=agnostic)
+    for b, (r, s0) in enumerate(zip(rows, img0_shapes)):
+        if not len(r):
+            res.append((r[:, :6], None))
+            continue
+        masks = process_mask(protos[b], r[:, 6:], r[:, :4], img1_shape)
+        boxes = r[:, :6].copy()
+        boxes[:, :4] = scale_boxes(img1_shape, boxes[:, :4], s0)
+        res.append((boxes, masks))
+    return res

@@ -62,6 +62,10 @@ def reference_cfg(model: str) -> dict:
         d = yaml_load(os.path.join(cfg_dir, "yolo11-pose.yaml"))
         d["scale"] = model[len("yolo11")]
         return d
+    if model.endswith("-seg"):  # cfg/models/11/yolo11-seg.yaml as shipped (Segment head, nm 32, npr 256)
+        d = yaml_load(os.path.join(cfg_dir, "yolo11-seg.yaml"))
+        d["scale"] = model[len("yolo11")]
+        return d
     assert model.startswith("yolo11")
     d = yaml_load(os.path.join(cfg_dir, "yolo11-seg.yaml"))
     d["scale"] = model[-1]
@@ -71,9 +75,10 @@ def reference_cfg(model: str) -> dict:
 
 def reference_model(model: str, state_dict=None):
     import_reference()
-    from ultralytics.nn.tasks import DetectionModel, PoseModel
+    from ultralytics.nn.tasks import DetectionModel, PoseModel, SegmentationModel
 
-    m = (PoseModel if model.endswith("-pose") else DetectionModel)(reference_cfg(model), verbose=False)
+    cls = PoseModel if model.endswith("-pose") else SegmentationModel if model.endswith("-seg") else DetectionModel
+    m = cls(reference_cfg(model), verbose=False)
     if state_dict is not None:
         m.load_state_dict(state_dict, strict=True)
     return m.eval()

@@ -12,6 +12,9 @@ The reference cannot travel to the GPU box, these vectors can.  What each file p
   net_<pose case>.npz / predict_<pose case>.npz ... the same two for the stock pose graph: PoseModel forward
                          (head.py:242-279: y incl. the decoded keypoint rows, raw keypoint maps) and
                          YOLO(pose ckpt).predict() -> Results.boxes.data + Results.keypoints.data (pose/predict.py:39-59)
+  net_<seg case>.npz / predict_<seg case>.npz ..... likewise for the stock segment graph: SegmentationModel forward (head.py:188-197:
+                         y incl. the mask-coefficient rows, prototypes) and YOLO(seg ckpt).predict() -> Results.boxes.data +
+                         Results.masks.data (segment/predict.py:29-57; masks bit-packed)
   val_match.npz ........ utils/metrics.py:52-71 box_iou and DetectionValidator._process_batch (detect/val.py:209-228 ->
                          engine/validator.py:222-258 match_predictions) on every tests/kat.py VAL_MATCH case
 """
@@ -90,6 +93,7 @@ def main():
 
     val_match()
     pose()
+    segment()
 
 
 def pose_checkpoint(model, imgsz, path):
@@ -128,6 +132,41 @@ def pose():
         print("predict", case, d["n"].tolist(), [d[f"kpts{i}"].shape for i in range(n)])
 
 
+def segment():
+    """the Segment head through the reference's own SegmentationModel / SegmentationPredictor."""
+    ref_import.import_reference()
+    from ultralytics import YOLO
+
+    for case, (model, *_rest) in kat.SEG_NET_CASES.items():
+        spec = arch.build_spec(model)
+        sd = arch.synth_state_dict(spec, 0)
+        m = ref_import.reference_model(model, sd)
+        with torch.no_grad():
+            y, (raws, mc, p) = m(torch.from_numpy(kat.net_input(case)))
+        np.savez_compressed(os.path.join(OUT, f"net_{case}.npz"), y=y.numpy(), mc=mc.numpy(), proto=p.numpy(),
+                            sd_checksum=np.float64(kat.state_dict_checksum(sd)))
+        print("net", case, tuple(y.shape), tuple(mc.shape), tuple(p.shape))
+    for case, (model, n, h, w, imgsz, seed) in kat.SEG_PREDICT_CASES.items():
+        spec = arch.build_spec(model)
+        m = ref_import.reference_model(model, arch.synth_state_dict(spec, 0))
+        m.names = {k: f"class{k}" for k in range(spec["nc"])}
+        m.args = {"task": "segment", "imgsz": imgsz}
+        path = f"/tmp/b2y_golden_{case}.pt"
+        torch.save({"model": m, "ema": None, "train_args": {"task": "segment", "imgsz": imgsz}}, path)
+        yolo = YOLO(path)
+        res = yolo.predict(kat.predict_input(case), device="cpu", imgsz=imgsz, conf=0.25, iou=0.7, max_det=300, verbose=False)
+        assert type(yolo.predictor).__name__ == "SegmentationPredictor"
+        d = {f"boxes{i}": r.boxes.data.numpy().astype(np.float32) for i, r in enumerate(res)}
+        for i, r in enumerate(res):
+            mk = r.masks.data.numpy()
+            assert set(np.unique(mk)) <= {0.0, 1.0}
+            d[f"masks{i}"] = np.packbits(mk.astype(np.uint8), axis=None)
+            d[f"mshape{i}"] = np.array(mk.shape, np.int64)
+        d["n"] = np.array([r.boxes.data.shape[0] for r in res], np.int64)
+        np.savez_compressed(os.path.join(OUT, f"predict_{case}.npz"), **d)
+        print("predict", case, d["n"].tolist(), [d[f"mshape{i}"].tolist() for i in range(n)])
+
+
 def val_match():
     """validator: IoU matrix and true-positive matrix of the reference's own validator methods."""
     ref_import.import_reference()
@@ -147,5 +186,5 @@ def val_match():
 
 
 if __name__ == "__main__":
-    # `make_golden.py val_match` / `make_golden.py pose` regenerate those files only
-    {"val_match": val_match, "pose": pose}.get((sys.argv[1:] or [""])[0], main)()
+    # `make_golden.py val_match` / `pose` / `segment` regenerate those files only
+    {"val_match": val_match, "pose": pose, "segment": segment}.get((sys.argv[1:] or [""])[0], main)()

@@ -17,8 +17,13 @@ POSE_NET_CASES = {  # the stock pose graph (yolo11-pose.yaml), sa
 }
 
 
+SEG_NET_CASES = {  # the stock segment graph (yolo11-seg.yaml): Proto + mask-coefficient branch
+    "yolo11n-seg_64x96": ("yolo11n-seg", 2, 64, 96, 15),
+}
+
+
 def net_input(name):
-    _, b, h, w, seed = (NET_CASES.get(name) or POSE_NET_CASES[name])
+    _, b, h, w, seed = (NET_CASES.get(name) or POSE_NET_CASES.get(name) or SEG_NET_CASES[name])
     return np.random.default_rng(seed).random((b, 3, h, w), dtype=np.float32)
 
 
@@ -131,8 +136,14 @@ POSE_PREDICT_CASES = {  # YOLO(pose ckpt).predict(): boxes + keypoints, letterbo
 }
 
 
+SEG_PREDICT_CASES = {  # YOLO(seg ckpt).predict(): boxes + (n, H', W') masks on the letterboxed canvas
+    "yolo11n-seg_240x320": ("yolo11n-seg", 2, 240, 320, 160, 25),
+    "yolo11n-seg_200x150": ("yolo11n-seg", 2, 200, 150, 160, 26),
+}
+
+
 def predict_input(name):
-    _, n, h, w, _, seed = (PREDICT_CASES.get(name) or POSE_PREDICT_CASES[name])
+    _, n, h, w, _, seed = (PREDICT_CASES.get(name) or POSE_PREDICT_CASES.get(name) or SEG_PREDICT_CASES[name])
     rng = np.random.default_rng(seed)
     return [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(n)]
 

@@ -166,6 +166,13 @@ class PlanEmulator:
             x = x.repeat_interleave(s, 1).repeat_interleave(s, 2)
         self.put(op.out, x)
 
+    def op_d2s(self, op):
+        """B2Y_OP_D2S: out[b, 2y+dy, 2x+dx, c] = in[b, y, x, (dy*2+dx)*cout + c]."""
+        x = self.get(op.ins[0])
+        B, H, W, _ = x.shape
+        c = op.cout
+        self.put(op.out, x.reshape(B, H, W, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, c))
+
     def op_attn(self, op):
         nh, kd, hd = op.ip
         qkv = self.get(op.ins[0])
@@ -242,6 +249,10 @@ class PlanEmulator:
         """(B, ne, A): the head's extra branch (Pose.cv4) in the reference's layout (head.py:245), pitch padding dropped."""
         ne = self.plan.ne
         return torch.cat([self.bufs[i][..., :ne].reshape(self.B, -1, ne).transpose(1, 2) for i in self.plan.extra_bufs], 2)
+
+    def protos(self):
+        """(B, nm, H/4, W/4): Segment's mask prototypes in the reference's layout (head.py:190)."""
+        return self.bufs[self.plan.proto_buf].permute(0, 3, 1, 2)
 
     def raws(self):
         return [self.bufs[i].permute(0, 3, 1, 2) for i in self.plan.head_bufs]
