@@ -19,7 +19,8 @@ scale_boxes, neighbouring chunks overlapped; boxes stay on the GPU, only the cou
 ``Results`` of chunk i under the GPU work of chunk i+1.  Ragged lists and tensor sources take the single-engine route.
 
 ``stream_inference`` itself is inherited, so callbacks, ``Results``, ``Results.speed`` and the per-predictor lock keep
-working.  There is no CPU fallback: a non-CUDA device, ``half=True``, ``augment``, ``visualize`` and ``embed`` raise.
+working.  There is no CPU fallback: a non-CUDA device, ``augment``, ``visualize`` and ``embed`` raise; ``half=True`` is accepted
+(the path's only 16-bit mode is bf16 operands with fp32 accumulation, and it is always on).
 
 The reference package is imported lazily (it is not a dependency of the kernels or of bench.py).
 """
@@ -234,7 +235,13 @@ def _build_class():
 
         def setup_model(self, model, verbose=True):
             if self.args.half:
-                raise NotImplementedError("half=True (fp16) is a reference-only dtype; the B200 path computes in bf16/fp32")
+                # engine/predictor.py:131 + autobackend.py:153: the reference casts model and input to fp16.  The B200 path has one
+                # 16-bit mode and always runs in it: bf16 operands, fp32 accumulation and fp32 decode / NMS (fp16's range would
+                # need loss scaling in the DFL exponentials; bf16 does not).  half=True therefore selects nothing new -- it is
+                # accepted so that callers' scripts keep working, and the flag is cleared (model.fp16 stays False: no .half()
+                # of the input anywhere downstream).  Parity gate: the same 1e-2 / IoU 0.99 gate as half=False.
+                from ultralytics.utils import LOGGER
+                LOGGER.info("bs_yolo_b200: half=True -> the B200 path already computes in 16 bit (bf16 operands, fp32 accumulate)")
             model = model if model is not None else self.args.model
             if isinstance(model, (str, bytes)) or hasattr(model, "__fspath__"):
                 from ultralytics.nn.tasks import attempt_load_weights  # the reference's own loader, unchanged
