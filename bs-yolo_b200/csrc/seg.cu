@@ -10,10 +10,12 @@
 //                            crop_mask against the box scaled to the prototype grid     (:681-690, :644-660)
 //                            F.interpolate(bilinear, align_corners=False) to (H, W)      (:692)
 //                            masks.gt_(0.0)                                              (:693)
-//                          A CTA owns one 64 x 64 output tile of one kept row: the (<= 18 x 18) low-resolution mask values
-//                          it needs are computed once into shared memory (nm-long dot products against bf16 prototypes,
-//                          fp32 accumulate) and each thread then blends / thresholds 16 output pixels.  The low-resolution
-//                          mask, its cropped copy and the upsampled float mask of the reference never touch HBM.
+//                          A CTA owns one 64 x 64 output tile of one kept row: the 18 x 18 low-resolution mask values it
+//                          needs are computed once into shared memory (nm-long dot products against bf16 prototypes,
+//                          fp32 accumulate), each thread then blends / thresholds 4 x 4 output pixels and writes them
+//                          with 16-byte stores; tiles that miss the box are zero-filled without touching the
+//                          prototypes.  The low-resolution mask, its cropped copy and the upsampled float mask of the
+//                          reference never touch HBM: the kernel is a pure HBM writer (rows x H x W x 4 bytes).
 #include "common.cuh"
 
 namespace {
@@ -60,52 +62,67 @@ __global__ void __launch_bounds__(256) process_mask_kernel(MaskParams p) {
   const int b = p.row_img[r], k = p.row_det[r];
   const int oy0 = blockIdx.y * TILE, ox0 = blockIdx.x * TILE;
   const int ly0 = oy0 / 4 - 1, lx0 = ox0 / 4 - 1;  // prototype-grid origin of the shared tile (may be -1)
-  if (threadIdx.x < p.nm) coef[threadIdx.x] = p.coeffs[((size_t)b * p.max_det + k) * p.nm + threadIdx.x];
   // box on the prototype grid (ops.py:681-688: x *= mw / iw, y *= mh / ih; fp32 products like the reference's in-place muls)
   const float *box = p.dets + ((size_t)b * p.max_det + k) * 6;
   const float wr = (float)p.mw / (float)p.W, hr = (float)p.mh / (float)p.H;
   const float x1 = __fmul_rn(box[0], wr), y1 = __fmul_rn(box[1], hr), x2 = __fmul_rn(box[2], wr), y2 = __fmul_rn(box[3], hr);
-  __syncthreads();
-  for (int i = threadIdx.x; i < LR * LR; i += blockDim.x) {
-    const int ly = ly0 + i / LR, lx = lx0 + i % LR;
-    float v = 0.f;
-    if (ly >= 0 && ly < p.mh && lx >= 0 && lx < p.mw) {
-      const float fx = (float)lx, fy = (float)ly;
-      if (fx >= x1 && fx < x2 && fy >= y1 && fy < y2) {  // crop_mask (ops.py:657-660): zero outside the box
-        const bf16 *q = p.protos + ((size_t)(b * p.mh + ly) * p.mw + lx) * p.cs;
-        for (int c = 0; c < p.nm; c += 8) {
-          float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4 *>(q + c)), f);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 quads of 4 columns x 16 rows per pass, 4 passes
+  const int ox = ox0 + 4 * tx;
+  float *o = p.out + (size_t)r * p.H * p.W + ox;
+  // the tile's prototype cells (clamped to the grid) against the box: no overlap -> the tile is all zeros (crop_mask)
+  const float cx_lo = (float)max(lx0, 0), cx_hi = (float)min(lx0 + LR - 1, p.mw - 1);
+  const float cy_lo = (float)max(ly0, 0), cy_hi = (float)min(ly0 + LR - 1, p.mh - 1);
+  if (!(cx_hi >= x1 && cx_lo < x2 && cy_hi >= y1 && cy_lo < y2)) {
+    if (ox < p.W) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v = fmaf(coef[c + j], f[j], v);
-        }
+      for (int pass = 0; pass < 4; ++pass) {
+        const int oy = oy0 + pass * 16 + ty;
+        if (oy < p.H) *reinterpret_cast<float4 *>(o + (size_t)oy * p.W) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
+  if (threadIdx.x < p.nm) coef[threadIdx.x] = p.coeffs[((size_t)b * p.max_det + k) * p.nm + threadIdx.x];
+  __syncthreads();
+  // Low-resolution cropped mask values under the tile, one halo cell on each side.  Coordinates are CLAMPED to the grid
+  // (edge replication): ATen's bilinear rule clamps the source index at 0 and takes i1 = i0 on the last cell, which is the
+  // same as blending a cell with its own replica.
+  for (int i = threadIdx.x; i < LR * LR; i += blockDim.x) {
+    const int ly = min(max(ly0 + i / LR, 0), p.mh - 1), lx = min(max(lx0 + i % LR, 0), p.mw - 1);
+    const float fx = (float)lx, fy = (float)ly;
+    float v = 0.f;
+    if (fx >= x1 && fx < x2 && fy >= y1 && fy < y2) {  // crop_mask (ops.py:657-660): zero outside the box
+      const bf16 *q = p.protos + ((size_t)(b * p.mh + ly) * p.mw + lx) * p.cs;
+      for (int c = 0; c < p.nm; c += 8) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(q + c)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v = fmaf(coef[c + j], f[j], v);
       }
     }
     low[i / LR][i % LR] = v;
   }
   __syncthreads();
-  // bilinear, align_corners=False, scale 1/4 (ATen upsample_bilinear2d: src = 0.25 * (dst + 0.5) - 0.5 clamped at 0,
-  // i1 = i0 + (i0 < in - 1), lambda1 = src - i0)
-  const int tx = threadIdx.x & 63, ty4 = threadIdx.x >> 6;  // 64 columns x 4 row groups of 16 rows
-  const int ox = ox0 + tx;
   if (ox >= p.W) return;
-  float sx = 0.25f * ((float)ox + 0.5f) - 0.5f;
-  if (sx < 0.f) sx = 0.f;
-  const int ix0 = (int)sx, ix1 = ix0 + (ix0 < p.mw - 1 ? 1 : 0);
-  const float lx1 = sx - (float)ix0, lx0w = 1.f - lx1;
-  const int cx0 = ix0 - lx0, cx1 = ix1 - lx0;
-  float *o = p.out + (size_t)r * p.H * p.W + ox;
-#pragma unroll 4
-  for (int j = 0; j < 16; ++j) {
-    const int oy = oy0 + ty4 * 16 + j;
+  // Bilinear x4, align_corners=False (ATen upsample_bilinear2d: src = 0.25 * (dst + 0.5) - 0.5): output 4m + i lies between
+  // cells m - 1 and m (i = 0, 1; weight of the upper cell 0.625, 0.875) or m and m + 1 (i = 2, 3; 0.125, 0.375).  A thread
+  // owns four consecutive columns (one cell triple) and writes them with one 16-byte store per row.
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int row = pass * 16 + ty, oy = oy0 + row;
     if (oy >= p.H) break;
-    float sy = 0.25f * ((float)oy + 0.5f) - 0.5f;
-    if (sy < 0.f) sy = 0.f;
-    const int iy0 = (int)sy, iy1 = iy0 + (iy0 < p.mh - 1 ? 1 : 0);
-    const float ly1 = sy - (float)iy0, ly0w = 1.f - ly1;
-    const int cy0 = iy0 - ly0, cy1 = iy1 - ly0;
-    const float v = ly0w * (lx0w * low[cy0][cx0] + lx1 * low[cy0][cx1]) + ly1 * (lx0w * low[cy1][cx0] + lx1 * low[cy1][cx1]);
-    o[(size_t)oy * p.W] = v > 0.f ? 1.f : 0.f;
+    const int m = row >> 2, i = row & 3;
+    const int cy0 = m + (i >> 1);
+    const float wy1 = (i == 0) ? 0.625f : (i == 1) ? 0.875f : (i == 2) ? 0.125f : 0.375f, wy0 = 1.f - wy1;
+    const float c0 = wy0 * low[cy0][tx] + wy1 * low[cy0 + 1][tx];
+    const float c1 = wy0 * low[cy0][tx + 1] + wy1 * low[cy0 + 1][tx + 1];
+    const float c2 = wy0 * low[cy0][tx + 2] + wy1 * low[cy0 + 1][tx + 2];
+    float4 v;
+    v.x = (0.375f * c0 + 0.625f * c1) > 0.f ? 1.f : 0.f;
+    v.y = (0.125f * c0 + 0.875f * c1) > 0.f ? 1.f : 0.f;
+    v.z = (0.875f * c1 + 0.125f * c2) > 0.f ? 1.f : 0.f;
+    v.w = (0.625f * c1 + 0.375f * c2) > 0.f ? 1.f : 0.f;
+    *reinterpret_cast<float4 *>(o + (size_t)oy * p.W) = v;
   }
 }
 }  // namespace
@@ -127,6 +144,7 @@ extern "C" int b2y_process_mask(const void *protos, int32_t proto_cs, int32_t nm
   B2Y_REQUIRE(nm > 0 && nm <= MAX_NM && nm % 8 == 0 && proto_cs >= nm && proto_cs % 8 == 0 && ((uintptr_t)protos & 15) == 0,
               B2Y_ERR_UNSUPPORTED, "process_mask: nm = %d (pitch %d) must be a multiple of 8, at most %d, 16-byte aligned", nm,
               proto_cs, MAX_NM);
+  B2Y_REQUIRE(W % 4 == 0 && ((uintptr_t)masks & 15) == 0, B2Y_ERR_UNSUPPORTED, "process_mask: W %% 4 and a 16-byte aligned output");
   B2Y_REQUIRE(mh * 4 == H && mw * 4 == W, B2Y_ERR_UNSUPPORTED,
               "process_mask: prototypes %dx%d must be the network input %dx%d divided by 4 (Proto on the stride-8 map)", mh, mw,
               H, W);

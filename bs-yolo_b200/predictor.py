@@ -79,8 +79,10 @@ class _Staging:
 
     DEPTH = 4
 
-    def __init__(self, B, h, w):
+    def __init__(self, B, h, w, depth: int | None = None):
         self.B, self.h, self.w = B, h, w
+        if depth is not None:
+            self.DEPTH = depth  # the single-engine route stages one batch at a time
         self.bufs = [torch.empty(B, h, w, 3, dtype=torch.uint8).pin_memory() for _ in range(self.DEPTH)]
         self.views = [b.numpy() for b in self.bufs]
         self.free = [threading.Event() for _ in range(self.DEPTH)]
@@ -170,6 +172,7 @@ class B200Backend:
         self.use_graph = use_graph
         self._engines: dict[tuple[int, int, int], Engine] = {}
         self._pipes: dict[tuple, tuple] = {}
+        self._stagings: dict[tuple, _Staging] = {}
 
     def engine(self, B: int, H: int, W: int) -> Engine:
         key = (B, H, W)
@@ -196,6 +199,18 @@ class B200Backend:
                                       use_graph=self.use_graph)
             hit = (pipe, _Staging(B, *src_hw))
             self._pipes[key] = hit
+        return hit
+
+    def staging(self, B: int, src_hw) -> "_Staging":
+        """Pinned staging ring for same-shape batches on the single-engine route (Pose / Segment predictors), cached per
+        (B, source shape): allocating pinned memory per batch (``.pin_memory()``) costs more than the whole GPU step."""
+        key = (B, tuple(src_hw))
+        hit = self._stagings.get(key)
+        if hit is None:
+            if len(self._stagings) >= 2:  # a stream of changing shapes must not accumulate pinned memory
+                self._stagings.pop(next(iter(self._stagings)))
+            hit = _Staging(B, *src_hw, depth=1)
+            self._stagings[key] = hit
         return hit
 
     def eval(self):
@@ -285,7 +300,12 @@ def _build_class():
             lib, st = A.lib(), torch.cuda.current_stream(dev).cuda_stream
             dst = eng.input_nhwc
             if hot:  # same-shape batch on the single-engine route (heads whose extras the chunked pipeline does not carry)
-                src = torch.from_numpy(np.ascontiguousarray(np.stack(im))).pin_memory().to(dev, non_blocking=True)
+                stg = self.model.staging(len(im), shapes[0][:2])
+                pinned = next(iter(stg.chunks(im)))  # cached pinned ring, filled by the copy pool (GIL-free memmoves)
+                src = pinned.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                stg.uploaded(pinned, ev)  # the ring slot may be refilled once this copy has completed
                 _, _, top, left, uh, uw = geo[0]
                 A.check(lib.b2y_preprocess(src.data_ptr(), len(im), shapes[0][0], shapes[0][1], dst.data_ptr(), H, W, top, left,
                                            uh, uw, 0, st))

@@ -99,36 +99,47 @@ def test_segment_plan_bf16_error_budget():
 
 
 def mask_kernel_model(protos, coeffs, boxes, H, W):
-    """Tile-faithful Python model of process_mask_kernel (csrc/seg.cu): 64 x 64 output tiles, an 18 x 18 shared tile of
-    cropped low-resolution values with origin (oy0/4 - 1, ox0/4 - 1), ATen's bilinear index rule.  protos (mh, mw, nm)."""
+    """Tile-faithful Python model of process_mask_kernel (csrc/seg.cu): 64 x 64 output tiles; an 18 x 18 shared tile of
+    cropped low-resolution values with origin (oy0/4 - 1, ox0/4 - 1) and edge-replicated coordinates; the zero-tile
+    shortcut; fixed x4 bilinear weights (0.625, 0.875, 0.125, 0.375), rows blended first, one quad of columns per
+    thread.  protos (mh, mw, nm)."""
     mh, mw, nm = protos.shape
     n = len(coeffs)
-    out = np.zeros((n, H, W), np.float32)
+    out = np.full((n, H, W), -1, np.float32)
     f = np.float32
+    wsel = (f(0.625), f(0.875), f(0.125), f(0.375))
     for r in range(n):
         x1, y1, x2, y2 = (f(boxes[r, j]) * f(0.25) for j in range(4))
         for oy0 in range(0, H, 64):
             for ox0 in range(0, W, 64):
                 ly0, lx0 = oy0 // 4 - 1, ox0 // 4 - 1
+                cx_lo, cx_hi = max(lx0, 0), min(lx0 + 17, mw - 1)
+                cy_lo, cy_hi = max(ly0, 0), min(ly0 + 17, mh - 1)
+                if not (cx_hi >= x1 and cx_lo < x2 and cy_hi >= y1 and cy_lo < y2):
+                    out[r, oy0:oy0 + 64, ox0:ox0 + 64] = 0
+                    continue
                 low = np.zeros((18, 18), np.float32)
                 for i in range(18 * 18):
-                    ly, lx = ly0 + i // 18, lx0 + i % 18
-                    if 0 <= ly < mh and 0 <= lx < mw and x1 <= lx < x2 and y1 <= ly < y2:
+                    ly, lx = min(max(ly0 + i // 18, 0), mh - 1), min(max(lx0 + i % 18, 0), mw - 1)
+                    if x1 <= lx < x2 and y1 <= ly < y2:
                         low[i // 18, i % 18] = np.dot(coeffs[r].astype(np.float64), protos[ly, lx].astype(np.float64))
-                for oy in range(oy0, min(oy0 + 64, H)):
-                    sy = max(f(0.25) * (f(oy) + f(0.5)) - f(0.5), f(0))
-                    iy0 = int(sy)
-                    iy1 = iy0 + (1 if iy0 < mh - 1 else 0)
-                    wy1 = f(sy - iy0)
-                    for ox in range(ox0, min(ox0 + 64, W)):
-                        sx = max(f(0.25) * (f(ox) + f(0.5)) - f(0.5), f(0))
-                        ix0 = int(sx)
-                        ix1 = ix0 + (1 if ix0 < mw - 1 else 0)
-                        wx1 = f(sx - ix0)
-                        a, b = low[iy0 - ly0, ix0 - lx0], low[iy0 - ly0, ix1 - lx0]
-                        c, d = low[iy1 - ly0, ix0 - lx0], low[iy1 - ly0, ix1 - lx0]
-                        v = (1 - wy1) * ((1 - wx1) * a + wx1 * b) + wy1 * ((1 - wx1) * c + wx1 * d)
-                        out[r, oy, ox] = 1.0 if v > 0 else 0.0
+                for row in range(64):
+                    oy = oy0 + row
+                    if oy >= H:
+                        break
+                    m, i = row >> 2, row & 3
+                    cy0 = m + (i >> 1)
+                    wy1 = wsel[i]
+                    col = (f(1) - wy1) * low[cy0] + wy1 * low[cy0 + 1]  # 18 blended columns
+                    for tx in range(16):
+                        ox = ox0 + 4 * tx
+                        if ox >= W:
+                            break
+                        c0, c1, c2 = col[tx], col[tx + 1], col[tx + 2]
+                        quad = (f(0.375) * c0 + f(0.625) * c1, f(0.125) * c0 + f(0.875) * c1,
+                                f(0.875) * c1 + f(0.125) * c2, f(0.625) * c1 + f(0.375) * c2)
+                        out[r, oy, ox:ox + 4] = [1.0 if v > 0 else 0.0 for v in quad]
+    assert (out >= 0).all()  # every pixel written exactly by some tile
     return out
 
 
@@ -136,9 +147,11 @@ def test_mask_kernel_index_arithmetic_matches_reference_process_mask():
     rng = np.random.default_rng(4)
     H, W, nm = 96, 160, 8  # 2 x 3 tiles, the bottom row of tiles is partial
     protos = rng.standard_normal((nm, H // 4, W // 4)).astype(np.float32)
-    coeffs = rng.standard_normal((4, nm)).astype(np.float32)
-    boxes = np.array([[10.3, 5.2, 150.9, 90.1], [0, 0, W, H], [60.0, 30.0, 70.0, 66.0], [-20, -20, 63.9, 200]], np.float32)
+    coeffs = rng.standard_normal((6, nm)).astype(np.float32)
+    boxes = np.array([[10.3, 5.2, 150.9, 90.1], [0, 0, W, H], [60.0, 30.0, 70.0, 66.0], [-20, -20, 63.9, 200],
+                      [130.0, 70.0, 159.0, 95.0], [13.3, 13.2, 13.9, 13.8]], np.float32)  # bottom-right corner; no cell inside
     ref = oracle_post.process_mask(protos, coeffs, boxes, (H, W))
     got = mask_kernel_model(protos.transpose(1, 2, 0), coeffs, boxes, H, W)
     assert got.shape == ref.shape and (got != ref).mean() < 2e-4 and 0.05 < ref.mean() < 0.95
-    assert np.array_equal(got[2].sum(), ref[2].sum())  # the small interior box: identical support
+    assert np.array_equal(got[2], ref[2]) and np.array_equal(got[4], ref[4])  # small boxes: identical masks
+    assert not got[5].any() and not ref[5].any()
