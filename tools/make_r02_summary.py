@@ -34,6 +34,30 @@ def launch_list(path):
     return [per[k] for k in sorted(per)]
 
 
+def f4_section():
+    """SURVEY §8 f4 (Pose / Segment heads): tools/f4_probe.py -> profiles/r02_f4_probe.json."""
+    p = f"{PROF}/{TAG}_f4_probe.json"
+    if not os.path.exists(p):
+        return []
+    d = json.load(open(p))
+    md = [f"## Pose and Segment heads (SURVEY §8 f4; `tools/f4_probe.py`, {d['frames']} synthetic {d['imgsz']}x{d['imgsz']} frames, one B200)", "",
+          "| head | drop-in end to end (img/s) | reference CPU predictor (img/s) | ratio | network graph ms | NMS ms | head post-process | device-timed img/s |",
+          "|---|---|---|---|---|---|---|---|"]
+    for k, h in d["heads"].items():
+        post = (f"kept-row gather + keypoint decode + scale_coords: {h['keypoints_kernel_ms'] * 1e3:.0f} us" if k == "pose" else
+                f"coefficient gather {h['coeff_gather_ms'] * 1e3:.0f} us + `process_mask_kernel` {h['process_mask_ms']:.2f} ms "
+                f"({h['mask_rows']} masks, {h['mask_bytes_written'] / 1e9:.1f} GB written: {h['process_mask_gbps']:.0f} GB/s = "
+                f"{h['process_mask_frac_of_hbm']:.2f} of the {HBM:.0f} GB/s copy peak)")
+        md.append(f"| {k} (`{h['model']}`, `{h['predictor']}`) | {h['e2e_images_per_s']:,.0f} | {h['reference_cpu_images_per_s']:.1f} "
+                  f"({h['reference_cpu_sample']}) | {h['e2e_over_reference']:.0f}x | {h['network_graph_ms']:.3f} | {h['nms_ms']:.3f} | {post} | "
+                  f"{h['images_per_s_device']:,.0f} |")
+    md += ["", "The synthetic checkpoints fill `max_det`: 300 detections per image, i.e. 19,200 640x640 fp32 masks per 64-frame batch -- the "
+           "worst case for the mask kernel and for `Results` construction (real scenes keep tens of rows).  First version of the mask "
+           "kernel (scalar 4-byte stores, per-pixel index arithmetic): 13.24 ms = 0.36 of HBM; with one column quad per thread, 16-byte "
+           "stores and fixed x4 weights: 5.15 ms = 0.93.  GPU tests: `profiles/r02_pose_gpu_tests.log`, `profiles/r02_seg_gpu_tests.log`.", ""]
+    return md
+
+
 def family_table(launches, title):
     agg = defaultdict(lambda: [0, 0.0])
     for L in launches:
@@ -178,6 +202,7 @@ def main():
             md.append(f"| {a['test']} | {a['total']} | {a['matched']} | {a['near_conf']} | {a['class_flip']} | {a['nms_iou_tie']} | "
                       f"{a['nms_cascade']} | {a['max_det_cut']} | {a['unexplained']} |")
         md.append("")
+    md += f4_section()
     open(f"{PROF}/{TAG}_summary.md", "w").write("\n".join(md) + "\n")
     print("\n".join(md[:40]))
 
