@@ -20,7 +20,9 @@ Headline workload: BASELINE.json configs[1] (stock yolo11n, batch 64 per GPU, bf
             @1280 batch 32 (N=1), configs[4] SAHI-style tiled inference of 3840x2160 frames (tiles sharded over the N
             GPUs, global NMS merge), the drop-in `YOLO.predict(list, predictor=B200DetectionPredictor)` (N=1), `ingest`
             (`predict("dir of image files", batch=64)`: prefetching loader vs the reference's) and `val`
-            (`YOLO.val(validator=B200DetectionValidator)` beside the reference's CPU validator) -- SURVEY §8 f2 / f1, N=1.
+            (`YOLO.val(validator=B200DetectionValidator)` beside the reference's CPU validator) -- SURVEY §8 f2 / f1, N=1;
+            `pose` / `segment` (SURVEY §8 f4, N=1): the Pose / Segment drop-in predictors end to end, device-timed stages,
+            the mask kernel's HBM roofline, the reference's CPU predictor beside them.
             `--workload X` makes X the headline instead; `--no-extras` prints the headline only.
 """
 from __future__ import annotations
@@ -130,7 +132,7 @@ def cpu_port_throughput(model, imgsz, n_images, batch, threads, steps=1, warmup=
     return steps * n_images / dt, dt / steps
 
 
-def reference_yolo(model, imgsz):
+def reference_yolo(model, imgsz, task="detect"):
     """YOLO(<synthetic checkpoint written like the reference's trainer does>) of the UNMODIFIED reference package
     (baseline/_ref, pip-installed from /root/reference by __graft_entry__.build()); None if it is not importable."""
     from oracle import ref_import
@@ -143,9 +145,11 @@ def reference_yolo(model, imgsz):
     spec = arch.build_spec(model)
     m = ref_import.reference_model(model, arch.synth_state_dict(spec, 0))
     m.names = {k: f"class{k}" for k in range(spec["nc"])}
-    m.args = {"task": "detect", "imgsz": imgsz}
+    if task == "pose":
+        m.kpt_shape = list(m.model[-1].kpt_shape)  # the reference's trainer sets it (models/yolo/pose/train.py:49)
+    m.args = {"task": task, "imgsz": imgsz}
     path = os.path.join(tempfile.mkdtemp(prefix="b2y_ref_"), f"{model}.pt")
-    torch.save({"model": m, "ema": None, "train_args": {"task": "detect", "imgsz": imgsz}}, path)
+    torch.save({"model": m, "ema": None, "train_args": {"task": task, "imgsz": imgsz}}, path)
     return YOLO(path)
 
 
@@ -702,6 +706,87 @@ def emit(line: dict):
     out.flush()
 
 
+def run_head_workload(ctx: Ctx, head: str, n: int = 32):
+    """SURVEY §8 f4, rank 0 at N=1: the Pose / Segment heads of the stock yolo11n-pose / yolo11n-seg graphs through their
+    drop-in predictors -- YOLO(ckpt).predict(list of n host frames, predictor=B200PosePredictor | B200SegmentationPredictor)
+    incl. Results (keypoints / masks stay on the GPU), wall clock, mean of 3 calls after the call that builds the engine --
+    plus device-timed stages on the predictor's own engine (CUDA events) and the reference's own CPU predictor on 8 frames.
+    The synthetic checkpoint fills max_det (300 rows per image): the worst case for the mask kernel, which writes
+    rows x 640 x 640 fp32 and is measured against the HBM copy peak."""
+    model, task = {"pose": ("yolo11n-pose", "pose"), "segment": ("yolo11n-seg", "segment")}[head]
+    yolo = reference_yolo(model, 640, task)
+    if yolo is None:
+        return {"unavailable": "reference package (baseline/_ref) not importable"}
+    from bs_yolo_b200 import ops
+    from bs_yolo_b200 import predictor as P
+    cls = P.B200PosePredictor if head == "pose" else P.B200SegmentationPredictor
+    frames = list(synth_frames(n, 640, 777))
+    kw = dict(device=ctx.local, imgsz=640, conf=0.25, iou=0.7, max_det=300, verbose=False)
+    res = yolo.predict(frames, predictor=cls, **kw)  # builds, autotunes and captures the (n, 640, 640) engine
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        res = yolo.predict(frames, **kw)
+    torch.cuda.synchronize()
+    e2e = 3 * n / (time.perf_counter() - t0)
+    assert len(res) == n and type(yolo.predictor).__name__ == cls.__name__
+    eng = next(iter(yolo.predictor.model._engines.values()))
+
+    def dev_ms(fn, iters=10, warm=2):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    rec = {"metric": metric_name(640), "value": None, "unit": UNIT, "frames_per_call": n, "model": model,
+           "api": f"YOLO(ckpt).predict(list_of_ndarrays, predictor={cls.__name__}, device=0) incl. Results construction",
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * 640 * 640 * 3, "d2h_bytes_per_step": n * 4},
+           "detections_per_image": float(np.mean([len(r.boxes) for r in res])), "plan_launches": eng.n_launches}
+    del res
+    with torch.cuda.device(eng.device):
+        stages = {"network_graph_ms": dev_ms(eng.forward)}
+        dets, counts, kept = eng.nms(0.25, 0.7, 300, return_anchors=True)
+        nl = counts.tolist()
+        stages["nms_ms"] = dev_ms(lambda: eng.nms(0.25, 0.7, 300, return_anchors=True))
+        if head == "pose":
+            geom = ops.coords_geometry((640, 640), [(640, 640)] * n, dets.device)
+            stages["keypoints_ms"] = dev_ms(lambda: eng.keypoints(kept, counts, geom=geom))
+        else:
+            coeffs = eng.mask_coeffs(kept, counts)
+            stages["coeff_gather_ms"] = dev_ms(lambda: eng.mask_coeffs(kept, counts))
+            ms = dev_ms(lambda: ops.process_mask_batched(eng.protos, coeffs, dets, nl, (640, 640)))
+            stages["process_mask_ms"] = ms
+            nbytes = int(sum(nl)) * 640 * 640 * 4
+            rec["roofline"] = {"bound": "hbm", "kernel": "process_mask_kernel", "achieved": nbytes / ms / 1e6, "peak": ctx.hbm,
+                               "unit": "GB/s", "frac": nbytes / ms / 1e6 / ctx.hbm, "peak_source": ctx.peak_src, "traffic": None,
+                               "what": f"{int(sum(nl))} masks of 640x640 fp32 written per launch (algorithmic bytes = the output)"}
+    rec["stages"] = stages
+    rec["value"] = n / sum(stages.values()) * 1e3  # device-timed: network graph + NMS + head post-process, frames resident
+
+    def cpu_ref():  # deferred to the end of the bench: the reference's CPU runs slow later engine builds in this process
+        torch.set_num_threads(os.cpu_count() or 1)
+        ykw = dict(device="cpu", imgsz=640, conf=0.25, iou=0.7, max_det=300, verbose=False)
+        ref = reference_yolo(model, 640, task)
+        ref.predict(frames[:1], **ykw)
+        t0 = time.perf_counter()
+        ref.predict(frames[:8], **ykw)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 8 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                               "sample": f"8 frames, one predict() call of the reference's {type(ref.predictor).__name__} (device='cpu')"}
+
+    _DEFERRED.append(cpu_ref)
+    return rec
+
+
+_DEFERRED: list = []
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -713,7 +798,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch of the headline workload (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no `workloads` sub-records)")
-    ap.add_argument("--extras", default="bsyolo_n,yolo11x,sahi,dropin,ingest,val", help="comma list of sub-records to run")
+    ap.add_argument("--extras", default="bsyolo_n,yolo11x,sahi,dropin,ingest,pose,segment,val", help="comma list of sub-records to run")
     ap.add_argument("--layers-out", default="", help="write the per-op timing table of the headline workload to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -748,6 +833,8 @@ def main():
                     r = run_val_workload(ctx) if ctx.world == 1 else None
                 elif w == "ingest":
                     r = run_ingest_workload(ctx) if ctx.world == 1 else None
+                elif w in ("pose", "segment"):
+                    r = run_head_workload(ctx, w) if ctx.world == 1 else None
                 else:
                     continue
             except Exception as e:  # noqa: BLE001 -- a failing sub-record must not take the headline down
@@ -759,6 +846,11 @@ def main():
                 subs[w] = r
     if ctx.rank == 0:
         line["clocks"] = sampler.stop()
+        for fn in _DEFERRED:  # CPU reference legs of the pose / segment sub-records (after every GPU workload and the clock window)
+            try:
+                fn()
+            except Exception as e:  # noqa: BLE001
+                print(f"deferred cpu baseline failed: {type(e).__name__}: {e}", file=sys.stderr)
         if subs:
             line["workloads"] = subs
         emit(line)
