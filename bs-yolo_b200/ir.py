@@ -59,6 +59,22 @@ def detect_node(ir: Node) -> Node:
     return ir["layers"][-1]["module"]
 
 
+def head_kind(ir: Node) -> str:
+    """"detect", "pose" or "segment": which Detect-derived head the graph ends in (head.py:21, 175, 230)."""
+    return detect_node(ir).get("head", "detect")
+
+
+def require_head(ir: Node, want: str | None, who: str) -> None:
+    """A predictor / validator class post-processes ONE head kind (the reference picks the class by task,
+    models/yolo/model.py task_map); pairing it with another head would silently drop the keypoints / masks (or look for
+    ones that do not exist), so the mismatch raises and names the class to use."""
+    kind = head_kind(ir)
+    if want is not None and kind != want:
+        use = {"detect": "B200DetectionPredictor", "pose": "B200PosePredictor", "segment": "B200SegmentationPredictor"}[kind]
+        raise NotImplementedError(f"{who} post-processes a {want} head, but the model ends in a {kind} head: use "
+                                  f"bs_yolo_b200.predictor.{use}" + (" (no B200 validator exists for this head)" if "alidator" in who and kind != "detect" else ""))
+
+
 def calibrate_cls_bias(ir: Node, head_logits: list[torch.Tensor], frac: float = 0.06, conf: float = 0.25) -> None:
     """Shift the class-branch bias of each level so that ``frac`` of its anchors clear ``conf``.
 

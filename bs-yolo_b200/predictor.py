@@ -157,12 +157,13 @@ class B200Backend:
     pt, triton, fp16, imx, dynamic, jit, nn_module = True, False, False, False, False, False, True
     max_engines = 4  # plans kept per backend (one per (batch, H, W)); the validator raises it for rect batches
 
-    def __init__(self, det_model, device: torch.device, use_graph: bool = True):
+    def __init__(self, det_model, device: torch.device, use_graph: bool = True, head: str | None = None, who: str = "B200Backend"):
         if device.type != "cuda":
             raise A.B2YError(f"B200DetectionPredictor needs a CUDA device, got '{device}' (no CPU fallback on this path)")
         self.model = det_model  # kept for attribute access by callers (e.g. tracker callbacks read predictor.model.model)
         self.device = device
         self.ir = _ir.ir_from_model(det_model)
+        _ir.require_head(self.ir, head, who)  # e.g. a pose checkpoint behind B200DetectionPredictor: raise, do not drop keypoints
         self.names = dict(getattr(det_model, "names", None) or self.ir["names"])
         self.stride = max(int(max(float(s) for s in det_model.stride)), 32)
         self.nc = self.ir["nc"]
@@ -247,6 +248,7 @@ def _build_class():
 
         max_chunk = int(os.environ.get("B2Y_PREDICT_BATCH", "64"))  # frames per pipelined chunk of a same-shape list
         pipelined = True  # same-shape uint8 lists stream through DetectPipeline (boxes only); False: single-engine route
+        head_kind = "detect"  # the head this class post-processes (ir.require_head)
 
         def setup_model(self, model, verbose=True):
             if self.args.half:
@@ -262,7 +264,7 @@ def _build_class():
                 from ultralytics.nn.tasks import attempt_load_weights  # the reference's own loader, unchanged
                 model = attempt_load_weights(str(model), device="cpu", inplace=True, fuse=False)
             device = select_device(self.args.device, verbose=verbose)
-            self.model = B200Backend(model, torch.device(device))
+            self.model = B200Backend(model, torch.device(device), head=self.head_kind, who=type(self).__name__)
             self.device = self.model.device
             self.args.half = False
 
@@ -375,6 +377,7 @@ def _build_class():
         the GPU.  Batches take the single-engine route (the chunked pipeline carries boxes only)."""
 
         pipelined = False
+        head_kind = "pose"
 
         def __init__(self, *args, **kwargs):
             super().__init__(*args, **kwargs)
@@ -409,6 +412,7 @@ def _build_class():
         of a per-image loop.  ``Results.masks`` stay on the GPU.  retina_masks=True (process_mask_native) is not built."""
 
         pipelined = False
+        head_kind = "segment"
 
         def __init__(self, *args, **kwargs):
             super().__init__(*args, **kwargs)

@@ -48,7 +48,7 @@ def _backend_for(model, device):
     hit = _BACKENDS.get(model)
     if hit is not None and hit[0] == device and hit[1] == fp:
         return hit[2]
-    backend = B200Backend(model, device)
+    backend = B200Backend(model, device, head="detect", who="B200DetectionValidator")
     backend.max_engines = 8  # rect batches: one plan per (batch, H, W); keep more of them than the predictor does
     _BACKENDS[model] = (device, fp, backend)
     return backend

@@ -200,3 +200,18 @@ def test_pose_dropin_empty_and_ragged(tmp_path):
     res = yolo.predict(imgs, device=0, imgsz=160, conf=0.25, verbose=False)
     assert type(yolo.predictor).__name__ == "B200PosePredictor"
     assert all(r.keypoints.data.shape[0] == r.boxes.data.shape[0] for r in res) and sum(len(r.boxes) for r in res) > 0
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference package not importable")
+def test_head_and_predictor_class_must_match(tmp_path):
+    """A pose checkpoint behind the detection predictor would silently drop the keypoints (the reference's own
+    DetectionPredictor would read the keypoint rows as classes): it raises and names the class to use."""
+    ref_import.import_reference()
+    from ultralytics import YOLO
+    from bs_yolo_b200.predictor import B200DetectionPredictor, B200SegmentationPredictor
+
+    path = _pose_checkpoint("yolo11n-pose", 160, tmp_path)
+    img = [np.zeros((160, 160, 3), np.uint8)]
+    for cls in (B200DetectionPredictor, B200SegmentationPredictor):
+        with pytest.raises(NotImplementedError, match="B200PosePredictor"):
+            YOLO(path).predict(img, predictor=cls, device=0, imgsz=160, verbose=False)

@@ -131,3 +131,15 @@ def test_coords_geometry_is_not_rounded():
     g2 = coords_geometry((160, 160), [(200, 151)], "cpu")[0].tolist()  # pad 19.6: scale_boxes rounds (19.6 - 0.1) to an integer, coords keep 19.6
     b2 = scale_geometry((160, 160), [(200, 151)], "cpu")[0].tolist()
     assert g2[1] == pytest.approx(19.6) and b2[1] == float(round(b2[1])) and b2[1] != g2[1]
+
+
+def test_head_kind_guard():
+    """A predictor class post-processes one head kind; a mismatch raises and names the class to use."""
+    for model, kind in (("yolo11n", "detect"), ("yolo11n-pose", "pose"), ("yolo11n-seg", "segment")):
+        g = dict(arch.build_spec(model))
+        assert ir.head_kind(g) == kind
+        ir.require_head(g, kind, "X")
+        ir.require_head(g, None, "X")
+        for other in {"detect", "pose", "segment"} - {kind}:
+            with pytest.raises(NotImplementedError, match=kind):
+                ir.require_head(g, other, "B200DetectionValidator" if other == "detect" else "X")
