@@ -763,8 +763,15 @@ def run_head_workload(ctx: Ctx, head: str, n: int = 32):
             ms = dev_ms(lambda: ops.process_mask_batched(eng.protos, coeffs, dets, nl, (640, 640)))
             stages["process_mask_ms"] = ms
             nbytes = int(sum(nl)) * 640 * 640 * 4
+            traffic = None  # DRAM bytes of this launch, scaled from the committed ncu capture (bytes per mask x masks)
+            try:
+                ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("process_mask")
+                if ent:
+                    traffic = ent["dram_bytes_per_mask"] * int(sum(nl))
+            except (OSError, ValueError, KeyError):
+                pass
             rec["roofline"] = {"bound": "hbm", "kernel": "process_mask_kernel", "achieved": nbytes / ms / 1e6, "peak": ctx.hbm,
-                               "unit": "GB/s", "frac": nbytes / ms / 1e6 / ctx.hbm, "peak_source": ctx.peak_src, "traffic": None,
+                               "unit": "GB/s", "frac": nbytes / ms / 1e6 / ctx.hbm, "peak_source": ctx.peak_src, "traffic": traffic,
                                "what": f"{int(sum(nl))} masks of 640x640 fp32 written per launch (algorithmic bytes = the output)"}
     rec["stages"] = stages
     rec["value"] = n / sum(stages.values()) * 1e3  # device-timed: network graph + NMS + head post-process, frames resident
