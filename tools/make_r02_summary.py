@@ -54,7 +54,10 @@ def f4_section():
     md += ["", "The synthetic checkpoints fill `max_det`: 300 detections per image, i.e. 19,200 640x640 fp32 masks per 64-frame batch -- the "
            "worst case for the mask kernel and for `Results` construction (real scenes keep tens of rows).  First version of the mask "
            "kernel (scalar 4-byte stores, per-pixel index arithmetic): 13.24 ms = 0.36 of HBM; with one column quad per thread, 16-byte "
-           "stores and fixed x4 weights: 5.15 ms = 0.93.  GPU tests: `profiles/r02_pose_gpu_tests.log`, `profiles/r02_seg_gpu_tests.log`.", ""]
+           "stores and fixed x4 weights: 5.15 ms = 0.93.  GPU tests: `profiles/r02_pose_gpu_tests.log`, `profiles/r02_seg_gpu_tests.log`.", "",
+           "ncu on the two stand-alone f4 kernels (`tools/ncu_f4.py`, `profiles/r02_ncu_f4.csv`; 2400 masks per launch, cold and serialised): "
+           "`process_mask_kernel` 746 us, DRAM write 3.868 GB + read 0.018 GB against 3.932 GB algorithmic (the output) -- traffic = 0.99 x "
+           "algorithmic, no re-reads (prototypes and coefficients come from L2); `gather_extras_kernel` 6.3 us, 0.34 MB read.", ""]
     return md
 
 
