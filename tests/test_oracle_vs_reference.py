@@ -152,3 +152,57 @@ def test_prefetch_image_loader_matches_reference_loader(tmp_path):
 
     with pytest.raises(ValueError):
         PrefetchImageLoader(VideoLoader())
+
+
+# ---- Pose / Segment heads ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["yolo11n-pose", "yolo11n-seg"])
+def test_head_spec_and_forward_match_live_reference(model):
+    spec = arch.build_spec(model)
+    sd = arch.synth_state_dict(spec, 5)
+    m = ref_import.reference_model(model, sd)  # PoseModel / SegmentationModel, strict load
+    assert ir.strip_tensors(ir.spec_from_model(m)) == ir.strip_tensors(spec)
+    g = ir.ir_from_model(m)
+    x = torch.rand(1, 3, 96, 64)
+    with torch.no_grad():
+        yr, extra_r = m(x)
+    y, extra = oracle_net.forward(g, x)
+    assert y.shape == yr.shape and float((y[:, :4] - yr[:, :4]).abs().max()) < 2e-3
+    assert float((y[:, 4:84] - yr[:, 4:84]).abs().max()) < 1e-5
+    for a, b in zip(extra[1:], extra_r[1:]):  # raw keypoint maps | (mask coefficients, prototypes)
+        assert a.shape == b.shape and float((a - b).norm() / b.norm()) < 1e-5
+
+
+def test_scale_coords_and_process_mask_match_reference_bit_for_bit():
+    ref_import.import_reference()
+    from ultralytics.utils import ops
+
+    rng = np.random.default_rng(1)
+    k = (rng.random((40, 17, 3)) * 700 - 30).astype(np.float32)
+    for s1, s0 in [((640, 640), (640, 640)), ((384, 640), (1080, 1920)), ((160, 128), (481, 321)), ((160, 160), (200, 151))]:
+        ref = ops.scale_coords(s1, torch.from_numpy(k.copy()), s0).numpy()
+        assert oracle_post.scale_coords(s1, k, s0).tobytes() == ref.tobytes()
+    protos = rng.standard_normal((32, 40, 32)).astype(np.float32)
+    coeffs = rng.standard_normal((9, 32)).astype(np.float32)
+    c, wh = rng.uniform(0, [128, 160], (9, 2)), rng.uniform(8, [128, 160], (9, 2))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    ref = ops.process_mask(torch.from_numpy(protos), torch.from_numpy(coeffs), torch.from_numpy(boxes.copy()), (160, 128), upsample=True)
+    assert np.array_equal(oracle_post.process_mask(protos, coeffs, boxes, (160, 128)), ref.numpy())
+
+
+def test_head_predictor_classes_plug_in_and_refuse_cpu(tmp_path):
+    """B200PosePredictor / B200SegmentationPredictor derive from the reference's DetectionPredictor, set the task the way
+    PosePredictor / SegmentationPredictor do, and raise without a CUDA device instead of falling back."""
+    ref_import.import_reference()
+    from ultralytics.models.yolo.detect.predict import DetectionPredictor
+
+    from bs_yolo_b200 import _cabi as A
+    from bs_yolo_b200.predictor import B200PosePredictor, B200SegmentationPredictor
+
+    for cls, task, model in ((B200PosePredictor, "pose", "yolo11n-pose"), (B200SegmentationPredictor, "segment", "yolo11n-seg")):
+        assert issubclass(cls, DetectionPredictor) and cls.head_kind == task and cls.pipelined is False
+        p = cls(overrides=dict(device="cpu", save=False, verbose=False))
+        assert p.args.task == task
+        spec = arch.build_spec(model)
+        m = ref_import.reference_model(model, arch.synth_state_dict(spec, 0))
+        with pytest.raises(A.B2YError, match="no CPU fallback"):
+            p.setup_model(m, verbose=False)
