@@ -143,3 +143,19 @@ def test_head_kind_guard():
         for other in {"detect", "pose", "segment"} - {kind}:
             with pytest.raises(NotImplementedError, match=kind):
                 ir.require_head(g, other, "B200DetectionValidator" if other == "detect" else "X")
+
+
+def test_single_class_pose_checkpoint_lowers(monkeypatch):
+    """Real pose checkpoints are single-class (nc = 1, kpt_shape [17, 3]): the class branch ends in a 64 -> 1 conv and y
+    is (B, 5, A).  Lowering and emulation against the oracle (the GPU suite covers nc = 80 / 12 / 100)."""
+    spec = arch.build_spec("yolo11n-pose", nc=1)
+    g = ir.build_ir(spec, arch.synth_state_dict(spec, 2))
+    plan = Plan(g, 64, 64, keep_fp32=True)
+    assert plan.nc == 1 and plan.bufs[plan.y_buf].H == 5 and plan.ne == 51
+    x = torch.from_numpy(np.random.default_rng(3).random((1, 3, 64, 64), dtype=np.float32))
+    emu = PlanEmulator(plan, 1)
+    emu.set_input(x)
+    emu.run()
+    y, (_, kpt) = oracle_net.forward(g, x)
+    assert y.shape[1] == 5 + 51
+    assert float((emu.y() - y[:, :5]).abs().max()) < 1e-3 and float((emu.extras() - kpt).norm() / kpt.norm()) < 2e-5
