@@ -774,6 +774,10 @@ def run_head_workload(ctx: Ctx, head: str, n: int = 32):
                                "unit": "GB/s", "frac": nbytes / ms / 1e6 / ctx.hbm, "peak_source": ctx.peak_src, "traffic": traffic,
                                "what": f"{int(sum(nl))} masks of 640x640 fp32 written per launch (algorithmic bytes = the output)"}
     rec["stages"] = stages
+    # per-layer roofline of the lowered network incl. the head's extra branches (same definition as the headline's)
+    tf_burst = float(ctx.peaks.get("bf16_tflops", 1590.0))
+    floor_ms = sum(max(eng.plan.op_bytes(o, n) / (ctx.hbm * 1e9), o.flops * n / (tf_burst * 1e12)) for o in eng.plan.ops) * 1e3
+    rec["network_floor_ms"], rec["network_roofline_frac"] = floor_ms, floor_ms / stages["network_graph_ms"]
     rec["value"] = n / sum(stages.values()) * 1e3  # device-timed: network graph + NMS + head post-process, frames resident
 
     def cpu_ref():  # deferred to the end of the bench: the reference's CPU runs slow later engine builds in this process
